@@ -1,0 +1,103 @@
+"""Differential pinning of the oracle (oracle/indel_oracle.c) against the reference's own
+object code (oracle/_ref/*.so, built from /root/reference by oracle/Makefile).  Skipped where
+the reference objects are absent (they are git-ignored; the GPU box receives the prebuilt files)."""
+import pytest
+
+from tests.util import make_rng, mutate, rseq, split_read_case
+
+
+@pytest.fixture(scope="module")
+def O(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    return oracle
+
+
+def test_local_align_small(O):
+    rng = make_rng(1)
+    p = O.default_params()
+    n = pos = 0
+    for _ in range(6000):
+        alpha = rng.choice(["AC", "ACGT", "ACGTN", "A"])
+        N = rng.randrange(8, 120)
+        ref = rseq(rng, N, alpha)
+        M = rng.randrange(1, 60)
+        if rng.random() < 0.7 and N > M + 2:
+            off = rng.randrange(0, N - M)
+            read = mutate(rng, ref[off:off + M], alpha)
+            d = off + rng.randrange(-3, 4)
+        else:
+            read = rseq(rng, M, alpha)
+            d = rng.randrange(-M + 1, N)
+        M = len(read)
+        w = rng.choice([1, 1, 2, 3, 5, 8, 13, 33])
+        low = d - w // 2
+        up = low + w - 1
+        if max(-M, low) > min(N, up):
+            continue
+        a = O.local_align(p, read, ref, low, up)
+        b = O.ref_local_align(read, ref, low, up)
+        assert a == b, (read, ref, low, up)
+        n += 1
+        pos += a[0] > 0
+    assert pos > n // 2
+
+
+def test_global_align_dc_script(O):
+    """ALIGN incl. the divide-and-conquer traceback: scores AND scripts (tie-heavy alphabets)."""
+    rng = make_rng(7)
+    p = O.default_params()
+    for _ in range(4000):
+        alpha = rng.choice(["AC", "ACGT", "ACGTN", "AAC"])
+        M = rng.randrange(1, 150)
+        A = rseq(rng, M, alpha)
+        B = mutate(rng, A, alpha, sub=rng.choice([0, 0.02, 0.2]), nindel=rng.randrange(0, 4), maxindel=30)
+        w = rng.choice([1, 2, 3, 4, 5, 9, 17, 33, 65, 129, 200])
+        low = -rng.randrange(0, w)
+        up = low + w - 1
+        assert O.global_align(p, A, B, low, up) == O.ref_ALIGN(A, B, low, up), (A, B, low, up)
+
+
+@pytest.mark.parametrize("k,g", [(6, 0), (6, 4), (4, 0), (8, 3), (2, 0), (11, 1)])
+def test_find_best_band(O, k, g):
+    rng = make_rng(100 + k * 16 + g)
+    O.ref_set_params(k, g, 1000, 10)
+    p = O.default_params(k, g)
+    for _ in range(700):
+        alpha = rng.choice(["AC", "ACGT", "ACGTN"])
+        L = rng.randrange(60, 600)
+        ref = rseq(rng, L, alpha)
+        zs1 = rng.randrange(0, 20)
+        e1 = rng.randrange(zs1 + 30, L)
+        M = rng.randrange(1, 50) if rng.random() < 0.1 else rng.randrange(10, 120)
+        if rng.random() < 0.7 and e1 - zs1 > M + 2:
+            off = rng.randrange(zs1, e1 - M)
+            read = mutate(rng, ref[off:off + M], alpha)
+        else:
+            read = rseq(rng, M, alpha)
+        rd = rseq(rng, 5, alpha) + read + rseq(rng, 5, alpha)
+        zs2 = rng.randrange(0, 6)
+        e2 = len(rd) - rng.randrange(0, 6)
+        if (e1 - zs1) + (e2 - zs2) - 2 * (k - 1) <= g:
+            continue
+        anchor = rng.randrange(0, L)
+        assert (O.find_best_band(p, ref, zs1, e1, anchor, rd, zs2, e2)
+                == O.ref_find_best_band(ref, zs1, e1, anchor, rd, zs2, e2))
+    O.ref_set_params()
+
+
+@pytest.mark.parametrize("k,g", [(6, 0), (6, 3), (8, 0), (5, 8)])
+def test_realign_two_rounds(O, k, g):
+    """attempt_diagonal_alignments + update_readsegs: final segment lists and evidence counts."""
+    rng = make_rng(11 + k + 31 * g)
+    O.ref_set_params(k, g, 1000, 10)
+    p = O.default_params(k, g)
+    seen = set()
+    for _ in range(500):
+        ref, position, range1, read = split_read_case(rng)
+        a = O.realign_read(p, ref, position, range1, read)
+        b = O.ref_realign(ref, position, range1, read)
+        assert (a.segments(), a.nevidence) == b, (k, g, position, range1, read)
+        seen.add(a.status)
+    assert {1, 2, 3, 4, 5, 6} <= seen
+    O.ref_set_params()
