@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""Benchmark of the split-read realignment hot path (BASELINE.json: reads/sec and GCUPS).
+
+A step = one pass of the batched attempt_pe_alignment over one batch of synthetic candidate reads
+of the cfg3 shape (64 Mb contig, planted 1-50 bp indels, 2x150 bp pairs; SURVEY.md 8d "D2").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, libindelgpu.so)
+  python bench.py --impl reference ...                            the reference's own CPU code
+  python bench.py --workload band --band 33                       banded-DP micro-bench (D1): GCUPS
+
+Under torchrun (N > 1) every rank realigns its own region's candidates (weak scaling, no
+data-path collective); NCCL carries only the tiny per-read-group insert-range all-reduce.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "split_read_realign_reads_per_sec"
+UNIT = "reads/s"
+INT_OPS_PER_CELL = 10          # fixed constant of the INT32 roofline
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "band"])
+    ap.add_argument("--reads", type=int, default=1 << 20, help="candidate reads per GPU per step")
+    ap.add_argument("--ref-mb", type=int, default=64, help="contig size in Mb")
+    ap.add_argument("--band", type=int, default=33)
+    ap.add_argument("--numgaps", type=int, default=0)
+    ap.add_argument("--tasks", type=int, default=1 << 17, help="alignments for --workload band")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads of the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            t = [x.strip() for x in ln.split(",")]
+            if len(t) < 9:
+                continue
+            try:
+                sm.append(float(t[1])); mx.append(float(t[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, t[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- CPU arms
+_CPU_SHARED = {}        # inherited by the forked workers (no pickling of the 64 MB contig)
+
+
+def cpu_worker(args):
+    """one process = one core: the reference's (or the port's) loop over a slice of the sample"""
+    kind, lo, hi, as_shipped = args
+    from oracle import oracle as O
+    ref_bytes, w = _CPU_SHARED["ref"], _CPU_SHARED["w"]
+    M = w["read_len"]
+    reflength = len(ref_bytes)
+    reads, off = w["read_bases"][lo * M:hi * M], w["read_off"][lo:hi + 1]
+    pos, rng = w["position"][lo:hi], w["range1"][lo:hi]
+    n = len(pos)
+    reads = np.ascontiguousarray(reads)
+    off = np.ascontiguousarray(off - off[0], dtype=np.int64)
+    pos = np.ascontiguousarray(pos, dtype=np.int32)
+    rng = np.ascontiguousarray(rng, dtype=np.int32)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        L = O.ref_align()
+        O.ref_set_params()
+        f = L.refshim_realign_batch
+        f.restype = C.c_long
+        f(C.c_char_p(ref_bytes), reflength, n, reads.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+          pos.ctypes.data_as(C.c_void_p), rng.ctypes.data_as(C.c_void_p), int(as_shipped), None)
+    else:
+        L = O.lib()
+        p = O.default_params()
+        f = L.orc_realign_batch
+        f.restype = C.c_long
+        f(C.byref(p), C.c_char_p(ref_bytes), reflength, n, reads.ctypes.data_as(C.c_void_p),
+          off.ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p), rng.ctypes.data_as(C.c_void_p), None)
+    return time.perf_counter() - t0
+
+
+def cpu_arm(ref, w, nsample, cores, as_shipped=False):
+    """reads/s of the CPU implementation on the first `nsample` reads, `cores` processes."""
+    import multiprocessing as mp
+    from oracle import oracle as O
+    kind = "reference" if O.have_ref() else "port"
+    if kind == "port":
+        O.lib()
+    nsample = min(nsample, len(w["position"]))
+    if _CPU_SHARED.get("refid") != id(ref):
+        _CPU_SHARED.update(ref=ref.tobytes(), refid=id(ref))
+    _CPU_SHARED["w"] = w
+    per = (nsample + cores - 1) // cores
+    jobs = []
+    for c in range(cores):
+        a, b = c * per, min(nsample, (c + 1) * per)
+        if a >= b:
+            break
+        jobs.append((kind, a, b, as_shipped))
+    t0 = time.perf_counter()
+    if len(jobs) == 1:
+        cpu_worker(jobs[0])
+    else:
+        with mp.get_context("fork").Pool(len(jobs)) as pool:
+            pool.map(cpu_worker, jobs)
+    dt = time.perf_counter() - t0
+    return nsample / dt, kind, len(jobs), dt
+
+
+def calibrate_cpu_sample(ref, w, cores, target_s=12.0):
+    """size the sample for ~target_s seconds of wall time on `cores` cores"""
+    probe = 2000
+    rate, _k, _c, _dt = cpu_arm(ref, w, probe, 1)
+    return int(max(probe, min(len(w["position"]), rate * cores * target_s)))
+
+
+# --------------------------------------------------------------------------- main arms
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    from indelminer_b200 import synth
+    ref = synth.make_reference(a.ref_mb * 1_000_000, seed=1)
+    w = synth.make_candidates(ref, a.reads, seed=20261018)
+    cores = os.cpu_count() or 1
+    nsample = a.cpu_sample or calibrate_cpu_sample(ref, w, cores, target_s=8.0)
+    vals = []
+    for s in range(a.warmup + a.steps):
+        rate, kind, used, dt = cpu_arm(ref, w, nsample, cores)
+        if s >= a.warmup:
+            vals.append((rate, dt))
+    rate = float(np.mean([v[0] for v in vals]))
+    ms = float(np.mean([v[1] for v in vals])) * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "cfg3: 64 Mb synthetic contig, planted 1-50 bp indels, 2x150 bp candidates, -g 0 -k 6",
+                   "reads_per_step": nsample, "ref_mb": a.ref_mb},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": used, "kind": kind,
+                         "sample": f"first {nsample} of {a.reads} candidate reads per step, function level "
+                                   "(attempt_diagonal_alignments with windows precomputed; the as-shipped per-read "
+                                   "strlen(contig) of alignment.c:771 is excluded), one process per core"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(a, rank, world, local_rank):
+    import torch
+    import indelminer_b200
+    from indelminer_b200 import lib as _lib, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peak, peak_src = peaks()
+    L = _lib.load()
+    R = indelminer_b200.Realigner(device=local_rank, numgaps=a.numgaps)
+    ref = synth.make_reference(a.ref_mb * 1_000_000, seed=1)
+    R.set_reference([ref.tobytes()])
+
+    if a.workload == "band":
+        return run_band(a, R, L, torch, dev, peak, peak_src)
+
+    # region sharding: rank r owns the r-th slice of the contig (weak scaling: same count per GPU)
+    Lr = len(ref)
+    region = (rank * Lr // world, (rank + 1) * Lr // world)
+    w = synth.make_candidates(ref, a.reads, seed=20261018 + rank, region=region)
+    n, M = a.reads, w["read_len"]
+
+    # the only collective on the path: per-read-group max proper insert (range[1]); a few bytes
+    rg = torch.tensor([int(w["range1"].max())], device=dev, dtype=torch.int32)
+    if dist is not None:
+        dist.all_reduce(rg, op=dist.ReduceOp.MAX)
+    max_range = int(rg.item())
+
+    # ---- device-resident inputs (value) -------------------------------------------------
+    d_reads = torch.from_numpy(w["read_bases"]).to(dev)
+    d_off = torch.from_numpy(w["read_off"]).to(dev)
+    d_tid = torch.from_numpy(w["tid"]).to(dev)
+    d_pos = torch.from_numpy(w["position"]).to(dev)
+    d_rng = torch.from_numpy(w["range1"]).to(dev)
+    cap = int(L.indelgpu_seg_bound(n, n * M))
+    d_status = torch.empty(n, dtype=torch.int32, device=dev)
+    d_nseg = torch.empty(n, dtype=torch.int32, device=dev)
+    d_rstart = torch.empty(n, dtype=torch.int32, device=dev)
+    d_segoff = torch.empty(n, dtype=torch.int64, device=dev)
+    d_segs = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_count = torch.zeros(1, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    b = _lib.Batch(n, d_reads.data_ptr(), d_off.data_ptr(), d_tid.data_ptr(), d_pos.data_ptr(), d_rng.data_ptr())
+    r = _lib.Result(d_status.data_ptr(), d_nseg.data_ptr(), d_rstart.data_ptr(), d_segoff.data_ptr(),
+                    d_segs.data_ptr(), cap, 0, None, None, None, 0)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        rc = L.indelgpu_realign_batch_device(R._ctx, C.byref(b), M, max_range, C.byref(r),
+                                             d_count.data_ptr(), C.c_void_p(stream.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(_lib.last_error())
+
+    for _ in range(a.warmup):
+        flush.fill_(1)
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = []
+    launches = 0
+    for _ in range(a.steps):
+        flush.fill_(1)                       # L2 flush between timed iterations, outside the event pair
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step_device()
+        e1.record(stream)
+        launches += L.indelgpu_last_launch_count(R._ctx)
+        evs.append((e0, e1))
+    barrier()
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    clocks = sampler.stop()
+    total_ms = float(sum(step_ms))
+    (cf, cr, cg), alg_bytes = R.last_counters()
+    nsplit = int((d_status == 6).sum().item())
+
+    # ---- end to end through the host API (pinned host buffers in, host results out) -----
+    def pinned(arr):
+        p = L.indelgpu_host_alloc(arr.nbytes)
+        out = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(arr.nbytes,)).view(arr.dtype).reshape(arr.shape)
+        out[...] = arr
+        return out
+
+    h = {k: pinned(w[k]) for k in ("read_bases", "read_off", "tid", "position", "range1")}
+    ho = {"status": pinned(np.zeros(n, np.int32)), "nseg": pinned(np.zeros(n, np.int32)),
+          "rstart": pinned(np.zeros(n, np.int32)), "seg_off": pinned(np.zeros(n, np.int64)),
+          "segs": pinned(np.zeros(cap, np.uint32))}
+    hb = _lib.Batch(n, h["read_bases"].ctypes.data, h["read_off"].ctypes.data, h["tid"].ctypes.data,
+                    h["position"].ctypes.data, h["range1"].ctypes.data)
+    hr = _lib.Result(ho["status"].ctypes.data, ho["nseg"].ctypes.data, ho["rstart"].ctypes.data,
+                     ho["seg_off"].ctypes.data, ho["segs"].ctypes.data, cap, 0, None, None, None, 0)
+
+    def step_host():
+        rc = L.indelgpu_realign_batch(R._ctx, C.byref(hb), C.byref(hr))
+        if rc != 0:
+            raise RuntimeError(_lib.last_error())
+
+    for _ in range(max(1, a.warmup)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    seg_words = int(hr.seg_count)
+    assert np.array_equal(ho["status"], d_status.cpu().numpy()), "host and device paths disagree"
+    h2d = int(w["read_bases"].nbytes + w["read_off"].nbytes + 12 * n)
+    d2h = int(20 * n + 4 * seg_words + 64)
+
+    # max over ranks, whole-job aggregate
+    t = torch.tensor([total_ms, e2e_s], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = float(t[0].item()), float(t[1].item())
+    ms_per_step = total_ms / a.steps
+    value = world * n * a.steps / (total_ms / 1e3)
+    e2e_value = world * n * a.steps / e2e_s
+    kernel_s = float(np.mean(step_ms)) / 1e3          # one launch per step: step time == kernel time
+    achieved = alg_bytes / kernel_s / 1e9
+    cells = cf + cr + cg
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "cfg3: 64 Mb synthetic contig, planted 1-50 bp indels, 2x150 bp candidates, -g %d -k 6" % a.numgaps,
+                   "reads_per_gpu_per_step": n, "ref_mb": a.ref_mb, "read_len": M, "max_range": max_range,
+                   "sharding": "contig region per rank, no data-path collective",
+                   "l2": "256 MB flush write between timed iterations (outside the event pairs)",
+                   "split_reads_per_step": nsplit},
+        "gcups": cells / kernel_s / 1e9,
+        "cells_per_step": {"forward": cf, "reverse": cr, "align": cg},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "realign_kernel<%s>" % ("true" if a.numgaps else "false"),
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_s * 1e3, "peak_source": peak_src},
+    }
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                line["roofline"]["traffic"] = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    if rank == 0 and world == 1 and not a.no_cpu:
+        cores = os.cpu_count() or 1
+        nsample = a.cpu_sample or calibrate_cpu_sample(ref, w, cores)
+        rate, kind, used, dt = cpu_arm(ref, w, nsample, cores)
+        shipped_n = 200
+        srate, _k, _u, _d = cpu_arm(ref, w, shipped_n, 1, as_shipped=True) if kind == "reference" else (None, 0, 0, 0)
+        line["cpu_baseline"] = {
+            "value": rate, "unit": UNIT, "cores": used, "kind": kind,
+            "sample": f"first {nsample} of {n} candidate reads ({dt:.1f} s), function level: "
+                      "attempt_diagonal_alignments with windows precomputed, one process per core",
+            "as_shipped_1core": srate,
+            "as_shipped_note": f"attempt_pe_alignment incl. its per-read strlen(contig) (alignment.c:771), {shipped_n} reads, 1 core",
+        }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_band(a, R, L, torch, dev, peak, peak_src):
+    """D1: banded local_align + ALIGN + fetch_cigar on independent tasks; GCUPS."""
+    from indelminer_b200 import synth
+    t = synth.make_band_tasks(a.tasks, a.band)
+    packed = (t["reads"], t["read_off"], t["wins"], t["win_off"])
+    for _ in range(a.warmup):
+        out = R.band_align_batch(None, None, t["low"], t["up"], packed=packed)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        out = R.band_align_batch(None, None, t["low"], t["up"], packed=packed)
+    dt = (time.perf_counter() - t0) / a.steps
+    cells = int(out["cells"].sum())
+    line = {"metric": "banded_dp_gcups", "value": cells / dt / 1e9, "unit": "GCUPS", "n_gpus": 1, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"D1 band sweep: {a.tasks} alignments, M=150, N=1410, band={a.band}", "timing": "host, incl. copies"},
+            "cells_per_step": {"forward": int(out["cells"][0]), "reverse": int(out["cells"][1]), "align": int(out["cells"][2])},
+            "int_ops_per_cell": INT_OPS_PER_CELL}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+    else:
+        run_ours(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

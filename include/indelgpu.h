@@ -1,0 +1,204 @@
+/* libindelgpu.so -- B200 (sm_100a) split-read realignment for indelMINER.
+ *
+ * Drop-in boundary for the hot path of ratan-lab/indelMINER:
+ *   attempt_pe_alignment        src/alignment.h:21-25   (src/alignment.c:764-799)
+ *     find_best_band            src/alignment.c:393-447 (static)
+ *     attempt_band_alignment    src/alignment.c:343-391 (static)
+ *       local_align             src/localalign.h:15-25
+ *         ALIGN                 src/globalalign.h:19-28
+ *       fetch_cigar             src/globalalign.h:39-48
+ *     update_readsegs           src/readaln.h:56-64     (segment list; materialised by the host)
+ *
+ * Plain C ABI: pointers and sizes only, no CUDA or torch types.  `stream` arguments are a
+ * cudaStream_t passed as void* (NULL = the context's own stream).  Buffers named h_* live in
+ * host memory (pinned memory from indelgpu_host_alloc makes the copies asynchronous), d_* in
+ * device memory of the context's GPU.
+ *
+ * Error convention.  The batched API returns 0 on success and a negative INDELGPU_E* code on
+ * failure, with text from indelgpu_last_error().  The reference-prototype entry points at the
+ * bottom keep the reference's own convention (message on stderr + exit(EXIT_FAILURE),
+ * src/asserts.h:12-19, src/errors.c:15-27): they have no way to return an error.
+ * There is NO CPU fallback anywhere in this library: without a usable GPU every call fails.
+ */
+#ifndef INDELGPU_H
+#define INDELGPU_H
+
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INDELGPU_VERSION 100
+
+enum {
+    INDELGPU_OK = 0,
+    INDELGPU_ECUDA = -1,      /* a CUDA runtime call failed                         */
+    INDELGPU_EINVAL = -2,     /* bad argument (NULL, negative size, unknown contig) */
+    INDELGPU_ELIMIT = -3,     /* a size exceeds what the kernels are built for      */
+    INDELGPU_ENOMEM = -4      /* host or device allocation failed                   */
+};
+
+/* The globals src/alignment.c reads (alignment.c:3-9; set by getopt in indelminer.c:948-1025)
+ * plus the compile-time scoring constants of src/localalign.c:10-13. */
+typedef struct indelgpu_params {
+    int32_t klength;      /* -k  default 6, 2..15          (indelminer.c:933,1028) */
+    int32_t numgaps;      /* -g  default 0                 (indelminer.c:934)      */
+    int32_t maxdelsize;   /* -s  default 1000              (indelminer.c:930)      */
+    int32_t ethreshold;   /* -n  default 10                (indelminer.c:940)      */
+    int32_t match;        /* +1                            (localalign.c:12)       */
+    int32_t mismatch;     /* -10                           (localalign.c:13)       */
+    int32_t gapopen;      /* 10                            (localalign.c:10)       */
+    int32_t gapextend;    /* 10                            (localalign.c:11)       */
+} indelgpu_params;
+
+typedef struct indelgpu_ctx indelgpu_ctx;
+
+int  indelgpu_version(void);
+void indelgpu_default_params(indelgpu_params* p);
+const char* indelgpu_last_error(void);
+
+/* One context per host worker thread / GPU (the reference's ALIGN keeps file-scope state,
+ * globalalign.c:19-37; this library keeps none). */
+indelgpu_ctx* indelgpu_create(int device, const indelgpu_params* p);
+void          indelgpu_destroy(indelgpu_ctx* ctx);
+int           indelgpu_device(const indelgpu_ctx* ctx);
+int           indelgpu_sm_count(const indelgpu_ctx* ctx);
+
+/* Pinned host memory for batch staging. */
+void* indelgpu_host_alloc(size_t bytes);
+void  indelgpu_host_free(void* p);
+
+/* Upload the reference contigs: replaces `char** sequences` of attempt_pe_alignment
+ * (built by read_reference, src/shared.c:46-82: one upper-cased string per contig).
+ * Kept resident in HBM as raw bytes (DP compares raw bytes, localalign.c:61-67) plus a
+ * 2-bit packed copy with every non-ACGT byte coded as A (base2bits, alignment.c:11-24). */
+int indelgpu_set_reference(indelgpu_ctx* ctx, int32_t ncontigs,
+                           const char* const* sequences, const int64_t* lengths);
+
+/* ---- batched attempt_pe_alignment ------------------------------------------------------
+ * Read i is h_read_bases[h_read_off[i] .. h_read_off[i+1]) (ASCII, already reverse-
+ * complemented by the caller as indelminer.c:404-409,479-484 does), realigned near
+ * (tid[i], position[i]) with range1[i] = range[1] of its read group (alignment.c:775,780).
+ *
+ * Per read the result is what update_readsegs (readaln.c:348-458) would have built:
+ *   status[i]   INDELGPU_ST_* (which exit of attempt_diagonal_alignments was taken)
+ *   nseg[i]     number of segments; 0 <=> the reference returns NULL
+ *   rstart[i]   refindx the first segment starts at (r1 or r3)
+ *   seg_off[i]  index of the read's first segment word in segs[]
+ *   segs[]      BAM-style words (len << 4 | op), ops = 7, X 8, I 1, D 2, S 4; walking them with
+ *               new_readseg's bookkeeping (readaln.c:24-99) from rstart gives every start/end.
+ * Evidence (alignment.c:449-476) = one record per I / D segment, built by the host.
+ */
+enum {
+    INDELGPU_ST_UNALIGNED = 0,   /* q1 == q2                               alignment.c:568        */
+    INDELGPU_ST_WHOLE     = 1,   /* whole read aligned in round 1          alignment.c:575        */
+    INDELGPU_ST_SHORT     = 2,   /* ethreshold guard                       :608,631,665,687       */
+    INDELGPU_ST_R2FAIL    = 3,   /* round 2 did not reach the read end     :623,645,679,701       */
+    INDELGPU_ST_NOBRANCH  = 4,   /* no round-2 branch applies              :651,657,707,712       */
+    INDELGPU_ST_NOCOMBINE = 5,   /* segments neither overlap nor abut      :750                   */
+    INDELGPU_ST_SPLIT     = 6,   /* two segments stitched                  :724-749               */
+    INDELGPU_ST_ASSERT    = 7    /* input on which the reference itself aborts (forceassert /
+                                    exit): bad contig, window asserts :548-553, numdiagonals <=
+                                    numgaps :405; nseg = 0 and the batch call returns ELIMIT     */
+};
+
+/* Optional per-read intermediates (kernel-level parity tests, debugging). */
+typedef struct indelgpu_detail {
+    int32_t low1, up1, r1, r2, q1, q2, n1, score1;   /* round 1: find_best_band + attempt_band_alignment */
+    int32_t low2, up2, r3, r4, q3, q4, n2, score2;   /* round 2 (n2 counts the added soft clip)          */
+    int32_t index;                                    /* junction passed to update_readsegs               */
+    int32_t cells_fwd, cells_rev, cells_glob;         /* DP cells swept (GCUPS numerator)      */
+} indelgpu_detail;
+
+typedef struct indelgpu_batch {
+    int32_t        n;             /* reads in the batch                      */
+    const uint8_t* read_bases;    /* concatenated read bytes                 */
+    const int64_t* read_off;      /* n + 1 offsets into read_bases           */
+    const int32_t* tid;           /* contig index of the mate                */
+    const int32_t* position;      /* 0-based mate position (core.mpos)       */
+    const int32_t* range1;        /* max proper insert of the read group     */
+} indelgpu_batch;
+
+typedef struct indelgpu_result {
+    int32_t*  status;             /* n                                       */
+    int32_t*  nseg;               /* n                                       */
+    int32_t*  rstart;             /* n                                       */
+    int64_t*  seg_off;            /* n                                       */
+    uint32_t* segs;               /* seg_capacity words                      */
+    int64_t   seg_capacity;       /* in: words available in segs             */
+    int64_t   seg_count;          /* out: words used                         */
+    indelgpu_detail* detail;      /* n, or NULL                              */
+    uint32_t* cigar1;             /* n * cigar_stride words, or NULL (round-1 CIGAR, debug) */
+    uint32_t* cigar2;             /* n * cigar_stride words, or NULL (round-2 CIGAR, debug) */
+    int32_t   cigar_stride;
+} indelgpu_result;
+
+/* worst-case number of segment words a batch can produce */
+int64_t indelgpu_seg_bound(int32_t n, int64_t total_read_bases);
+
+/* Host buffers in, host buffers out: H2D copies, kernels, D2H copies, synchronised on return. */
+int indelgpu_realign_batch(indelgpu_ctx* ctx, const indelgpu_batch* h_in, indelgpu_result* h_out);
+
+/* Device buffers in and out (all pointers in *d_in / *d_out are device pointers, the structs
+ * themselves live on the host).  d_out->seg_count is not filled; the count is left in the
+ * int64 device word *d_seg_count.  Asynchronous on `stream`. */
+int indelgpu_realign_batch_device(indelgpu_ctx* ctx, const indelgpu_batch* d_in,
+                                  int32_t max_read_len, int32_t max_range1,
+                                  indelgpu_result* d_out, int64_t* d_seg_count, void* stream);
+
+/* Counters of the last batch call; synchronises the context's stream.
+ *   out[0..2]  DP cells swept: forward, reverse, ALIGN (the GCUPS numerator)
+ *   out[3]     algorithmic bytes: sum over alignments of N + M + 4 * (6 + ncigar) */
+int indelgpu_last_counters(indelgpu_ctx* ctx, int64_t out[4]);
+
+/* number of kernels the last indelgpu_realign_batch[_device] call launched */
+int indelgpu_last_launch_count(const indelgpu_ctx* ctx);
+
+/* ---- batched kernel-level entry points (band sweeps, parity tests) ---------------------
+ * n independent (read, window) tasks: read j = h_reads[read_off[j]..read_off[j+1]),
+ * window j = h_refs[ref_off[j]..ref_off[j+1]).  Semantics of one task = find_best_band /
+ * local_align (+ALIGN) + fetch_cigar of the reference with absolute offsets zstart = 0. */
+int indelgpu_find_best_band_batch(indelgpu_ctx* ctx, int32_t n,
+                                  const uint8_t* h_reads, const int64_t* h_read_off,
+                                  const uint8_t* h_refs, const int64_t* h_ref_off,
+                                  const int32_t* h_anchor_rel,      /* anchor - zstart1 */
+                                  int32_t* h_low, int32_t* h_up);
+
+int indelgpu_band_align_batch(indelgpu_ctx* ctx, int32_t n,
+                              const uint8_t* h_reads, const int64_t* h_read_off,
+                              const uint8_t* h_refs, const int64_t* h_ref_off,
+                              const int32_t* h_low, const int32_t* h_up,
+                              int32_t* h_score,            /* n; 0 = no alignment                 */
+                              int32_t* h_ends,             /* 4n: si, sj, ei, ej (1-based incl.)  */
+                              int32_t* h_ncigar,           /* n                                   */
+                              uint32_t* h_cigar,           /* n * cigar_stride                    */
+                              int32_t cigar_stride,
+                              int32_t* h_script,           /* n * script_stride ints, or NULL     */
+                              int32_t script_stride,
+                              int64_t* h_cells);           /* 3: fwd, rev, glob totals, or NULL   */
+
+/* ---- reference-prototype entry points (1-element batches on the default context) --------
+ * Same names, arguments and results as the reference so the rest of the C caller links
+ * unchanged.  The default context is created on first use on device $INDELGPU_DEVICE (0). */
+
+/* src/localalign.h:15-25 */
+int local_align(char* seq1, const int seq1len, char* seq2, const int seq2len,
+                const int indx1, const int indx2,
+                int* const psi, int* const psj, int* const pei, int* const pej, int* const S);
+
+/* src/globalalign.h:19-28; A and B point one element BEFORE the first symbol */
+int ALIGN(char* A, char* B, int M, int N, int low, int up, int W[][128], int G, int H, int* S);
+
+/* src/globalalign.h:30-37 (debug pretty-printer; formats on the host) */
+int DISPLAY(FILE* F, char* A, char* B, int M, int N, int* S, int AP, int BP);
+
+/* src/globalalign.h:39-48; *pcigar is caller-allocated (>= 1 word) and may be realloc'ed */
+int fetch_cigar(char* A, char* B, int M, int N, int* S, int AP, int BP,
+                const int readlength, int* const pnumops, uint32_t** pcigar);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,389 @@
+// Banded affine local/global alignment for bands wider than one diagonal (-g N > 0):
+//   local_align   src/localalign.c:15-196   forward sweep (end point), reverse sweep (start point)
+//   ALIGN/align   src/globalalign.c:66-401  linear-space divide-and-conquer script
+//   fetch_cigar   src/globalalign.c:507-604
+// The script of ALIGN differs from a plain traceback whenever the plain traceback meets a tie
+// (SURVEY.md 0.5), so the divide-and-conquer procedure itself is reproduced: same sweep, same
+// crossing-point bookkeeping, same block order.  Recursion is an explicit frame stack; the work
+// arrays are shared by all levels exactly as in the reference (a child only touches rows below
+// the ones its parent still reads, globalalign.c:280).
+#pragma once
+
+#include "kernels.cuh"
+
+namespace indelgpu {
+
+// global-memory scratch, one slice per CTA (only warp 0 of a CTA aligns)
+struct BandScratch {
+    int* base;
+    long long stride;        // ints per CTA
+    int max_band;            // widest band the slice was sized for (after ALIGN's widening)
+    int max_rows;            // longest read
+};
+
+__host__ __device__ inline long long band_scratch_ints(int max_band, int max_rows)
+{
+    // cc dd cp dp | 2 x (hp dp) rolling rows | mp[3] fp | mt[3] ft | script | frames
+    return 8LL * (max_band + 4) + 8LL * (max_rows + 2) + (2LL * max_rows + max_band + 16) + 40 * 16;
+}
+
+__device__ __forceinline__ const int* band_script_ptr(const BandScratch& scr)
+{
+    return scr.base + (long long)blockIdx.x * scr.stride + 8 * (scr.max_band + 4) + 8 * (scr.max_rows + 2);
+}
+
+struct DcFrame {
+    int a, b;                // offsets of the "1-based" views into read / window
+    int M, N, low, up;
+    int tb, te;
+    int stage, k, l, kt, rmid, t2, t3, pad;
+};
+
+struct DcCtx {
+    const DevParams* P;
+    const uint8_t* A;        // read slice, 0-based
+    const uint8_t* B;        // window, 0-based
+    int *cc, *dd, *cp, *dp;
+    int *mp[3], *mt[3], *fp, *ft;
+    int* S; int ns; int last;
+    int cells;
+};
+
+__device__ __forceinline__ void put_del(DcCtx& x, int k)      // globalalign.c:40-46
+{
+    if (x.last < 0) { x.S[x.ns - 1] -= k; x.last = x.S[x.ns - 1]; }
+    else { x.S[x.ns++] = -k; x.last = -k; }
+}
+__device__ __forceinline__ void put_ins(DcCtx& x, int k)      // globalalign.c:48-54
+{
+    if (x.last > 0) { x.S[x.ns - 1] += k; x.last = x.S[x.ns - 1]; }
+    else { x.S[x.ns++] = k; x.last = k; }
+}
+__device__ __forceinline__ void put_rep(DcCtx& x) { x.S[x.ns++] = 0; x.last = 0; }
+
+// One sweep of align() (globalalign.c:95-258): fills the crossing list, returns through f the
+// first crossing row (k = r, or -1), its successor l and type kt.  a1/b1 index so that a1[1] is
+// the first symbol.
+__device__ void dc_sweep(DcCtx& x, DcFrame& f)
+{
+    const int g = x.P->G, h = x.P->H, m = g + h;
+    const uint8_t* a1 = x.A + f.a - 1;
+    const uint8_t* b1 = x.B + f.b - 1;
+    const int M = f.M, N = f.N, low = f.low, up = f.up, tb = f.tb, te = f.te;
+    int *CC = x.cc, *DD = x.dd, *CP = x.cp, *DP = x.dp;
+    const int band = up - low + 1;
+    const int midd = band / 2 + 1;
+    const int rmid = low + midd - 1;
+    int leftd = 1 - low, rightd = band;
+    int IP = 0;
+    if (leftd < midd) {
+        for (int j = 0; j < midd; j++) CP[j] = DP[j] = -1;
+        for (int j = midd; j <= rightd; j++) CP[j] = DP[j] = 0;
+        x.mp[0][0] = x.mp[1][0] = x.mp[2][0] = -1;
+    } else if (leftd > midd) {
+        const int fr = leftd - midd;
+        for (int j = 0; j <= midd; j++) CP[j] = DP[j] = fr;
+        for (int j = midd + 1; j <= rightd; j++) CP[j] = DP[j] = -1;
+        x.mp[0][fr] = x.mp[1][fr] = x.mp[2][fr] = -1;
+    } else {
+        for (int j = 0; j <= rightd; j++) CP[j] = DP[j] = 0;
+        x.mp[0][0] = x.mp[1][0] = x.mp[2][0] = -1;
+    }
+    CC[leftd] = 0;
+    {
+        int t = (tb == 2) ? 0 : -g;
+        for (int j = leftd + 1; j <= rightd; j++) { t -= h; CC[j] = t; DD[j] = t - g; }
+    }
+    CC[rightd + 1] = DD[rightd + 1] = kNeg;
+    DD[leftd] = (tb == 1) ? 0 : -g;
+    CC[leftd - 1] = kNeg;
+
+    int c = 0, d = 0, e = 0;
+    for (int i = 1; i <= M; i++) {
+        if (i > N - up) rightd--;
+        if (leftd > 1) leftd--;
+        const uint8_t ai = a1[i];
+        {
+            const int open = CC[leftd + 1] - m, ext = DD[leftd + 1] - h;
+            if (open > ext) { d = open; DP[leftd] = CP[leftd + 1]; }
+            else            { d = ext;  DP[leftd] = DP[leftd + 1]; }
+            const int ib = leftd + low - 1 + i;
+            c = open;
+            if (ib > 0) c = CC[leftd] + (ai == b1[ib] ? x.P->match : x.P->mismatch);
+            if (d > c || ib <= 0) { c = d; CP[leftd] = DP[leftd]; }
+            e = c - g;
+            DD[leftd] = d; CC[leftd] = c;
+            IP = CP[leftd];
+            if (leftd == midd) CP[leftd] = DP[leftd] = IP = i;
+        }
+        x.cells += rightd - leftd + 1;
+        for (int q = leftd + 1; q <= rightd; q++) {
+            const int sub = (ai == b1[q + low - 1 + i]) ? x.P->match : x.P->mismatch;
+            if (q != midd) {
+                int open = c - m; e -= h;
+                if (open > e) { e = open; IP = CP[q - 1]; }
+                open = CC[q + 1] - m; d = DD[q + 1] - h;
+                if (open > d) { d = open; DP[q] = CP[q + 1]; }
+                else          { DP[q] = DP[q + 1]; }
+                c = CC[q] + sub;
+                if (c < d || c < e) {
+                    if (e > d) { c = e; CP[q] = IP; }
+                    else       { c = d; CP[q] = DP[q]; }
+                }
+                CC[q] = c; DD[q] = d;
+            } else {
+                int open = c - m; e -= h;
+                if (open > e) { e = open; x.mp[1][i] = CP[q - 1]; }
+                else          { x.mp[1][i] = IP; }
+                x.mt[1][i] = 2;
+                open = CC[q + 1] - m; d = DD[q + 1] - h;
+                if (open > d) { d = open; x.mp[2][i] = CP[q + 1]; }
+                else          { x.mp[2][i] = DP[q + 1]; }
+                x.mt[2][i] = 1;
+                c = CC[q] + sub;
+                if (c < d || c < e) {
+                    if (e > d) { c = e; x.mp[0][i] = x.mp[1][i]; x.mt[0][i] = 2; }
+                    else       { c = d; x.mp[0][i] = x.mp[2][i]; x.mt[0][i] = 1; }
+                } else { x.mp[0][i] = i - 1; x.mt[0][i] = 0; }
+                if (c - g > e) { x.mp[1][i] = x.mp[0][i]; x.mt[1][i] = x.mt[0][i]; }
+                if (c - g > d) { x.mp[2][i] = x.mp[0][i]; x.mt[2][i] = x.mt[0][i]; }
+                CP[q] = DP[q] = IP = i;
+                CC[q] = c; DD[q] = d;
+            }
+        }
+    }
+    int k, l;
+    if (te == 1 && d + g > c)      { k = DP[rightd]; l = 2; }
+    else if (te == 2 && e + g > c) { k = IP;         l = 1; }
+    else                           { k = CP[rightd]; l = 0; }
+    if (rmid > N - M) l = 2; else if (rmid < N - M) l = 1;
+    int r = -1;
+    while (k > -1) {
+        x.fp[k] = r; x.ft[k] = l;
+        r = k;
+        const int nk = x.mp[l][r], nl = x.mt[l][r];
+        k = nk; l = nl;
+    }
+    f.rmid = rmid;
+    f.k = r;
+    if (r != -1) { f.l = x.fp[r]; f.kt = x.ft[r]; }
+    f.t2 = up - rmid - 1; f.t3 = low - rmid + 1;
+}
+
+__device__ __forceinline__ void dc_push(DcFrame* st, int& sp, int a, int b, int M, int N,
+                                        int low, int up, int tb, int te)
+{
+    DcFrame& f = st[sp++];
+    f.a = a; f.b = b; f.M = M; f.N = N; f.low = low; f.up = up; f.tb = tb; f.te = te; f.stage = 0;
+}
+
+// align() of globalalign.c:66-307 with the recursion unrolled into frames.
+__device__ void dc_align(DcCtx& x, DcFrame* st, int a0, int b0, int M0, int N0, int low0, int up0)
+{
+    int sp = 0;
+    dc_push(st, sp, a0, b0, M0, N0, low0, up0, 0, 0);
+    while (sp > 0) {
+        DcFrame& f = st[sp - 1];
+        switch (f.stage) {
+        case 0: {
+            if (f.N <= 0) { if (f.M > 0) put_del(x, f.M); sp--; break; }
+            if (f.M <= 0) { put_ins(x, f.N); sp--; break; }
+            if (f.up - f.low + 1 <= 1) { for (int i = 0; i < f.M; i++) put_rep(x); sp--; break; }
+            dc_sweep(x, f);
+            const int r = f.k, rmid = f.rmid;
+            if (r == -1) {                                   // :260-262
+                f.stage = 6;
+                if (rmid < 0) dc_push(st, sp, f.a, f.b, f.M, f.N, rmid + 1, f.up, f.tb, f.te);
+                else          dc_push(st, sp, f.a, f.b, f.M, f.N, f.low, rmid - 1, f.tb, f.te);
+                break;
+            }
+            if (rmid < 0)      { f.stage = 1; dc_push(st, sp, f.a, f.b, r - 1, r + rmid, rmid + 1, min(f.up, r + rmid), f.tb, 1); }
+            else if (rmid > 0) { f.stage = 2; dc_push(st, sp, f.a, f.b, r, r + rmid - 1, max(-r, f.low), rmid - 1, f.tb, 2); }
+            else f.stage = 3;
+            break;
+        }
+        case 1: put_del(x, 1); f.stage = 3; break;           // :271
+        case 2: put_ins(x, 1); f.stage = 3; break;           // :274
+        case 3: {
+            if (f.l > -1) {                                  // :280-293
+                const int t1 = f.l - f.k - 1;
+                if (f.kt == 0) { put_rep(x); f.k = f.l; f.l = x.fp[f.k]; f.kt = x.ft[f.k]; }
+                else if (f.kt == 1) {
+                    put_ins(x, 1); f.stage = 4;
+                    dc_push(st, sp, f.a + f.k, f.b + f.k + f.rmid + 1, t1, t1, 0, min(t1, f.t2), 2, 1);
+                } else {
+                    put_del(x, 1); f.stage = 5;
+                    dc_push(st, sp, f.a + f.k + 1, f.b + f.k + f.rmid, t1, t1, max(-t1, f.t3), 0, 1, 2);
+                }
+            } else {                                         // :296-304
+                const int k = f.k, rmid = f.rmid;
+                if (f.N - f.M > rmid) {
+                    put_ins(x, 1); f.stage = 6;
+                    const int t1 = k + rmid + 1;
+                    dc_push(st, sp, f.a + k, f.b + t1, f.M - k, f.N - t1, 0, min(f.N - t1, f.t2), 2, f.te);
+                } else if (f.N - f.M < rmid) {
+                    put_del(x, 1); f.stage = 6;
+                    const int t1 = f.M - (k + 1);
+                    dc_push(st, sp, f.a + k + 1, f.b + k + rmid, t1, f.N - (k + rmid), max(-t1, f.t3), 0, 1, f.te);
+                } else sp--;
+            }
+            break;
+        }
+        case 4: put_del(x, 1); f.k = f.l; f.l = x.fp[f.k]; f.kt = x.ft[f.k]; f.stage = 3; break;   // :286
+        case 5: put_ins(x, 1); f.k = f.l; f.l = x.fp[f.k]; f.kt = x.ft[f.k]; f.stage = 3; break;   // :291
+        default: sp--; break;
+        }
+    }
+}
+
+// ALIGN (globalalign.c:333-401): A, B 0-based first symbols.  Returns the number of script entries.
+__device__ int global_align_script(DcCtx& x, DcFrame* st, int M, int N, int low, int up)
+{
+    x.ns = 0; x.last = 0;
+    low = min(max(-M, low), min(N - M, 0));                  // :347-348
+    up  = max(min(N, up), max(N - M, 0));
+    if (N <= 0) { if (M > 0) put_del(x, M); }
+    else if (M <= 0) put_ins(x, N);
+    else if (up - low + 1 <= 1) { for (int i = 0; i < M; i++) put_rep(x); }
+    else dc_align(x, st, 1, 1, M, N, low, up);
+    return x.ns;
+}
+
+// fetch_cigar (globalalign.c:507-604): A, B 0-based first ALIGNED symbols
+__device__ int script_to_cigar(const uint8_t* A, const uint8_t* B, int M, int N, const int* S,
+                               int AP, int readlength, uint32_t* cig)
+{
+    int n = 0, i = 0, j = 0;
+    const int clip = AP - 1;
+    if (clip > 0) cig[n++] = ((uint32_t)clip << 4) | OP_SOFT;
+    int run_op = -1, run_len = 0, total = clip, pending = 0;
+    while (i < M || j < N) {
+        int op;
+        if (pending == 0 && *S == 0) { S++; op = (A[i] == B[j]) ? OP_EQ : OP_X; i++; j++; }
+        else {
+            if (pending == 0) pending = *S++;
+            if (pending > 0) { pending--; j++; op = OP_DEL; }
+            else             { pending++; i++; op = OP_INS; }
+        }
+        if (run_op != -1 && run_op != op) { cig[n++] = ((uint32_t)run_len << 4) | (uint32_t)run_op; total += run_len; run_len = 0; }
+        run_op = op; run_len++;
+    }
+    if (run_op != -1 && run_len > 0) { cig[n++] = ((uint32_t)run_len << 4) | (uint32_t)run_op; total += run_len; }
+    if (total < readlength) cig[n++] = ((uint32_t)(readlength - total) << 4) | OP_SOFT;
+    return n;
+}
+
+// warp-wide entry: local_align + ALIGN + fetch_cigar on a band of >= 2 diagonals.
+// `low`/`up` are already clamped (localalign.c:70-71).  Version 1: lane 0 runs the sweeps
+// sequentially (exact by construction); the other lanes wait.
+// s_out: score, q1, r1, q2, r2 (1-based inclusive, slice/window relative), ncigar, cells fwd, rev, glob, nscript
+__device__ void align_banded(const DevParams& P, const BandScratch& scr, const uint8_t* read, int M,
+                             const uint8_t* __restrict__ win, int N, int low, int up,
+                             uint32_t* cig, int ops_cap, int* s_out)
+{
+    (void)ops_cap;
+    if ((threadIdx.x & 31) == 0) {
+        const int G = P.G, H = P.H, m = G + H;
+        const int band = up - low + 1;
+        int* base = scr.base + (long long)blockIdx.x * scr.stride;
+        const int wb = scr.max_band + 4, wr = scr.max_rows + 2;
+        DcCtx x;
+        x.P = &P; x.A = read; x.B = win; x.cells = 0;
+        x.cc = base; x.dd = base + wb; x.cp = base + 2 * wb; x.dp = base + 3 * wb;
+        int* Hp = base + 4 * wb; int* Dp = base + 5 * wb; int* Hn = base + 6 * wb; int* Dn = base + 7 * wb;
+        int* rows = base + 8 * wb;
+        x.mp[0] = rows; x.mp[1] = rows + wr; x.mp[2] = rows + 2 * wr; x.fp = rows + 3 * wr;
+        x.mt[0] = rows + 4 * wr; x.mt[1] = rows + 5 * wr; x.mt[2] = rows + 6 * wr; x.ft = rows + 7 * wr;
+        x.S = rows + 8 * wr;
+        DcFrame* st = reinterpret_cast<DcFrame*>(x.S + (2 * scr.max_rows + scr.max_band + 16));
+#define AT(arr, t) ((arr)[(t) + 1])
+        // forward (localalign.c:82-131)
+        const int si = max(0, -up), ei = min(M, N - low);
+        for (int t = -1; t <= band; t++) { AT(Hp, t) = kNeg; AT(Dp, t) = kNeg; }
+        for (int t = 0; t < band; t++) {
+            const int j = si + low + t;
+            if (j >= 0 && j <= N) { AT(Hp, t) = 0; AT(Dp, t) = -G; }
+        }
+        int best = 0, endi = si, endj = si + low, cf = 0, cr = 0;
+        for (int i = si + 1; i <= ei; i++) {
+            const int tlo = max(0, -i - low), thi = min(band - 1, N - i - low);
+            for (int t = -1; t <= band; t++) { AT(Hn, t) = kNeg; AT(Dn, t) = kNeg; }
+            int e = kNeg, left = kNeg;
+            const uint8_t ai = read[i - 1];
+            for (int t = tlo; t <= thi; t++) {
+                const int j = i + low + t;
+                const int d = max(AT(Hp, t + 1) - m, AT(Dp, t + 1) - H);
+                int c;
+                if (j == 0) c = d;
+                else {
+                    c = AT(Hp, t) + (ai == win[j - 1] ? P.match : P.mismatch);
+                    if (t > tlo) { e = max(left - m, e - H); if (e > c) c = e; }
+                    if (d > c) c = d;
+                }
+                if (c < 0) c = 0;
+                if (t == tlo) e = c - G;
+                left = c;
+                AT(Hn, t) = c; AT(Dn, t) = d;
+                if (c > best) { best = c; endi = i; endj = j; }
+            }
+            cf += thi - tlo + 1;
+            int* tmp = Hp; Hp = Hn; Hn = tmp; tmp = Dp; Dp = Dn; Dn = tmp;
+        }
+        // reverse (localalign.c:132-176)
+        int starti = 0, startj = 0; bool found = false;
+        if (best > 0) {
+            const int tend = (endj - endi) - low;
+            for (int t = -1; t <= band; t++) { AT(Hp, t) = kNeg; AT(Dp, t) = kNeg; }
+            {
+                const int tl = max(0, -endi - low);
+                AT(Hp, tend) = 0; AT(Dp, tend) = -G;
+                int acc = -G;
+                for (int t = tend - 1; t >= tl; t--) { acc -= H; AT(Hp, t) = acc; AT(Dp, t) = acc - G; }
+            }
+            for (int i = endi; i >= 1 && !found; i--) {
+                for (int t = -1; t <= band; t++) { AT(Hn, t) = kNeg; AT(Dn, t) = kNeg; }
+                const int thi = min(band - 1, tend + (endi - i) + 1);
+                const int tlo = max(0, 1 - i - low);
+                int e = kNeg, right = kNeg;
+                const uint8_t ai = read[i - 1];
+                for (int t = thi; t >= tlo; t--) {
+                    const int j = i + low + t;
+                    const int d = max(AT(Hp, t - 1) - m, AT(Dp, t - 1) - H);
+                    int c;
+                    if (t == thi) {
+                        c = (j <= N) ? AT(Hp, t) + (ai == win[j - 1] ? P.match : P.mismatch) : AT(Hp, t - 1) - m;
+                        if (d > c) c = d;
+                        e = c - G;
+                    } else {
+                        e = max(right - m, e - H);
+                        c = AT(Hp, t) + (ai == win[j - 1] ? P.match : P.mismatch);
+                        if (e > c) c = e;
+                        if (d > c) c = d;
+                    }
+                    right = c;
+                    AT(Hn, t) = c; AT(Dn, t) = d;
+                    cr++;
+                    if (c == best) { starti = i; startj = j; found = true; break; }
+                }
+                int* tmp = Hp; Hp = Hn; Hn = tmp; tmp = Dp; Dp = Dn; Dn = tmp;
+            }
+        }
+#undef AT
+        bool none = best <= 0 || !found || starti > M || startj > N ||
+                    endi - starti == 0 || endj - startj == 0;            // localalign.c:180-193
+        int n = 0;
+        if (!none) {
+            const int M2 = endi - starti + 1, N2 = endj - startj + 1;
+            x.A = read + starti - 1; x.B = win + startj - 1;
+            global_align_script(x, st, M2, N2, low - (startj - starti), up - (startj - starti));
+            n = script_to_cigar(x.A, x.B, M2, N2, x.S, starti, M, cig);
+        }
+        s_out[0] = none ? 0 : best;       // ALIGN's score equals the local optimum
+        s_out[1] = starti; s_out[2] = startj; s_out[3] = endi; s_out[4] = endj;
+        s_out[5] = n; s_out[6] = cf; s_out[7] = cr; s_out[8] = none ? 0 : x.cells;
+        s_out[9] = none ? 0 : x.ns;       // script entries, left at band_script_ptr()
+    }
+    __syncwarp();
+}
+
+}  // namespace indelgpu

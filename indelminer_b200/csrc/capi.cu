@@ -1,0 +1,705 @@
+// Host side of libindelgpu.so: the C ABI declared in include/indelgpu.h.
+// Owns device memory, streams and launches; no torch, no CPU compute path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/indelgpu.h"
+#include "kernels.cuh"
+#include "band_dp.cuh"
+#include "realign_kernel.cuh"
+#include "task_kernels.cuh"
+
+using namespace indelgpu;
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(INDELGPU_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+extern "C" const char* indelgpu_last_error(void) { return g_err; }
+extern "C" int indelgpu_version(void) { return INDELGPU_VERSION; }
+
+extern "C" void indelgpu_default_params(indelgpu_params* p)
+{
+    p->klength = 6; p->numgaps = 0; p->maxdelsize = 1000; p->ethreshold = 10;
+    p->match = 1; p->mismatch = -10; p->gapopen = 10; p->gapextend = 10;
+}
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return fail(INDELGPU_ENOMEM, "cudaMalloc(%zu) failed", want); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct indelgpu_ctx {
+    int device = 0;
+    int sms = 0;
+    int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    indelgpu_params params;
+    DevParams P;
+    // reference
+    DevBuf ref_raw, ref_packed, ref_off, ref_len;
+    int ncontigs = 0;
+    int64_t ref_bases = 0;
+    // batch staging
+    DevBuf in_reads, in_off, in_tid, in_pos, in_rng;
+    DevBuf out_status, out_nseg, out_rstart, out_segoff, out_segs, out_detail, out_cig1, out_cig2;
+    DevBuf counters;         // bytes: 0 work counter (int) | 8 seg count (u64) | 16 cells (3 x u64) | 40 error flag (int) | 48 algorithmic bytes (u64)
+    DevBuf scratch;
+    // task API staging
+    DevBuf t_reads, t_roff, t_refs, t_woff, t_packed, t_anchor, t_low, t_up, t_score, t_ends, t_ncig, t_cig, t_script;
+    void* pinned_small = nullptr;   // 64 bytes for counter read-back
+    int launches = 0;
+};
+
+static int* ctr_work(indelgpu_ctx* c) { return c->counters.as<int>(); }
+static unsigned long long* ctr_segs(indelgpu_ctx* c) { return reinterpret_cast<unsigned long long*>(c->counters.as<char>() + 8); }
+static unsigned long long* ctr_cells(indelgpu_ctx* c) { return reinterpret_cast<unsigned long long*>(c->counters.as<char>() + 16); }
+static int* ctr_err(indelgpu_ctx* c) { return reinterpret_cast<int*>(c->counters.as<char>() + 40); }
+
+static int check_params(const indelgpu_params* p)
+{
+    if (p->klength < 2 || p->klength > 15) return fail(INDELGPU_EINVAL, "klength must be 2..15 (indelminer.c:1028)");
+    if (p->numgaps < 0) return fail(INDELGPU_EINVAL, "numgaps must be >= 0");
+    if (p->maxdelsize <= 0) return fail(INDELGPU_EINVAL, "maxdelsize must be > 0 (indelminer.c:1027)");
+    if (p->ethreshold < 0) return fail(INDELGPU_EINVAL, "ethreshold must be >= 0");
+    if (p->gapopen < 0 || p->gapextend < 0) return fail(INDELGPU_EINVAL, "gap penalties must be >= 0");
+    return 0;
+}
+
+static int ctx_init(indelgpu_ctx* c, int device, const indelgpu_params* p)
+{
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) return fail(INDELGPU_ECUDA, "no CUDA device visible; libindelgpu has no CPU path");
+    if (device < 0 || device >= ndev) return fail(INDELGPU_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
+    CU(cudaSetDevice(device));
+    c->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sms = prop.multiProcessorCount;
+    c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (prop.major < 10) return fail(INDELGPU_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->params = *p;
+    c->P.k = p->klength; c->P.g = p->numgaps; c->P.maxdel = p->maxdelsize; c->P.ethr = p->ethreshold;
+    c->P.match = p->match; c->P.mismatch = p->mismatch; c->P.G = p->gapopen; c->P.H = p->gapextend;
+    c->P.kmask = (uint32_t)((1ULL << (2 * p->klength)) - 1ULL);
+    if (c->counters.ensure(64)) return INDELGPU_ENOMEM;
+    CU(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
+    CU(cudaMallocHost(&c->pinned_small, 64));
+    return 0;
+}
+
+extern "C" indelgpu_ctx* indelgpu_create(int device, const indelgpu_params* p)
+{
+    indelgpu_params def;
+    if (!p) { indelgpu_default_params(&def); p = &def; }
+    if (check_params(p)) return nullptr;
+    indelgpu_ctx* c = new indelgpu_ctx();
+    if (ctx_init(c, device, p)) { delete c; return nullptr; }
+    return c;
+}
+
+extern "C" void indelgpu_destroy(indelgpu_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    DevBuf* all[] = {&c->ref_raw, &c->ref_packed, &c->ref_off, &c->ref_len, &c->in_reads, &c->in_off, &c->in_tid,
+                     &c->in_pos, &c->in_rng, &c->out_status, &c->out_nseg, &c->out_rstart, &c->out_segoff,
+                     &c->out_segs, &c->out_detail, &c->out_cig1, &c->out_cig2, &c->counters, &c->scratch,
+                     &c->t_reads, &c->t_roff, &c->t_refs, &c->t_woff, &c->t_packed, &c->t_anchor, &c->t_low,
+                     &c->t_up, &c->t_score, &c->t_ends, &c->t_ncig, &c->t_cig, &c->t_script};
+    for (DevBuf* b : all) b->release();
+    if (c->pinned_small) cudaFreeHost(c->pinned_small);
+    delete c;
+}
+
+extern "C" int indelgpu_device(const indelgpu_ctx* c) { return c ? c->device : -1; }
+extern "C" int indelgpu_sm_count(const indelgpu_ctx* c) { return c ? c->sms : 0; }
+extern "C" int indelgpu_last_launch_count(const indelgpu_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" void* indelgpu_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); fail(INDELGPU_ENOMEM, "cudaMallocHost(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+extern "C" void indelgpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---------------------------------------------------------------------------------------
+// reference upload
+// ---------------------------------------------------------------------------------------
+static int pack_device(indelgpu_ctx* c, const uint8_t* d_raw, uint32_t* d_packed, int64_t nwords)
+{
+    if (nwords <= 0) return 0;
+    int blocks = (int)std::min<int64_t>((nwords + 255) / 256, (int64_t)c->sms * 16);
+    pack_reference_kernel<<<blocks, 256, 0, c->stream>>>(d_raw, d_packed, nwords);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int indelgpu_set_reference(indelgpu_ctx* c, int32_t ncontigs, const char* const* sequences,
+                                      const int64_t* lengths)
+{
+    if (!c || ncontigs <= 0 || !sequences || !lengths) return fail(INDELGPU_EINVAL, "set_reference: bad arguments");
+    CU(cudaSetDevice(c->device));
+    std::vector<int64_t> off(ncontigs), len(ncontigs);
+    int64_t total = 0;
+    for (int i = 0; i < ncontigs; i++) {
+        if (lengths[i] < 0 || lengths[i] > 0x7FFFFFFF) return fail(INDELGPU_ELIMIT, "contig %d length %lld not in [0, 2^31)", i, (long long)lengths[i]);
+        off[i] = total; len[i] = lengths[i];
+        total += (lengths[i] + 63) / 64 * 64 + 64;       // 64-base aligned start + slack
+    }
+    total += 64;
+    if (c->ref_raw.ensure((size_t)total)) return INDELGPU_ENOMEM;
+    if (c->ref_packed.ensure((size_t)(total / 16 + 4) * 4)) return INDELGPU_ENOMEM;
+    if (c->ref_off.ensure(sizeof(int64_t) * ncontigs) || c->ref_len.ensure(sizeof(int64_t) * ncontigs)) return INDELGPU_ENOMEM;
+    CU(cudaMemsetAsync(c->ref_raw.p, 0, (size_t)total, c->stream));
+    for (int i = 0; i < ncontigs; i++)
+        if (len[i] > 0) CU(cudaMemcpyAsync(c->ref_raw.as<uint8_t>() + off[i], sequences[i], (size_t)len[i], cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->ref_off.p, off.data(), sizeof(int64_t) * ncontigs, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->ref_len.p, len.data(), sizeof(int64_t) * ncontigs, cudaMemcpyHostToDevice, c->stream));
+    c->launches = 0;
+    if (pack_device(c, c->ref_raw.as<uint8_t>(), c->ref_packed.as<uint32_t>(), total / 16)) return INDELGPU_ECUDA;
+    CU(cudaMemsetAsync(c->ref_packed.as<uint32_t>() + total / 16, 0, 16, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->ncontigs = ncontigs; c->ref_bases = total;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// batched attempt_pe_alignment
+// ---------------------------------------------------------------------------------------
+extern "C" int64_t indelgpu_seg_bound(int32_t n, int64_t total_read_bases)
+{
+    // <= (M+2) ops per CIGAR, two CIGARs + one I + one D per read
+    return 2 * total_read_bases + 8LL * n + 16;
+}
+
+static int ensure_scratch(indelgpu_ctx* c, int blocks, int max_read, BandScratch* out)
+{
+    out->base = nullptr; out->stride = 0; out->max_band = 0; out->max_rows = 0;
+    if (c->P.g <= 0) return 0;
+    const int max_band = 2 * (c->P.g + 1);
+    const long long ints = band_scratch_ints(max_band, max_read);
+    if (c->scratch.ensure((size_t)ints * 4 * (size_t)blocks)) return INDELGPU_ENOMEM;
+    out->base = c->scratch.as<int>(); out->stride = ints; out->max_band = max_band; out->max_rows = max_read;
+    return 0;
+}
+
+static int launch_realign(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_read, int max_range1,
+                          indelgpu_result* d_out, unsigned long long* d_seg_count, cudaStream_t st)
+{
+    if (c->ncontigs <= 0) return fail(INDELGPU_EINVAL, "realign: no reference uploaded (indelgpu_set_reference)");
+    if (max_read <= 0 || max_read > 65000) return fail(INDELGPU_ELIMIT, "read length %d outside 1..65000", max_read);
+    const long long nd = 2LL * ((long long)max_range1 + c->P.maxdel) + max_read + 2;
+    if (nd > (1 << 20)) return fail(INDELGPU_ELIMIT, "window of %lld diagonals exceeds the kernel limit", nd);
+    const int max_numdiag = (int)nd;
+    const SmemLayout L = make_layout(max_read, max_numdiag);
+    if (L.total > c->max_smem_optin - 1024)
+        return fail(INDELGPU_ELIMIT, "window/read sizes need %d bytes of shared memory per CTA (limit %d): range1 + maxdelsize too large",
+                    L.total, c->max_smem_optin - 1024);
+    auto kern = c->P.g > 0 ? realign_kernel<true> : realign_kernel<false>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, L.total));
+    if (occ < 1) return fail(INDELGPU_ELIMIT, "realign kernel does not fit on an SM");
+    const int blocks = (int)std::min<long long>((long long)c->sms * occ, std::max(1, d_in->n));
+
+    RealignArgs a;
+    a.P = c->P;
+    a.ref.raw = c->ref_raw.as<uint8_t>(); a.ref.packed = c->ref_packed.as<uint32_t>();
+    a.ref.contig_off = c->ref_off.as<int64_t>(); a.ref.contig_len = c->ref_len.as<int64_t>(); a.ref.ncontigs = c->ncontigs;
+    a.n = d_in->n; a.reads = d_in->read_bases; a.read_off = d_in->read_off;
+    a.tid = d_in->tid; a.position = d_in->position; a.range1 = d_in->range1;
+    a.status = d_out->status; a.nseg = d_out->nseg; a.rstart = d_out->rstart; a.seg_off = d_out->seg_off;
+    a.segs = d_out->segs; a.seg_capacity = d_out->seg_capacity; a.seg_count = d_seg_count;
+    a.detail = d_out->detail; a.cigar1 = d_out->cigar1; a.cigar2 = d_out->cigar2; a.cigar_stride = d_out->cigar_stride;
+    a.work_counter = ctr_work(c); a.cell_totals = ctr_cells(c); a.error_flag = ctr_err(c);
+    a.max_read = max_read; a.max_numdiag = max_numdiag;
+    if (ensure_scratch(c, blocks, max_read, &a.scratch)) return INDELGPU_ENOMEM;
+
+    CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
+    if (d_seg_count != ctr_segs(c)) CU(cudaMemsetAsync(d_seg_count, 0, 8, st));
+    kern<<<blocks, kThreads, L.total, st>>>(a);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int indelgpu_realign_batch_device(indelgpu_ctx* c, const indelgpu_batch* d_in, int32_t max_read_len,
+                                             int32_t max_range1, indelgpu_result* d_out, int64_t* d_seg_count,
+                                             void* stream)
+{
+    if (!c || !d_in || !d_out || !d_seg_count) return fail(INDELGPU_EINVAL, "realign_batch_device: NULL argument");
+    if (d_in->n < 0) return fail(INDELGPU_EINVAL, "negative batch size");
+    CU(cudaSetDevice(c->device));
+    c->launches = 0;
+    if (d_in->n == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    return launch_realign(c, d_in, max_read_len, max_range1, d_out, reinterpret_cast<unsigned long long*>(d_seg_count), st);
+}
+
+extern "C" int indelgpu_last_counters(indelgpu_ctx* c, int64_t out[4])
+{
+    if (!c || !out) return fail(INDELGPU_EINVAL, "last_counters: NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(c->pinned_small, c->counters.p, 64, cudaMemcpyDeviceToHost));
+    memcpy(out, (char*)c->pinned_small + 16, 24);
+    memcpy(out + 3, (char*)c->pinned_small + 48, 8);
+    return 0;
+}
+
+extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, indelgpu_result* o)
+{
+    if (!c || !h || !o) return fail(INDELGPU_EINVAL, "realign_batch: NULL argument");
+    const int n = h->n;
+    if (n < 0) return fail(INDELGPU_EINVAL, "negative batch size");
+    o->seg_count = 0;
+    c->launches = 0;
+    if (n == 0) return 0;
+    if (!h->read_bases || !h->read_off || !h->tid || !h->position || !h->range1 ||
+        !o->status || !o->nseg || !o->rstart || !o->seg_off || !o->segs)
+        return fail(INDELGPU_EINVAL, "realign_batch: NULL buffer");
+    CU(cudaSetDevice(c->device));
+    int max_read = 0, max_range = 0;
+    for (int i = 0; i < n; i++) {
+        const int64_t len = h->read_off[i + 1] - h->read_off[i];
+        if (len <= 0 || len > 65000) return fail(INDELGPU_ELIMIT, "read %d has length %lld (must be 1..65000)", i, (long long)len);
+        max_read = std::max(max_read, (int)len);
+        if (h->range1[i] < 0) return fail(INDELGPU_EINVAL, "read %d: negative range", i);
+        max_range = std::max(max_range, h->range1[i]);
+    }
+    const int64_t nbases = h->read_off[n] - h->read_off[0];
+    if (h->read_off[0] != 0) return fail(INDELGPU_EINVAL, "read_off[0] must be 0");
+    const int64_t segcap = std::min<int64_t>(o->seg_capacity, indelgpu_seg_bound(n, nbases));
+    cudaStream_t st = c->stream;
+    if (c->in_reads.ensure((size_t)nbases + 16) || c->in_off.ensure(8 * (size_t)(n + 1)) || c->in_tid.ensure(4 * (size_t)n) ||
+        c->in_pos.ensure(4 * (size_t)n) || c->in_rng.ensure(4 * (size_t)n) || c->out_status.ensure(4 * (size_t)n) ||
+        c->out_nseg.ensure(4 * (size_t)n) || c->out_rstart.ensure(4 * (size_t)n) || c->out_segoff.ensure(8 * (size_t)n) ||
+        c->out_segs.ensure(4 * (size_t)std::max<int64_t>(segcap, 1)))
+        return INDELGPU_ENOMEM;
+    if (o->detail && c->out_detail.ensure(sizeof(indelgpu_detail) * (size_t)n)) return INDELGPU_ENOMEM;
+    const size_t cigbytes = 4 * (size_t)n * (size_t)std::max(o->cigar_stride, 0);
+    if (o->cigar1 && c->out_cig1.ensure(cigbytes + 4)) return INDELGPU_ENOMEM;
+    if (o->cigar2 && c->out_cig2.ensure(cigbytes + 4)) return INDELGPU_ENOMEM;
+
+    CU(cudaMemcpyAsync(c->in_reads.p, h->read_bases, (size_t)nbases, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->in_off.p, h->read_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->in_tid.p, h->tid, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->in_pos.p, h->position, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->in_rng.p, h->range1, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (o->cigar1) CU(cudaMemsetAsync(c->out_cig1.p, 0, cigbytes, st));
+    if (o->cigar2) CU(cudaMemsetAsync(c->out_cig2.p, 0, cigbytes, st));
+
+    indelgpu_batch din = *h;
+    din.read_bases = c->in_reads.as<uint8_t>(); din.read_off = c->in_off.as<int64_t>();
+    din.tid = c->in_tid.as<int32_t>(); din.position = c->in_pos.as<int32_t>(); din.range1 = c->in_rng.as<int32_t>();
+    indelgpu_result dout = *o;
+    dout.status = c->out_status.as<int32_t>(); dout.nseg = c->out_nseg.as<int32_t>(); dout.rstart = c->out_rstart.as<int32_t>();
+    dout.seg_off = c->out_segoff.as<int64_t>(); dout.segs = c->out_segs.as<uint32_t>(); dout.seg_capacity = segcap;
+    dout.detail = o->detail ? c->out_detail.as<indelgpu_detail>() : nullptr;
+    dout.cigar1 = o->cigar1 ? c->out_cig1.as<uint32_t>() : nullptr;
+    dout.cigar2 = o->cigar2 ? c->out_cig2.as<uint32_t>() : nullptr;
+    int rc = launch_realign(c, &din, max_read, max_range, &dout, ctr_segs(c), st);
+    if (rc) return rc;
+
+    CU(cudaMemcpyAsync(o->status, dout.status, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(o->nseg, dout.nseg, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(o->rstart, dout.rstart, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(o->seg_off, dout.seg_off, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (o->detail) CU(cudaMemcpyAsync(o->detail, dout.detail, sizeof(indelgpu_detail) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (o->cigar1) CU(cudaMemcpyAsync(o->cigar1, dout.cigar1, cigbytes, cudaMemcpyDeviceToHost, st));
+    if (o->cigar2) CU(cudaMemcpyAsync(o->cigar2, dout.cigar2, cigbytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->pinned_small, c->counters.p, 64, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    unsigned long long segcount; int err;
+    memcpy(&segcount, (char*)c->pinned_small + 8, 8);
+    memcpy(&err, (char*)c->pinned_small + 40, 4);
+    if (err == 2 || (int64_t)segcount > segcap) return fail(INDELGPU_ELIMIT, "segment buffer too small: need %llu words, have %lld", segcount, (long long)segcap);
+    o->seg_count = (int64_t)segcount;
+    if (segcount) CU(cudaMemcpyAsync(o->segs, dout.segs, 4 * (size_t)segcount, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (err == 1) return fail(INDELGPU_ELIMIT, "at least one read was rejected (status %d): bad contig/position, window assert of alignment.c:548-553 or a size limit", ST_ASSERT);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// task API
+// ---------------------------------------------------------------------------------------
+static int upload_tasks(indelgpu_ctx* c, int n, const uint8_t* h_reads, const int64_t* h_read_off,
+                        const uint8_t* h_refs, const int64_t* h_ref_off, int* max_read, int* max_win)
+{
+    if (h_read_off[0] != 0 || h_ref_off[0] != 0) return fail(INDELGPU_EINVAL, "offset arrays must start at 0");
+    int mr = 0, mw = 0;
+    for (int i = 0; i < n; i++) {
+        const int64_t m = h_read_off[i + 1] - h_read_off[i], w = h_ref_off[i + 1] - h_ref_off[i];
+        if (m <= 0 || m > 65000) return fail(INDELGPU_ELIMIT, "task %d: read length %lld outside 1..65000", i, (long long)m);
+        if (w <= 0 || w > (1 << 20)) return fail(INDELGPU_ELIMIT, "task %d: window length %lld outside 1..2^20", i, (long long)w);
+        mr = std::max(mr, (int)m); mw = std::max(mw, (int)w);
+    }
+    *max_read = mr; *max_win = mw;
+    const int64_t nb = h_read_off[n], nw = h_ref_off[n];
+    if (c->t_reads.ensure((size_t)nb + 16) || c->t_roff.ensure(8 * (size_t)(n + 1)) ||
+        c->t_refs.ensure((size_t)nw + 64) || c->t_woff.ensure(8 * (size_t)(n + 1))) return INDELGPU_ENOMEM;
+    cudaStream_t st = c->stream;
+    CU(cudaMemcpyAsync(c->t_reads.p, h_reads, (size_t)nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->t_roff.p, h_read_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(c->t_refs.as<uint8_t>() + nw, 0, 64, st));
+    CU(cudaMemcpyAsync(c->t_refs.p, h_refs, (size_t)nw, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->t_woff.p, h_ref_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+extern "C" int indelgpu_find_best_band_batch(indelgpu_ctx* c, int32_t n, const uint8_t* h_reads,
+                                             const int64_t* h_read_off, const uint8_t* h_refs,
+                                             const int64_t* h_ref_off, const int32_t* h_anchor_rel,
+                                             int32_t* h_low, int32_t* h_up)
+{
+    if (!c || n < 0 || !h_reads || !h_read_off || !h_refs || !h_ref_off || !h_anchor_rel || !h_low || !h_up)
+        return fail(INDELGPU_EINVAL, "find_best_band_batch: bad argument");
+    c->launches = 0;
+    if (n == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    int max_read, max_win;
+    int rc = upload_tasks(c, n, h_reads, h_read_off, h_refs, h_ref_off, &max_read, &max_win);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    const int64_t nw = h_ref_off[n];
+    const int64_t words = (nw + 63) / 16 + 1;
+    if (c->t_packed.ensure(4 * (size_t)(words + 4)) || c->t_anchor.ensure(4 * (size_t)n) ||
+        c->t_low.ensure(4 * (size_t)n) || c->t_up.ensure(4 * (size_t)n)) return INDELGPU_ENOMEM;
+    CU(cudaMemcpyAsync(c->t_anchor.p, h_anchor_rel, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (pack_device(c, c->t_refs.as<uint8_t>(), c->t_packed.as<uint32_t>(), words)) return INDELGPU_ECUDA;
+
+    const int max_numdiag = max_win + max_read + 4;
+    const SmemLayout L = make_layout(max_read, max_numdiag);
+    if (L.total > c->max_smem_optin - 1024) return fail(INDELGPU_ELIMIT, "window too large for shared memory (%d bytes)", L.total);
+    CU(cudaFuncSetAttribute(vote_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vote_tasks_kernel, kThreads, L.total));
+    if (occ < 1) return fail(INDELGPU_ELIMIT, "vote kernel does not fit on an SM");
+    TaskArgs a; memset(&a, 0, sizeof(a));
+    a.P = c->P; a.n = n;
+    a.reads = c->t_reads.as<uint8_t>(); a.read_off = c->t_roff.as<int64_t>();
+    a.refs = c->t_refs.as<uint8_t>(); a.ref_off = c->t_woff.as<int64_t>();
+    a.packed = c->t_packed.as<uint32_t>(); a.anchor_rel = c->t_anchor.as<int32_t>();
+    a.low = c->t_low.as<int32_t>(); a.up = c->t_up.as<int32_t>();
+    a.work_counter = ctr_work(c); a.cell_totals = ctr_cells(c); a.error_flag = ctr_err(c);
+    a.max_read = max_read; a.max_numdiag = max_numdiag;
+    CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
+    const int blocks = (int)std::min<long long>((long long)c->sms * occ, n);
+    vote_tasks_kernel<<<blocks, kThreads, L.total, st>>>(a);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h_low, a.low, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_up, a.up, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->pinned_small, c->counters.p, 64, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int err; memcpy(&err, (char*)c->pinned_small + 40, 4);
+    if (err) return fail(INDELGPU_ELIMIT, "find_best_band_batch: a task violates numdiagonals > numgaps (alignment.c:405) or a size limit");
+    return 0;
+}
+
+extern "C" int indelgpu_band_align_batch(indelgpu_ctx* c, int32_t n, const uint8_t* h_reads,
+                                         const int64_t* h_read_off, const uint8_t* h_refs,
+                                         const int64_t* h_ref_off, const int32_t* h_low, const int32_t* h_up,
+                                         int32_t* h_score, int32_t* h_ends, int32_t* h_ncigar,
+                                         uint32_t* h_cigar, int32_t cigar_stride, int32_t* h_script,
+                                         int32_t script_stride, int64_t* h_cells)
+{
+    if (!c || n < 0 || !h_reads || !h_read_off || !h_refs || !h_ref_off || !h_low || !h_up || !h_score || !h_ends || !h_ncigar)
+        return fail(INDELGPU_EINVAL, "band_align_batch: bad argument");
+    c->launches = 0;
+    if (h_cells) h_cells[0] = h_cells[1] = h_cells[2] = 0;
+    if (n == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    int max_read, max_win;
+    int rc = upload_tasks(c, n, h_reads, h_read_off, h_refs, h_ref_off, &max_read, &max_win);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    int max_band = 1;
+    for (int i = 0; i < n; i++) {
+        const int M = (int)(h_read_off[i + 1] - h_read_off[i]), N = (int)(h_ref_off[i + 1] - h_ref_off[i]);
+        const int lo = std::max(-M, h_low[i]), hi = std::min(N, h_up[i]);
+        if (hi - lo + 1 < 1) return fail(INDELGPU_EINVAL, "task %d: low > up is unacceptable! low:%d up:%d (localalign.c:74-77)", i, lo, hi);
+        max_band = std::max(max_band, hi - lo + 1);
+    }
+    if (cigar_stride < 0) cigar_stride = 0;
+    if (script_stride < 0) script_stride = 0;
+    if (c->t_low.ensure(4 * (size_t)n) || c->t_up.ensure(4 * (size_t)n) || c->t_score.ensure(4 * (size_t)n) ||
+        c->t_ends.ensure(16 * (size_t)n) || c->t_ncig.ensure(4 * (size_t)n) ||
+        c->t_cig.ensure(4 * (size_t)n * (size_t)cigar_stride + 4) ||
+        c->t_script.ensure(4 * (size_t)n * (size_t)script_stride + 4)) return INDELGPU_ENOMEM;
+    CU(cudaMemcpyAsync(c->t_low.p, h_low, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->t_up.p, h_up, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+
+    const SmemLayout L = make_layout(max_read, 0);
+    if (L.total > c->max_smem_optin - 1024) return fail(INDELGPU_ELIMIT, "read too long for shared memory (%d bytes)", L.total);
+    CU(cudaFuncSetAttribute(align_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align_tasks_kernel, 32, L.total));
+    if (occ < 1) return fail(INDELGPU_ELIMIT, "align kernel does not fit on an SM");
+    const int blocks = (int)std::min<long long>((long long)c->sms * occ, n);
+    TaskArgs a; memset(&a, 0, sizeof(a));
+    a.P = c->P; a.n = n;
+    a.reads = c->t_reads.as<uint8_t>(); a.read_off = c->t_roff.as<int64_t>();
+    a.refs = c->t_refs.as<uint8_t>(); a.ref_off = c->t_woff.as<int64_t>();
+    a.low = c->t_low.as<int32_t>(); a.up = c->t_up.as<int32_t>();
+    a.score = c->t_score.as<int32_t>(); a.ends = c->t_ends.as<int32_t>(); a.ncigar = c->t_ncig.as<int32_t>();
+    a.cigar = h_cigar ? c->t_cig.as<uint32_t>() : nullptr; a.cigar_stride = cigar_stride;
+    a.script = h_script ? c->t_script.as<int32_t>() : nullptr; a.script_stride = script_stride;
+    a.work_counter = ctr_work(c); a.cell_totals = ctr_cells(c); a.error_flag = ctr_err(c);
+    a.max_read = max_read; a.max_numdiag = 0;
+    a.scratch.base = nullptr; a.scratch.stride = 0; a.scratch.max_band = 0; a.scratch.max_rows = 0;
+    if (max_band > 1) {
+        const int mb = 2 * max_band;
+        const long long ints = band_scratch_ints(mb, max_read);
+        if (c->scratch.ensure((size_t)ints * 4 * (size_t)blocks)) return INDELGPU_ENOMEM;
+        a.scratch.base = c->scratch.as<int>(); a.scratch.stride = ints; a.scratch.max_band = mb; a.scratch.max_rows = max_read;
+    }
+    CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
+    if (h_cigar) CU(cudaMemsetAsync(c->t_cig.p, 0, 4 * (size_t)n * (size_t)cigar_stride, st));
+    align_tasks_kernel<<<blocks, 32, L.total, st>>>(a);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h_score, a.score, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_ends, a.ends, 16 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_ncigar, a.ncigar, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (h_cigar) CU(cudaMemcpyAsync(h_cigar, a.cigar, 4 * (size_t)n * (size_t)cigar_stride, cudaMemcpyDeviceToHost, st));
+    if (h_script) CU(cudaMemcpyAsync(h_script, a.script, 4 * (size_t)n * (size_t)script_stride, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->pinned_small, c->counters.p, 64, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int err; memcpy(&err, (char*)c->pinned_small + 40, 4);
+    if (h_cells) memcpy(h_cells, (char*)c->pinned_small + 16, 24);
+    if (err) return fail(INDELGPU_ELIMIT, "band_align_batch: a task exceeds a size limit");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// reference-prototype entry points (default context, 1-element batches)
+// ---------------------------------------------------------------------------------------
+static indelgpu_ctx* g_default = nullptr;
+static std::mutex g_default_mu;
+
+[[noreturn]] static void die(const char* what)
+{
+    // the reference's convention: message on stderr, exit(EXIT_FAILURE) (errors.c:15-27)
+    fprintf(stderr, "libindelgpu: %s: %s\n", what, g_err);
+    exit(EXIT_FAILURE);
+}
+
+static indelgpu_ctx* default_ctx()
+{
+    if (!g_default) {
+        const char* dev = getenv("INDELGPU_DEVICE");
+        g_default = indelgpu_create(dev ? atoi(dev) : 0, nullptr);   // scratch is sized per call
+        if (!g_default) die("cannot create the default GPU context");
+    }
+    return g_default;
+}
+
+static int script_length(const int* S, int M, int N)
+{
+    int i = 0, j = 0, k = 0;
+    while (i < M || j < N) {
+        const int op = S[k++];
+        if (op == 0) { i++; j++; } else if (op > 0) j += op; else i -= op;
+    }
+    return k;
+}
+
+extern "C" int local_align(char* seq1, const int seq1len, char* seq2, const int seq2len, const int indx1,
+                           const int indx2, int* const psi, int* const psj, int* const pei, int* const pej,
+                           int* const S)
+{
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    indelgpu_ctx* c = default_ctx();
+    if (seq1len <= 0 || seq2len <= 0) { fprintf(stderr, "Assertion failed: strlen(seq) > 0 file localalign.c\n"); exit(EXIT_FAILURE); }
+    if (std::max(-seq1len, indx1) > std::min(seq2len, indx2)) {
+        // localalign.c:74-77 prints to stdout; stdout is the VCF stream, so stderr here
+        fprintf(stderr, "low > up is unacceptable! low:%d up:%d\n", std::max(-seq1len, indx1), std::min(seq2len, indx2));
+        exit(1);
+    }
+    const int64_t roff[2] = {0, seq1len}, woff[2] = {0, seq2len};
+    int32_t low = indx1, up = indx2, score = 0, ends[4], ncig = 0;
+    const int stride = seq1len + seq2len + 2;
+    std::vector<int32_t> script((size_t)stride);
+    if (indelgpu_band_align_batch(c, 1, (const uint8_t*)seq1, roff, (const uint8_t*)seq2, woff, &low, &up,
+                                  &score, ends, &ncig, nullptr, 0, script.data(), stride, nullptr))
+        die("local_align");
+    if (score <= 0) return 0;
+    *psi = ends[0]; *psj = ends[1]; *pei = ends[2]; *pej = ends[3];
+    const int n = script_length(script.data(), ends[2] - ends[0] + 1, ends[3] - ends[1] + 1);
+    memcpy(S, script.data(), sizeof(int) * (size_t)n);
+    return score;
+}
+
+// one (A, B, S) problem on the device; shared by fetch_cigar and ALIGN
+static int upload_pair(indelgpu_ctx* c, const uint8_t* A, int M, const uint8_t* B, int N)
+{
+    if (c->t_reads.ensure((size_t)std::max(M, 0) + 16) || c->t_refs.ensure((size_t)std::max(N, 0) + 64)) return INDELGPU_ENOMEM;
+    if (M > 0) CU(cudaMemcpyAsync(c->t_reads.p, A, (size_t)M, cudaMemcpyHostToDevice, c->stream));
+    if (N > 0) CU(cudaMemcpyAsync(c->t_refs.p, B, (size_t)N, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+static int fetch_cigar_gpu(indelgpu_ctx* c, const uint8_t* A, const uint8_t* B, int M, int N, const int* S, int nS,
+                           int AP, int readlength, std::vector<uint32_t>& cig, int* mm)
+{
+    CU(cudaSetDevice(c->device));
+    int rc = upload_pair(c, A, M, B, N);
+    if (rc) return rc;
+    const size_t cap = (size_t)std::max(M, 0) + (size_t)std::max(N, 0) + 4;
+    if (c->t_script.ensure(4 * (size_t)(nS + 4)) || c->t_cig.ensure(4 * cap) || c->t_ncig.ensure(16)) return INDELGPU_ENOMEM;
+    if (nS > 0) CU(cudaMemcpyAsync(c->t_script.p, S, 4 * (size_t)nS, cudaMemcpyHostToDevice, c->stream));
+    fetch_cigar_one_kernel<<<1, 32, 0, c->stream>>>(c->t_reads.as<uint8_t>(), c->t_refs.as<uint8_t>(), M, N,
+                                                     c->t_script.as<int>(), AP, readlength, c->t_cig.as<uint32_t>(),
+                                                     c->t_ncig.as<int>());
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->pinned_small, c->t_ncig.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    int meta[2]; memcpy(meta, c->pinned_small, 8);
+    cig.resize((size_t)meta[0]);
+    if (meta[0] > 0) CU(cudaMemcpy(cig.data(), c->t_cig.p, 4 * (size_t)meta[0], cudaMemcpyDeviceToHost));
+    *mm = meta[1];
+    return 0;
+}
+
+extern "C" int fetch_cigar(char* A, char* B, int M, int N, int* S, int AP, int BP, const int readlength,
+                           int* const pnumops, uint32_t** pcigar)
+{
+    // A[1], B[1] are the first aligned symbols (alignment.c:374).  The run-length encoding runs on the
+    // GPU like everything else; only the caller's realloc'ed buffer convention (globalalign.c:474-476)
+    // is handled here.
+    (void)BP;
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    indelgpu_ctx* c = default_ctx();
+    c->launches = 0;
+    const int nS = script_length(S, M, N);
+    std::vector<uint32_t> cig; int mm = 0;
+    if (fetch_cigar_gpu(c, (const uint8_t*)A + 1, (const uint8_t*)B + 1, M, N, S, nS, AP, readlength, cig, &mm)) die("fetch_cigar");
+    const int n = (int)cig.size();
+    if (n > 1) {
+        *pcigar = (uint32_t*)realloc(*pcigar, sizeof(uint32_t) * (size_t)n);
+        if (!*pcigar) { fprintf(stderr, "libindelgpu: realloc failed\n"); exit(2); }
+    }
+    for (int t = 0; t < n; t++) (*pcigar)[t] = cig[t];
+    *pnumops = n;
+    return mm;
+}
+
+static int global_align_one(indelgpu_ctx* c, const uint8_t* A, const uint8_t* B, int M, int N, int low, int up,
+                            int match, int mismatch, int G, int H, int* S, int* score)
+{
+    CU(cudaSetDevice(c->device));
+    int rc = upload_pair(c, A, M, B, N);
+    if (rc) return rc;
+    const int m = std::max(M, 0), n = std::max(N, 0);
+    const int lo = std::min(std::max(-M, low), std::min(N - M, 0)), hi = std::max(std::min(N, up), std::max(N - M, 0));
+    const int band = std::max(hi - lo + 1, 1);
+    BandScratch scr;
+    scr.max_band = band; scr.max_rows = m; scr.stride = band_scratch_ints(band, m);
+    if (c->scratch.ensure(4 * (size_t)scr.stride) || c->t_script.ensure(4 * (size_t)(m + n + 8)) || c->t_ncig.ensure(16)) return INDELGPU_ENOMEM;
+    scr.base = c->scratch.as<int>();
+    DevParams P = c->P;
+    P.match = match; P.mismatch = mismatch; P.G = G; P.H = H;
+    global_align_one_kernel<<<1, 32, 0, c->stream>>>(P, scr, c->t_reads.as<uint8_t>(), c->t_refs.as<uint8_t>(), M, N, low, up,
+                                                      c->t_script.as<int>(), c->t_ncig.as<int>());
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->pinned_small, c->t_ncig.p, 12, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    int meta[3]; memcpy(meta, c->pinned_small, 12);
+    if (meta[1] > 0) CU(cudaMemcpy(S, c->t_script.p, 4 * (size_t)meta[1], cudaMemcpyDeviceToHost));
+    *score = meta[0];
+    return 0;
+}
+
+extern "C" int ALIGN(char* A, char* B, int M, int N, int low, int up, int W[][128], int G, int H, int* S)
+{
+    // A, B point one element before the first symbol (globalalign.h:19-28).  The kernels score
+    // by byte equality with one match and one mismatch value, which is the only table the
+    // reference ever passes (localalign.c:61-67); verify that instead of silently assuming it.
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    indelgpu_ctx* c = default_ctx();
+    const int match = W['A']['A'], mismatch = W['A']['C'];
+    for (int a = 0; a < 128; a++)
+        for (int b = 0; b < 128; b++)
+            if (W[a][b] != (a == b ? match : mismatch)) {
+                fprintf(stderr, "libindelgpu: ALIGN supports match/mismatch tables only (W[%d][%d] = %d)\n", a, b, W[a][b]);
+                exit(EXIT_FAILURE);
+            }
+    c->launches = 0;
+    int score = 0;
+    if (global_align_one(c, (const uint8_t*)A + 1, (const uint8_t*)B + 1, M, N, low, up, match, mismatch, G, H, S, &score)) die("ALIGN");
+    return score;
+}
+
+extern "C" int DISPLAY(FILE* F, char* A, char* B, int M, int N, int* S, int AP, int BP)
+{
+    // debug pretty-printer of globalalign.c:408-457: 50 columns per block, '|' under matches,
+    // '-' under gaps.  Pure formatting, host only.
+    char al[51], bl[51], cl[51];
+    int i = 0, j = 0, op = 0, lines = 0, ap = AP, bp = BP, w = 0;
+    while (i < M || j < N) {
+        if (op == 0 && *S == 0) { op = *S++; al[w] = A[++i]; bl[w] = B[++j]; cl[w] = (al[w] == bl[w]) ? '|' : ' '; w++; }
+        else {
+            if (op == 0) op = *S++;
+            if (op > 0) { al[w] = ' '; bl[w] = B[++j]; op--; }
+            else        { al[w] = A[++i]; bl[w] = ' '; op++; }
+            cl[w++] = '-';
+        }
+        if (w >= 50 || (i >= M && j >= N)) {
+            al[w] = bl[w] = cl[w] = '\0';
+            fprintf(F, "\n%5d ", 50 * lines++);
+            for (int t = 10; t <= w; t += 10) fprintf(F, "    .    :");
+            if (w % 10 >= 5) fprintf(F, "    .");
+            fprintf(F, "\n%5d %s\n      %s\n%5d %s\n", ap, al, cl, bp, bl);
+            ap = AP + i; bp = BP + j; w = 0;
+        }
+    }
+    return -1;
+}

@@ -1,0 +1,459 @@
+// Device code of libindelgpu.so: split-read realignment kernels for sm_100a.
+//
+// One persistent CTA realigns one read at a time (work taken from an atomic counter):
+//   round 1  vote (k-mer diagonal histogram)  ->  align on the voted band  ->  CIGAR
+//   plan     which window / read slice round 2 uses (attempt_diagonal_alignments' branches)
+//   round 2  vote -> align -> CIGAR
+//   combine  junction choice + segment stitching (update_readsegs)
+// Everything between the read bytes coming in and the segment words going out stays in
+// shared memory / registers; the reference windows are read from the resident 2-bit packed
+// copy (voting) and raw bytes (DP) in HBM/L2.
+//
+// Reference behaviour reproduced (file:line of ratan-lab/indelMINER):
+//   find_best_band        src/alignment.c:393-447 (+ :29-181)
+//   local_align           src/localalign.c:15-196
+//   ALIGN / align         src/globalalign.c:66-401
+//   fetch_cigar           src/globalalign.c:507-604
+//   attempt_diagonal_alignments  src/alignment.c:539-759
+//   update_readsegs       src/readaln.c:348-458
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/indelgpu.h"
+
+namespace indelgpu {
+
+constexpr int kThreads = 128;             // threads per CTA of the realign kernel
+constexpr int kWarps = kThreads / 32;
+constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
+constexpr int kNeg = -9999999;            // MININT (localalign.c:3, globalalign.h:16)
+
+enum { OP_INS = 1, OP_DEL = 2, OP_SOFT = 4, OP_EQ = 7, OP_X = 8 };   // bam.h:138-155, readaln.h:10-11
+constexpr int ST_ASSERT = 7;              // the reference would have hit a forceassert / exit()
+
+struct DevParams {
+    int k, g, maxdel, ethr;
+    int match, mismatch, G, H;
+    uint32_t kmask;                       // 2k low bits
+};
+
+struct RefView {
+    const uint8_t* raw;                   // concatenated contigs, each starting on a 64-base boundary
+    const uint32_t* packed;               // 2 bits per base, 16 bases per word, non-ACGT -> 0
+    const int64_t* contig_off;            // base offset of each contig in raw
+    const int64_t* contig_len;
+    int ncontigs;
+};
+
+// shared-memory layout, computed identically on host and device
+struct SmemLayout {
+    int ht_slots;        // power of two
+    int hist_words;      // uint32 words (2 x uint16 counters each)
+    int read_bytes;      // padded
+    int ops_cap;         // words per CIGAR buffer
+    int off_keys, off_vals, off_hist, off_read, off_bits, off_psum, off_cig1, off_cig2, off_segs;
+    int total;
+};
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+__host__ __device__ inline SmemLayout make_layout(int max_read, int max_numdiag)
+{
+    SmemLayout L;
+    int ht = 256;
+    while (ht < 4 * max_read) ht <<= 1;
+    L.ht_slots = ht;
+    L.hist_words = round_up(max_numdiag + 2, 8) / 2 + 4;
+    L.read_bytes = round_up(max_read + 16, 16);
+    L.ops_cap = max_read + 4;
+    int o = 0;
+    L.off_keys = o; o += ht * 4;
+    L.off_vals = o; o += ht * 4;
+    L.off_hist = o; o += round_up(L.hist_words * 4, 16);
+    L.off_read = o; o += L.read_bytes;
+    L.off_bits = o; o += round_up((max_read / 32 + 2) * 4, 16);
+    L.off_psum = o; o += round_up((max_read + 2) * 4, 16);
+    L.off_cig1 = o; o += round_up(L.ops_cap * 4, 16);
+    L.off_cig2 = o; o += round_up(L.ops_cap * 4, 16);
+    L.off_segs = o; o += round_up((2 * L.ops_cap + 4) * 4, 16);
+    L.total = o;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------
+// 2-bit packing of the reference (once per upload)
+// ---------------------------------------------------------------------------------------
+
+// base2bits of alignment.c:11-24 up to a relabelling (only equality of k-mers matters):
+// A/a -> 0, C/c -> 1, T/t -> 2, G/g -> 3, every other byte -> 0 (same as A).
+__host__ __device__ inline uint32_t base_code(uint32_t b)
+{
+    uint32_t u = b & 0xDFu;
+    uint32_t idx = u - 0x41u;
+    uint32_t ok = (idx < 20u) ? ((0x80045u >> idx) & 1u) : 0u;
+    return ok ? ((u >> 1) & 3u) : 0u;
+}
+
+__global__ void pack_reference_kernel(const uint8_t* __restrict__ raw, uint32_t* __restrict__ packed,
+                                      int64_t nwords)
+{
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; w < nwords; w += stride) {
+        const uint4 v = reinterpret_cast<const uint4*>(raw)[w];
+        const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+        uint32_t out = 0;
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            uint32_t b = (q[t >> 2] >> ((t & 3) * 8)) & 0xFFu;
+            out |= base_code(b) << (2 * t);
+        }
+        packed[w] = out;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t hash_slot(uint32_t code, int mask)
+{
+    return ((code * 2654435761u) >> 12) & (uint32_t)mask;
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+struct Cta {
+    // dynamic shared memory views
+    uint32_t* keys; uint32_t* vals; uint32_t* hist; uint8_t* read; uint32_t* bits; int* psum;
+    uint32_t* cig1; uint32_t* cig2; uint32_t* segs;
+    SmemLayout L;
+};
+
+// result of one attempt_band_alignment (alignment.c:343-391); coordinates already absolute
+struct Aln {
+    int low, up, score, r1, r2, q1, q2, n;
+    int cells_fwd, cells_rev, cells_glob;
+};
+
+// ---------------------------------------------------------------------------------------
+// find_best_band: k-mer diagonal voting, CTA-wide
+// ---------------------------------------------------------------------------------------
+// Restated set-wise (SURVEY.md 8a''): for every window offset j whose k-mer equals a k-mer that
+// occurs exactly once in the read slice (at offset i): diag[j - i + (M-k+1)]++ ; then the
+// arg-max band with the reference's tie rule.  The reference builds chained position tables of
+// the WINDOW (alignment.c:29-68); here the (much smaller) READ side is indexed in a shared-memory
+// hash table and the window's packed 2-bit stream is scanned once with coalesced loads.
+//
+// All threads must call.  Returns low (up = low + g) to every thread; `ok` false when the
+// reference would have aborted (numdiagonals <= numgaps, alignment.c:405).
+__device__ int vote_band(const DevParams& P, Cta& S, const uint32_t* __restrict__ packed,
+                         int64_t wabs, int N, int zs2, int M, int anchor_rel, bool* ok,
+                         unsigned long long* s_red)
+{
+    const int tid = threadIdx.x;
+    const int k = P.k, g = P.g;
+    const int numdiag = (N - (k - 1)) + (M - (k - 1));           // alignment.c:403-404
+    *ok = numdiag > g;
+    if (!*ok) return 0;
+    if (M < k) return numdiag - 1;                               // alignment.c:408-412
+
+    // 1. index the read slice's k-mers: key -> (count << 16 | offset + 1)
+    const int ht_mask = S.L.ht_slots - 1;
+    for (int s = tid; s < S.L.ht_slots; s += kThreads) { S.keys[s] = kEmptyKey; S.vals[s] = 0; }
+    __syncthreads();
+    const uint8_t* r = S.read + zs2;
+    for (int i = tid; i + k <= M; i += kThreads) {
+        uint32_t code = 0;
+        for (int t = 0; t < k; t++) code |= base_code(r[i + t]) << (2 * t);
+        uint32_t slot = hash_slot(code, ht_mask);
+        while (true) {
+            uint32_t prev = atomicCAS(&S.keys[slot], kEmptyKey, code);
+            if (prev == kEmptyKey || prev == code) { atomicAdd(&S.vals[slot], (1u << 16) | (uint32_t)(i + 1)); break; }
+            slot = (slot + 1) & ht_mask;
+        }
+    }
+    __syncthreads();
+
+    // 2. scan the window: one packed word (16 bases) per thread per step
+    if (N >= k) {
+        const int64_t first = wabs, last = wabs + N - k;         // k-mer start positions, inclusive
+        const int64_t w0 = first >> 4, w1 = last >> 4;
+        const int shiftM = M - k + 1;
+        for (int64_t wi = w0 + tid; wi <= w1; wi += kThreads) {
+            const uint32_t lo = __ldg(packed + wi), hi = __ldg(packed + wi + 1);
+            const unsigned long long x = ((unsigned long long)hi << 32) | lo;
+            const int64_t pos0 = wi << 4;
+#pragma unroll
+            for (int p = 0; p < 16; p++) {
+                const int64_t pos = pos0 + p;
+                if (pos < first || pos > last) continue;
+                const uint32_t code = (uint32_t)(x >> (2 * p)) & P.kmask;
+                uint32_t slot = hash_slot(code, ht_mask);
+                while (true) {
+                    const uint32_t kk = S.keys[slot];
+                    if (kk == code) {
+                        const uint32_t v = S.vals[slot];
+                        if ((v >> 16) == 1u) {                   // unique in the read (alignment.c:97-98)
+                            const int idx = (int)(pos - first) - (int)((v & 0xFFFFu) - 1u) + shiftM;
+                            atomicAdd(&S.hist[idx >> 1], 1u << ((idx & 1) * 16));
+                        }
+                        break;
+                    }
+                    if (kk == kEmptyKey) break;
+                    slot = (slot + 1) & ht_mask;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // 3. bin_bands + select_band (alignment.c:130-181): arg-max by (count desc, |a - i| asc, i asc)
+    int a = anchor_rel;
+    a = a < -1 ? -1 : (a > numdiag ? numdiag : a);               // clamping keeps every comparison
+    unsigned long long best = 0;
+    const uint16_t* h16 = reinterpret_cast<const uint16_t*>(S.hist);
+    for (int i = tid; i < numdiag; i += kThreads) {
+        uint32_t b = 0;
+        if (i < numdiag - g) for (int j = 0; j <= g; j++) b += h16[i + j];
+        const uint32_t dist = (uint32_t)(a > i ? a - i : i - a);
+        const unsigned long long key = ((unsigned long long)b << 42) |
+                                       ((unsigned long long)(0x1FFFFFu - dist) << 21) |
+                                       (unsigned long long)(0x1FFFFFu - (uint32_t)i);
+        best = key > best ? key : best;
+    }
+    best = warp_max_u64(best);
+    if ((tid & 31) == 0) s_red[tid >> 5] = best;
+    __syncthreads();
+    best = s_red[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; w++) best = s_red[w] > best ? s_red[w] : best;
+    // leave the histogram clean for the next use
+    for (int s = tid; s < (numdiag + 2) / 2 + 1; s += kThreads) S.hist[s] = 0;
+    __syncthreads();
+    const int idx = (int)(0x1FFFFFu - (uint32_t)(best & 0x1FFFFFu));
+    return idx - (M - k + 1);                                    // alignment.c:438
+}
+
+// ---------------------------------------------------------------------------------------
+// band of one diagonal: local_align degenerates to a max-segment scan (SURVEY.md 8a'),
+// ALIGN takes its all-REP exit (globalalign.c:358-365).  Executed by warp 0.
+// ---------------------------------------------------------------------------------------
+__device__ void align_diag1(const DevParams& P, Cta& S, const uint8_t* __restrict__ win,
+                            int N, int zs2, int M, int d, uint32_t* cig, int* s_out /* >= 9 ints */)
+{
+    const int lane = threadIdx.x & 31;
+    const uint8_t* r = S.read + zs2;
+    const int si = max(0, -d), ei = min(M, N - d);               // localalign.c:86-87
+    int best = 0, endi = si;
+    int carryP = 0, carryMin = 0;
+    if (lane == 0) S.psum[0] = 0;
+    for (int base = si; base < ei; base += 32) {
+        const int i = base + 1 + lane;                           // 1-based read row
+        const bool valid = i <= ei;
+        bool eq = false;
+        if (valid) eq = r[i - 1] == __ldg(win + (i + d - 1));
+        const uint32_t mbits = __ballot_sync(0xFFFFFFFFu, eq);
+        if (lane == 0) S.bits[(base - si) >> 5] = mbits;
+        int p = valid ? (eq ? P.match : P.mismatch) : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, p, o); if (lane >= o) p += t; }
+        p += carryP;                                             // prefix sum P_i
+        int mn = p;                                              // min_{j<=i} P_j  (P_si = 0 included)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, mn, o); if (lane >= o) mn = min(mn, t); }
+        mn = min(mn, carryMin);
+        const int run = valid ? p - mn : -1;                     // max(0, run + w) recursion, localalign.c:100-131
+        if (valid) S.psum[i - si] = p;
+        int cmax = run;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, o));
+        if (cmax > best) {                                       // strict: the first maximum wins
+            const uint32_t who = __ballot_sync(0xFFFFFFFFu, run == cmax);
+            best = cmax; endi = base + __ffs(who);
+        }
+        carryP = __shfl_sync(0xFFFFFFFFu, p, 31);
+        carryMin = min(carryMin, __shfl_sync(0xFFFFFFFFu, mn, 31));
+    }
+    __syncwarp();
+    int starti = 0;
+    if (best > 0) {
+        // reverse sweep (localalign.c:144-176): first row, walking down from endi, whose suffix sum equals best
+        const int target = S.psum[endi - si] - best;
+        for (int base = endi; base > si; base -= 32) {
+            const int i = base - lane;
+            const bool hit = i > si && S.psum[i - 1 - si] == target;
+            const uint32_t who = __ballot_sync(0xFFFFFFFFu, hit);
+            if (who) { starti = base - (__ffs(who) - 1); break; }
+        }
+    }
+    const bool none = best <= 0 || starti == 0 || endi == starti;   // localalign.c:191-193
+    if (lane == 0) {
+        int n = 0;
+        if (!none) {
+            // fetch_cigar (globalalign.c:507-604) on an all-REP script
+            if (starti - 1 > 0) cig[n++] = ((uint32_t)(starti - 1) << 4) | OP_SOFT;
+            int pos = starti - 1 - si, end = endi - 1 - si;      // bit positions in S.bits
+            while (pos <= end) {
+                const uint32_t word = S.bits[pos >> 5];
+                const int bit = (word >> (pos & 31)) & 1;
+                // length of the run starting at pos
+                int q = pos;
+                while (true) {
+                    const uint32_t wq = S.bits[q >> 5];
+                    uint32_t diff = (bit ? ~wq : wq) >> (q & 31);   // 1 where the run is broken
+                    const int room = 32 - (q & 31);
+                    if (diff) { q += __ffs(diff) - 1; break; }
+                    q += room;
+                    if (q > end) break;
+                }
+                if (q > end + 1) q = end + 1;
+                cig[n++] = ((uint32_t)(q - pos) << 4) | (bit ? OP_EQ : OP_X);
+                pos = q;
+            }
+            if (M - endi > 0) cig[n++] = ((uint32_t)(M - endi) << 4) | OP_SOFT;
+        }
+        s_out[0] = none ? 0 : best;
+        s_out[1] = none ? 0 : starti;        // q1 (1-based inclusive)
+        s_out[2] = none ? 0 : starti + d;    // r1
+        s_out[3] = none ? 0 : endi;          // q2
+        s_out[4] = none ? 0 : endi + d;      // r2
+        s_out[5] = n;
+        s_out[6] = ei - si;                                  // forward cells
+        s_out[7] = best > 0 ? endi - starti + 1 : 0;         // reverse cells until the hit
+        s_out[8] = 0;                                        // ALIGN exits before any sweep (band <= 1)
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------
+// scalar pieces of attempt_diagonal_alignments, executed by one thread
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int cig_op(uint32_t c) { return (int)(c & 15u); }
+__device__ __forceinline__ int cig_len(uint32_t c) { return (int)(c >> 4); }
+
+// alignment.c:219-303
+__device__ int count_matches(const uint32_t* c1, int n1, int q1, int q2,
+                             const uint32_t* c2, int n2, int q3, int q4, int* pmm)
+{
+    int i, j, matches = 0, mm = 0;
+    for (i = 0, j = q1; i < n1; i++) {
+        const int len = cig_len(c1[i]), op = cig_op(c1[i]);
+        if (op != OP_DEL) j += len;
+        if (j < q2) { if (op == OP_EQ) matches += len; else if (op == OP_X) mm += len; }
+        if (j >= q2) {
+            if (op == OP_EQ) matches += q2 - (j - len); else if (op == OP_X) mm += q2 - (j - len);
+            break;
+        }
+    }
+    for (i = 0, j = 0; i < n2; i++) {
+        const int len = cig_len(c2[i]), op = cig_op(c2[i]);
+        if (op != OP_DEL) j += len;
+        if (j >= q3) {
+            if (op == OP_EQ) matches += j - q3; else if (op == OP_X) mm += j - q3;
+            i++; break;
+        }
+    }
+    for (; i < n2; i++) {
+        const int len = cig_len(c2[i]), op = cig_op(c2[i]);
+        if (op != OP_DEL) j += len;
+        if (j < q4) { if (op == OP_EQ) matches += len; else if (op == OP_X) mm += len; }
+        if (j >= q4) {
+            if (op == OP_EQ) matches += q4 - (j - len); else if (op == OP_X) mm += q4 - (j - len);
+            break;
+        }
+    }
+    *pmm = mm;
+    return matches;
+}
+
+// alignment.c:306-339, candidates spread over the lanes of warp 0:
+// arg-max by (matches desc, mismatches asc, i asc) == the reference's first-wins scan with its early exit
+__device__ int best_junction_warp(int q1, int q2, const uint32_t* c1, int n1,
+                                  int q3, int q4, const uint32_t* c2, int n2)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned long long best = 0;
+    for (int base = q3; base <= q2; base += 32) {
+        const int i = base + lane;
+        unsigned long long key = 0;
+        if (i <= q2) {
+            int mm;
+            const int matches = count_matches(c1, n1, q1, i, c2, n2, i, q4, &mm);
+            key = ((unsigned long long)(uint32_t)(matches + 1) << 42) |
+                  ((unsigned long long)(0x1FFFFFu - (uint32_t)mm) << 21) |
+                  (unsigned long long)(0x1FFFFFu - (uint32_t)(i - q3));
+        }
+        key = warp_max_u64(key);
+        best = key > best ? key : best;
+    }
+    return q3 + (int)(0x1FFFFFu - (uint32_t)(best & 0x1FFFFFu));
+}
+
+struct SegWriter {
+    uint32_t* segs; int n; int refindx; int readindx;
+    __device__ void emit(uint32_t c)
+    {
+        const int op = cig_op(c), len = cig_len(c);              // new_readseg, readaln.c:24-99
+        segs[n++] = c;
+        if (op == OP_EQ || op == OP_X) { readindx += len; refindx += len; }
+        else if (op == OP_DEL) refindx += len;
+        else readindx += len;
+    }
+};
+
+// update_readsegs (readaln.c:348-458): returns the number of segment words
+__device__ int stitch_segments(uint32_t* segs, int r1, const uint32_t* c1, int n1, int index,
+                               int q2, int r2, const uint32_t* c2, int n2)
+{
+    SegWriter w{segs, 0, r1, 0};
+    int i, j;
+    for (i = 0, j = 0; i < n1; i++) {
+        const int op = cig_op(c1[i]), len = cig_len(c1[i]);
+        if (op != OP_DEL) j += len;
+        if (j <= index) w.emit(c1[i]);
+        if (j > index) {
+            const int part = index - (j - len);
+            if (part > 0) w.emit(((uint32_t)part << 4) | (uint32_t)op);
+            break;
+        }
+    }
+    int rindex = r2, nextindex = index;
+    if (index >= q2) {
+        int offset = 0;
+        for (i = 0, j = 0; i < n2; i++) {
+            const int op = cig_op(c2[i]), len = cig_len(c2[i]);
+            if (op != OP_DEL) j += len;
+            if (j <= q2) { }
+            else if (j <= index) {
+                if (op != OP_INS) { offset += len; if ((j - len) <= q2) offset -= q2 - (j - len); }
+            } else {
+                if (op != OP_INS && (j - len) <= index) offset += index - (j - len);
+            }
+        }
+        rindex = r2 + offset;
+    } else {
+        w.emit(((uint32_t)(q2 - index) << 4) | OP_INS);
+        nextindex += q2 - index;
+    }
+    if (w.refindx < rindex) w.emit(((uint32_t)(rindex - w.refindx) << 4) | OP_DEL);
+    for (i = 0, j = 0; i < n2; i++) {
+        const int op = cig_op(c2[i]), len = cig_len(c2[i]);
+        if (op != OP_DEL) j += len;
+        if (j > nextindex) { w.emit(((uint32_t)(j - nextindex) << 4) | (uint32_t)op); i++; break; }
+    }
+    for (; i < n2; i++) w.emit(c2[i]);
+    return w.n;
+}
+
+}  // namespace indelgpu

@@ -1,0 +1,171 @@
+// Kernel-level entry points over independent (read, window) tasks: the band-sweep micro-bench
+// (SURVEY.md 8d, D1), the reference-prototype shims and the kernel parity tests.
+#pragma once
+
+#include "kernels.cuh"
+#include "band_dp.cuh"
+
+namespace indelgpu {
+
+struct TaskArgs {
+    DevParams P;
+    int n;
+    const uint8_t* reads; const int64_t* read_off;
+    const uint8_t* refs;  const int64_t* ref_off;
+    const uint32_t* packed;            // 2-bit copy of refs (vote only)
+    const int32_t* anchor_rel;         // vote only
+    int32_t* low; int32_t* up;         // vote: out; align: in
+    int32_t* score; int32_t* ends; int32_t* ncigar; uint32_t* cigar; int cigar_stride;
+    int32_t* script; int script_stride;
+    int* work_counter;
+    unsigned long long* cell_totals;
+    int* error_flag;
+    int max_read, max_numdiag;
+    BandScratch scratch;
+};
+
+__device__ __forceinline__ void bind_smem(Cta& S, unsigned char* smem, int max_read, int max_numdiag)
+{
+    S.L = make_layout(max_read, max_numdiag);
+    S.keys = reinterpret_cast<uint32_t*>(smem + S.L.off_keys);
+    S.vals = reinterpret_cast<uint32_t*>(smem + S.L.off_vals);
+    S.hist = reinterpret_cast<uint32_t*>(smem + S.L.off_hist);
+    S.read = smem + S.L.off_read;
+    S.bits = reinterpret_cast<uint32_t*>(smem + S.L.off_bits);
+    S.psum = reinterpret_cast<int*>(smem + S.L.off_psum);
+    S.cig1 = reinterpret_cast<uint32_t*>(smem + S.L.off_cig1);
+    S.cig2 = reinterpret_cast<uint32_t*>(smem + S.L.off_cig2);
+    S.segs = reinterpret_cast<uint32_t*>(smem + S.L.off_segs);
+}
+
+// find_best_band over n tasks (alignment.c:393-447 with zstart1 = zstart2 = 0)
+__global__ void __launch_bounds__(kThreads)
+vote_tasks_kernel(const __grid_constant__ TaskArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_idx;
+    __shared__ unsigned long long s_red[kWarps];
+    Cta S;
+    bind_smem(S, smem, a.max_read, a.max_numdiag);
+    const int tid = threadIdx.x;
+    for (int s = tid; s < S.L.hist_words; s += kThreads) S.hist[s] = 0;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_idx = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const int idx = s_idx;
+        if (idx >= a.n) break;
+        const int64_t roff = a.read_off[idx], woff = a.ref_off[idx];
+        const int M = (int)(a.read_off[idx + 1] - roff), N = (int)(a.ref_off[idx + 1] - woff);
+        if (M <= 0 || M > a.max_read || N + M + 2 > a.max_numdiag) {
+            if (tid == 0) { a.low[idx] = 0; a.up[idx] = 0; atomicExch(a.error_flag, 1); }
+            continue;
+        }
+        for (int t = tid; t < M; t += kThreads) S.read[t] = a.reads[roff + t];
+        __syncthreads();
+        bool ok;
+        const int low = vote_band(a.P, S, a.packed, woff, N, 0, M, a.anchor_rel[idx], &ok, s_red);
+        if (tid == 0) {
+            if (!ok) { a.low[idx] = 0; a.up[idx] = 0; atomicExch(a.error_flag, 1); }
+            else { a.low[idx] = low; a.up[idx] = low + (M < a.P.k ? 0 : a.P.g); }
+        }
+    }
+}
+
+// local_align + ALIGN + fetch_cigar over n tasks, one warp per task
+__global__ void __launch_bounds__(32)
+align_tasks_kernel(const __grid_constant__ TaskArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_idx;
+    __shared__ int s_tmp[16];
+    Cta S;
+    bind_smem(S, smem, a.max_read, 0);
+    const int lane = threadIdx.x;
+    unsigned long long cells[3] = {0, 0, 0};
+    while (true) {
+        __syncwarp();
+        if (lane == 0) s_idx = atomicAdd(a.work_counter, 1);
+        __syncwarp();
+        const int idx = s_idx;
+        if (idx >= a.n) break;
+        const int64_t roff = a.read_off[idx], woff = a.ref_off[idx];
+        const int M = (int)(a.read_off[idx + 1] - roff), N = (int)(a.ref_off[idx + 1] - woff);
+        const int lo = max(-M, a.low[idx]), hi = min(N, a.up[idx]);       // localalign.c:70-71
+        const int band = hi - lo + 1;
+        const bool bad = M <= 0 || N <= 0 || M > a.max_read || band < 1 ||
+                         (band > 1 && (2 * band > a.scratch.max_band || M > a.scratch.max_rows));
+        if (bad) {
+            if (lane == 0) { a.score[idx] = 0; a.ncigar[idx] = 0; for (int t = 0; t < 4; t++) a.ends[4 * idx + t] = 0; atomicExch(a.error_flag, 1); }
+            continue;
+        }
+        for (int t = lane; t < M; t += 32) S.read[t] = a.reads[roff + t];
+        __syncwarp();
+        const uint8_t* win = a.refs + woff;
+        if (band == 1) align_diag1(a.P, S, win, N, 0, M, lo, S.cig1, s_tmp);
+        else align_banded(a.P, a.scratch, S.read, M, win, N, lo, hi, S.cig1, S.L.ops_cap, s_tmp);
+        const int score = s_tmp[0], n = s_tmp[5];
+        if (lane == 0) {
+            a.score[idx] = score;
+            for (int t = 0; t < 4; t++) a.ends[4 * idx + t] = score > 0 ? s_tmp[1 + t] : 0;   // q1 r1 q2 r2
+            a.ncigar[idx] = score > 0 ? n : 0;
+            cells[0] += (unsigned long long)s_tmp[6]; cells[1] += (unsigned long long)s_tmp[7]; cells[2] += (unsigned long long)s_tmp[8];
+        }
+        if (score > 0 && a.cigar) for (int t = lane; t < min(n, a.cigar_stride); t += 32) a.cigar[(int64_t)idx * a.cigar_stride + t] = S.cig1[t];
+        if (score > 0 && a.script) {
+            int32_t* out = a.script + (int64_t)idx * a.script_stride;
+            if (band == 1) { const int len = s_tmp[3] - s_tmp[1] + 1; for (int t = lane; t < min(len, a.script_stride); t += 32) out[t] = 0; if (lane == 0 && len < a.script_stride) out[len] = 0x7FFFFFFF; }
+            else {
+                const int* Sg = band_script_ptr(a.scratch);
+                const int len = s_tmp[9];
+                for (int t = lane; t < min(len, a.script_stride); t += 32) out[t] = Sg[t];
+                if (lane == 0 && len < a.script_stride) out[len] = 0x7FFFFFFF;
+            }
+        }
+    }
+    if (lane == 0 && (cells[0] | cells[1] | cells[2])) {
+        atomicAdd(a.cell_totals + 0, cells[0]);
+        atomicAdd(a.cell_totals + 1, cells[1]);
+        atomicAdd(a.cell_totals + 2, cells[2]);
+    }
+}
+
+// ALIGN (globalalign.c:333-401) for one pair; the score is the re-scored script
+// (CHECK_SCORE, globalalign.c:311-330, which the reference asserts equal to align()'s value)
+__global__ void global_align_one_kernel(DevParams P, BandScratch scr, const uint8_t* A, const uint8_t* B,
+                                        int M, int N, int low, int up, int* out_script, int* out_meta)
+{
+    if (threadIdx.x != 0) return;
+    int* base = scr.base;
+    const int wb = scr.max_band + 4, wr = scr.max_rows + 2;
+    DcCtx x;
+    x.P = &P; x.A = A; x.B = B; x.cells = 0;
+    x.cc = base; x.dd = base + wb; x.cp = base + 2 * wb; x.dp = base + 3 * wb;
+    int* rows = base + 8 * wb;
+    x.mp[0] = rows; x.mp[1] = rows + wr; x.mp[2] = rows + 2 * wr; x.fp = rows + 3 * wr;
+    x.mt[0] = rows + 4 * wr; x.mt[1] = rows + 5 * wr; x.mt[2] = rows + 6 * wr; x.ft = rows + 7 * wr;
+    x.S = out_script;
+    DcFrame* st = reinterpret_cast<DcFrame*>(rows + 8 * wr + (2 * scr.max_rows + scr.max_band + 16));
+    const int ns = global_align_script(x, st, M, N, low, up);
+    int score = 0, i = 0, j = 0;
+    for (int t = 0; t < ns; t++) {
+        const int op = x.S[t];
+        if (op == 0) { score += (A[i] == B[j]) ? P.match : P.mismatch; i++; j++; }
+        else if (op > 0) { score -= P.G + op * P.H; j += op; }
+        else { score -= P.G - op * P.H; i -= op; }
+    }
+    out_meta[0] = score; out_meta[1] = ns; out_meta[2] = x.cells;
+}
+
+// fetch_cigar (globalalign.c:507-604) for one script
+__global__ void fetch_cigar_one_kernel(const uint8_t* A, const uint8_t* B, int M, int N, const int* S,
+                                       int AP, int readlength, uint32_t* cig, int* out_meta)
+{
+    if (threadIdx.x != 0) return;
+    const int n = script_to_cigar(A, B, M, N, S, AP, readlength, cig);
+    int mm = 0;
+    for (int t = 0; t < n; t++) if ((cig[t] & 15u) == OP_X) mm += (int)(cig[t] >> 4);
+    out_meta[0] = n; out_meta[1] = mm;
+}
+
+}  // namespace indelgpu

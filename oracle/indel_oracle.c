@@ -757,3 +757,20 @@ void orc_realign_read(const orc_params* p, const char* refseq, int reflength,
     count_evidence(o);
     o->status = ORC_ST_SPLIT;
 }
+
+/* batch loop for bench.py's cpu_baseline "port" leg (used only when oracle/_ref is absent) */
+long orc_realign_batch(const orc_params* p, const char* refseq, int reflength, int n,
+                       const char* reads, const long long* off, const int* position,
+                       const int* range1, int* nseg_out)
+{
+    long total = 0;
+    orc_result* o = xalloc(sizeof(orc_result));
+    for (int i = 0; i < n; i++) {
+        orc_realign_read(p, refseq, reflength, position[i], range1[i], reads + off[i],
+                         (int)(off[i + 1] - off[i]), o, NULL);
+        if (nseg_out) nseg_out[i] = o->nseg;
+        total += o->nseg;
+    }
+    free(o);
+    return total;
+}

@@ -109,6 +109,10 @@ void orc_realign_read(const orc_params* p, const char* refseq, int reflength,
                       int position, int range1, const char* read, int readlength,
                       orc_result* out, orc_cells* cells);
 
+long orc_realign_batch(const orc_params* p, const char* refseq, int reflength, int n,
+                       const char* reads, const long long* off, const int* position,
+                       const int* range1, int* nseg_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,6 +134,44 @@ int refshim_realign(char* refseq, int reflength, int position, int range1, char*
        lives in evidence.c but needs isused bookkeeping) */
     return n;
 }
+
+/* CPU-baseline loops for bench.py: the reference's own code over a batch, one call.
+ * as_shipped = 1 goes through attempt_pe_alignment itself, i.e. pays the per-read
+ * strlen(contig) of alignment.c:771 (refseq must be NUL-terminated);
+ * as_shipped = 0 calls attempt_diagonal_alignments with the windows precomputed (function level). */
+long refshim_realign_batch(char* refseq, int reflength, int n, const char* reads, const long long* off,
+                           const int* position, const int* range1, int as_shipped, int* nseg_out)
+{
+    long total = 0;
+    char* sequences[1] = { refseq };
+    for (int i = 0; i < n; i++) {
+        int len = (int)(off[i + 1] - off[i]);
+        char* read = ckallocz(len + 1);
+        memcpy(read, reads + off[i], len);
+        int ns;
+        if (as_shipped) {
+            readaln rln; memset(&rln, 0, sizeof(rln));
+            rln.qname = "r"; rln.tid = -1; rln.strand = '+'; rln.index = '1'; rln.qual = 60;
+            uint32_t cigar = ((uint32_t)len << BAM_CIGAR_SHIFT) + BAM_CSOFT_CLIP;
+            int refindx = 0, readindx = 0;
+            rln.segments = new_readseg(read, cigar, &refindx, &readindx);
+            int range[2] = { 0, range1[i] };
+            cap_n = -1; cap_armed = 1;
+            evidence* ev = attempt_pe_alignment(sequences, 0, position[i], range, &rln);
+            cap_armed = 0;
+            ns = cap_n < 0 ? 0 : cap_n;
+            if (cap_n < 0 && rln.segments) free_readsegs(&rln.segments);
+            while (ev) { evidence* nx = ev->next; ev->isused = TRUE; ev->next = NULL; free_used_evidence(ev); ev = nx; }
+        } else {
+            int sop[REFSHIM_MAXSEG], sl[REFSHIM_MAXSEG], ss[REFSHIM_MAXSEG], se[REFSHIM_MAXSEG], nev;
+            ns = refshim_realign(refseq, reflength, position[i], range1[i], read, sop, sl, ss, se, REFSHIM_MAXSEG, &nev);
+        }
+        if (nseg_out) nseg_out[i] = ns;
+        total += ns;
+        ckfree(read);
+    }
+    return total;
+}
 #endif /* !REFSHIM_TRACE */
 
 #ifdef REFSHIM_TRACE
