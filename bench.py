@@ -270,7 +270,8 @@ def run_ours(a, rank, world, local_rank):
     b = _lib.Batch(n, d_reads.data_ptr(), d_off.data_ptr(), d_tid.data_ptr(), d_pos.data_ptr(), d_rng.data_ptr())
     r = _lib.Result(d_status.data_ptr(), d_nseg.data_ptr(), d_rstart.data_ptr(), d_segoff.data_ptr(),
                     d_segs.data_ptr(), cap, 0, None, None, None, 0)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)      # a real (non-default) stream: the library treats NULL as "use mine"
+    torch.cuda.set_stream(stream)
 
     def step_device():
         rc = L.indelgpu_realign_batch_device(R._ctx, C.byref(b), M, max_range, C.byref(r),

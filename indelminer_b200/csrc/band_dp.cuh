@@ -11,7 +11,15 @@
 
 #include "kernels.cuh"
 
+// IG_HD: the serial pieces are plain C++ and are also compiled for the host so that
+// tests/host_harness can exercise this exact source without a GPU (test only; the library
+// never calls them on the host).
+#define IG_HD __host__ __device__
+
 namespace indelgpu {
+
+IG_HD inline int ig_min(int a, int b) { return a < b ? a : b; }
+IG_HD inline int ig_max(int a, int b) { return a > b ? a : b; }
 
 // global-memory scratch, one slice per CTA (only warp 0 of a CTA aligns)
 struct BandScratch {
@@ -49,22 +57,22 @@ struct DcCtx {
     int cells;
 };
 
-__device__ __forceinline__ void put_del(DcCtx& x, int k)      // globalalign.c:40-46
+IG_HD inline void put_del(DcCtx& x, int k)      // globalalign.c:40-46
 {
     if (x.last < 0) { x.S[x.ns - 1] -= k; x.last = x.S[x.ns - 1]; }
     else { x.S[x.ns++] = -k; x.last = -k; }
 }
-__device__ __forceinline__ void put_ins(DcCtx& x, int k)      // globalalign.c:48-54
+IG_HD inline void put_ins(DcCtx& x, int k)      // globalalign.c:48-54
 {
     if (x.last > 0) { x.S[x.ns - 1] += k; x.last = x.S[x.ns - 1]; }
     else { x.S[x.ns++] = k; x.last = k; }
 }
-__device__ __forceinline__ void put_rep(DcCtx& x) { x.S[x.ns++] = 0; x.last = 0; }
+IG_HD inline void put_rep(DcCtx& x) { x.S[x.ns++] = 0; x.last = 0; }
 
 // One sweep of align() (globalalign.c:95-258): fills the crossing list, returns through f the
 // first crossing row (k = r, or -1), its successor l and type kt.  a1/b1 index so that a1[1] is
 // the first symbol.
-__device__ void dc_sweep(DcCtx& x, DcFrame& f)
+IG_HD inline void dc_sweep(DcCtx& x, DcFrame& f)
 {
     const int g = x.P->G, h = x.P->H, m = g + h;
     const uint8_t* a1 = x.A + f.a - 1;
@@ -170,7 +178,7 @@ __device__ void dc_sweep(DcCtx& x, DcFrame& f)
     f.t2 = up - rmid - 1; f.t3 = low - rmid + 1;
 }
 
-__device__ __forceinline__ void dc_push(DcFrame* st, int& sp, int a, int b, int M, int N,
+IG_HD inline void dc_push(DcFrame* st, int& sp, int a, int b, int M, int N,
                                         int low, int up, int tb, int te)
 {
     DcFrame& f = st[sp++];
@@ -178,7 +186,7 @@ __device__ __forceinline__ void dc_push(DcFrame* st, int& sp, int a, int b, int 
 }
 
 // align() of globalalign.c:66-307 with the recursion unrolled into frames.
-__device__ void dc_align(DcCtx& x, DcFrame* st, int a0, int b0, int M0, int N0, int low0, int up0)
+IG_HD inline void dc_align(DcCtx& x, DcFrame* st, int a0, int b0, int M0, int N0, int low0, int up0)
 {
     int sp = 0;
     dc_push(st, sp, a0, b0, M0, N0, low0, up0, 0, 0);
@@ -197,8 +205,8 @@ __device__ void dc_align(DcCtx& x, DcFrame* st, int a0, int b0, int M0, int N0, 
                 else          dc_push(st, sp, f.a, f.b, f.M, f.N, f.low, rmid - 1, f.tb, f.te);
                 break;
             }
-            if (rmid < 0)      { f.stage = 1; dc_push(st, sp, f.a, f.b, r - 1, r + rmid, rmid + 1, min(f.up, r + rmid), f.tb, 1); }
-            else if (rmid > 0) { f.stage = 2; dc_push(st, sp, f.a, f.b, r, r + rmid - 1, max(-r, f.low), rmid - 1, f.tb, 2); }
+            if (rmid < 0)      { f.stage = 1; dc_push(st, sp, f.a, f.b, r - 1, r + rmid, rmid + 1, ig_min(f.up, r + rmid), f.tb, 1); }
+            else if (rmid > 0) { f.stage = 2; dc_push(st, sp, f.a, f.b, r, r + rmid - 1, ig_max(-r, f.low), rmid - 1, f.tb, 2); }
             else f.stage = 3;
             break;
         }
@@ -210,21 +218,21 @@ __device__ void dc_align(DcCtx& x, DcFrame* st, int a0, int b0, int M0, int N0, 
                 if (f.kt == 0) { put_rep(x); f.k = f.l; f.l = x.fp[f.k]; f.kt = x.ft[f.k]; }
                 else if (f.kt == 1) {
                     put_ins(x, 1); f.stage = 4;
-                    dc_push(st, sp, f.a + f.k, f.b + f.k + f.rmid + 1, t1, t1, 0, min(t1, f.t2), 2, 1);
+                    dc_push(st, sp, f.a + f.k, f.b + f.k + f.rmid + 1, t1, t1, 0, ig_min(t1, f.t2), 2, 1);
                 } else {
                     put_del(x, 1); f.stage = 5;
-                    dc_push(st, sp, f.a + f.k + 1, f.b + f.k + f.rmid, t1, t1, max(-t1, f.t3), 0, 1, 2);
+                    dc_push(st, sp, f.a + f.k + 1, f.b + f.k + f.rmid, t1, t1, ig_max(-t1, f.t3), 0, 1, 2);
                 }
             } else {                                         // :296-304
                 const int k = f.k, rmid = f.rmid;
                 if (f.N - f.M > rmid) {
                     put_ins(x, 1); f.stage = 6;
                     const int t1 = k + rmid + 1;
-                    dc_push(st, sp, f.a + k, f.b + t1, f.M - k, f.N - t1, 0, min(f.N - t1, f.t2), 2, f.te);
+                    dc_push(st, sp, f.a + k, f.b + t1, f.M - k, f.N - t1, 0, ig_min(f.N - t1, f.t2), 2, f.te);
                 } else if (f.N - f.M < rmid) {
                     put_del(x, 1); f.stage = 6;
                     const int t1 = f.M - (k + 1);
-                    dc_push(st, sp, f.a + k + 1, f.b + k + rmid, t1, f.N - (k + rmid), max(-t1, f.t3), 0, 1, f.te);
+                    dc_push(st, sp, f.a + k + 1, f.b + k + rmid, t1, f.N - (k + rmid), ig_max(-t1, f.t3), 0, 1, f.te);
                 } else sp--;
             }
             break;
@@ -237,20 +245,20 @@ __device__ void dc_align(DcCtx& x, DcFrame* st, int a0, int b0, int M0, int N0, 
 }
 
 // ALIGN (globalalign.c:333-401): A, B 0-based first symbols.  Returns the number of script entries.
-__device__ int global_align_script(DcCtx& x, DcFrame* st, int M, int N, int low, int up)
+IG_HD inline int global_align_script(DcCtx& x, DcFrame* st, int M, int N, int low, int up)
 {
     x.ns = 0; x.last = 0;
-    low = min(max(-M, low), min(N - M, 0));                  // :347-348
-    up  = max(min(N, up), max(N - M, 0));
+    low = ig_min(ig_max(-M, low), ig_min(N - M, 0));                  // :347-348
+    up  = ig_max(ig_min(N, up), ig_max(N - M, 0));
     if (N <= 0) { if (M > 0) put_del(x, M); }
     else if (M <= 0) put_ins(x, N);
     else if (up - low + 1 <= 1) { for (int i = 0; i < M; i++) put_rep(x); }
-    else dc_align(x, st, 1, 1, M, N, low, up);
+    else dc_align(x, st, 0, 0, M, N, low, up);           // views start one before the first symbol
     return x.ns;
 }
 
 // fetch_cigar (globalalign.c:507-604): A, B 0-based first ALIGNED symbols
-__device__ int script_to_cigar(const uint8_t* A, const uint8_t* B, int M, int N, const int* S,
+IG_HD inline int script_to_cigar(const uint8_t* A, const uint8_t* B, int M, int N, const int* S,
                                int AP, int readlength, uint32_t* cig)
 {
     int n = 0, i = 0, j = 0;
@@ -273,117 +281,126 @@ __device__ int script_to_cigar(const uint8_t* A, const uint8_t* B, int M, int N,
     return n;
 }
 
-// warp-wide entry: local_align + ALIGN + fetch_cigar on a band of >= 2 diagonals.
-// `low`/`up` are already clamped (localalign.c:70-71).  Version 1: lane 0 runs the sweeps
-// sequentially (exact by construction); the other lanes wait.
-// s_out: score, q1, r1, q2, r2 (1-based inclusive, slice/window relative), ncigar, cells fwd, rev, glob, nscript
-__device__ void align_banded(const DevParams& P, const BandScratch& scr, const uint8_t* read, int M,
-                             const uint8_t* __restrict__ win, int N, int low, int up,
-                             uint32_t* cig, int ops_cap, int* s_out)
+// local_align + ALIGN + fetch_cigar on a band of >= 2 diagonals, executed by ONE thread.
+// `low`/`up` are already clamped (localalign.c:70-71); `base` is this CTA's scratch slice.
+// out: score, q1, r1, q2, r2 (1-based inclusive, slice/window relative), ncigar, cells fwd, rev, glob, nscript
+IG_HD inline void align_banded_serial(const DevParams& P, int* base, int max_band, int max_rows,
+                                      const uint8_t* read, int M, const uint8_t* win, int N,
+                                      int low, int up, uint32_t* cig, int* out)
 {
-    (void)ops_cap;
-    if ((threadIdx.x & 31) == 0) {
-        const int G = P.G, H = P.H, m = G + H;
-        const int band = up - low + 1;
-        int* base = scr.base + (long long)blockIdx.x * scr.stride;
-        const int wb = scr.max_band + 4, wr = scr.max_rows + 2;
-        DcCtx x;
-        x.P = &P; x.A = read; x.B = win; x.cells = 0;
-        x.cc = base; x.dd = base + wb; x.cp = base + 2 * wb; x.dp = base + 3 * wb;
-        int* Hp = base + 4 * wb; int* Dp = base + 5 * wb; int* Hn = base + 6 * wb; int* Dn = base + 7 * wb;
-        int* rows = base + 8 * wb;
-        x.mp[0] = rows; x.mp[1] = rows + wr; x.mp[2] = rows + 2 * wr; x.fp = rows + 3 * wr;
-        x.mt[0] = rows + 4 * wr; x.mt[1] = rows + 5 * wr; x.mt[2] = rows + 6 * wr; x.ft = rows + 7 * wr;
-        x.S = rows + 8 * wr;
-        DcFrame* st = reinterpret_cast<DcFrame*>(x.S + (2 * scr.max_rows + scr.max_band + 16));
+    const int G = P.G, H = P.H, m = G + H;
+    const int band = up - low + 1;
+    const int wb = max_band + 4, wr = max_rows + 2;
+    DcCtx x;
+    x.P = &P; x.A = read; x.B = win; x.cells = 0; x.ns = 0; x.last = 0;
+    x.cc = base; x.dd = base + wb; x.cp = base + 2 * wb; x.dp = base + 3 * wb;
+    int* Hp = base + 4 * wb; int* Dp = base + 5 * wb; int* Hn = base + 6 * wb; int* Dn = base + 7 * wb;
+    int* rows = base + 8 * wb;
+    x.mp[0] = rows; x.mp[1] = rows + wr; x.mp[2] = rows + 2 * wr; x.fp = rows + 3 * wr;
+    x.mt[0] = rows + 4 * wr; x.mt[1] = rows + 5 * wr; x.mt[2] = rows + 6 * wr; x.ft = rows + 7 * wr;
+    x.S = rows + 8 * wr;
+    DcFrame* st = reinterpret_cast<DcFrame*>(x.S + (2 * max_rows + max_band + 16));
 #define AT(arr, t) ((arr)[(t) + 1])
-        // forward (localalign.c:82-131)
-        const int si = max(0, -up), ei = min(M, N - low);
-        for (int t = -1; t <= band; t++) { AT(Hp, t) = kNeg; AT(Dp, t) = kNeg; }
-        for (int t = 0; t < band; t++) {
-            const int j = si + low + t;
-            if (j >= 0 && j <= N) { AT(Hp, t) = 0; AT(Dp, t) = -G; }
+    // forward (localalign.c:82-131)
+    const int si = ig_max(0, -up), ei = ig_min(M, N - low);
+    for (int t = -1; t <= band; t++) { AT(Hp, t) = kNeg; AT(Dp, t) = kNeg; }
+    for (int t = 0; t < band; t++) {
+        const int j = si + low + t;
+        if (j >= 0 && j <= N) { AT(Hp, t) = 0; AT(Dp, t) = -G; }
+    }
+    int best = 0, endi = si, endj = si + low, cf = 0, cr = 0;
+    for (int i = si + 1; i <= ei; i++) {
+        const int tlo = ig_max(0, -i - low), thi = ig_min(band - 1, N - i - low);
+        for (int t = -1; t <= band; t++) { AT(Hn, t) = kNeg; AT(Dn, t) = kNeg; }
+        int e = kNeg, left = kNeg;
+        const uint8_t ai = read[i - 1];
+        for (int t = tlo; t <= thi; t++) {
+            const int j = i + low + t;
+            const int d = ig_max(AT(Hp, t + 1) - m, AT(Dp, t + 1) - H);
+            int c;
+            if (j == 0) c = d;
+            else {
+                c = AT(Hp, t) + (ai == win[j - 1] ? P.match : P.mismatch);
+                if (t > tlo) { e = ig_max(left - m, e - H); if (e > c) c = e; }
+                if (d > c) c = d;
+            }
+            if (c < 0) c = 0;
+            if (t == tlo) e = c - G;
+            left = c;
+            AT(Hn, t) = c; AT(Dn, t) = d;
+            if (c > best) { best = c; endi = i; endj = j; }
         }
-        int best = 0, endi = si, endj = si + low, cf = 0, cr = 0;
-        for (int i = si + 1; i <= ei; i++) {
-            const int tlo = max(0, -i - low), thi = min(band - 1, N - i - low);
+        cf += thi - tlo + 1;
+        int* tmp = Hp; Hp = Hn; Hn = tmp; tmp = Dp; Dp = Dn; Dn = tmp;
+    }
+    // reverse (localalign.c:132-176)
+    int starti = 0, startj = 0; bool found = false;
+    if (best > 0) {
+        const int tend = (endj - endi) - low;
+        for (int t = -1; t <= band; t++) { AT(Hp, t) = kNeg; AT(Dp, t) = kNeg; }
+        {
+            const int tl = ig_max(0, -endi - low);
+            AT(Hp, tend) = 0; AT(Dp, tend) = -G;
+            int acc = -G;
+            for (int t = tend - 1; t >= tl; t--) { acc -= H; AT(Hp, t) = acc; AT(Dp, t) = acc - G; }
+        }
+        for (int i = endi; i >= 1 && !found; i--) {
             for (int t = -1; t <= band; t++) { AT(Hn, t) = kNeg; AT(Dn, t) = kNeg; }
-            int e = kNeg, left = kNeg;
+            const int thi = ig_min(band - 1, tend + (endi - i) + 1);
+            const int tlo = ig_max(0, 1 - i - low);
+            int e = kNeg, right = kNeg;
             const uint8_t ai = read[i - 1];
-            for (int t = tlo; t <= thi; t++) {
+            for (int t = thi; t >= tlo; t--) {
                 const int j = i + low + t;
-                const int d = max(AT(Hp, t + 1) - m, AT(Dp, t + 1) - H);
+                const int d = ig_max(AT(Hp, t - 1) - m, AT(Dp, t - 1) - H);
                 int c;
-                if (j == 0) c = d;
-                else {
+                if (t == thi) {
+                    c = (j <= N) ? AT(Hp, t) + (ai == win[j - 1] ? P.match : P.mismatch) : AT(Hp, t - 1) - m;
+                    if (d > c) c = d;
+                    e = c - G;
+                } else {
+                    e = ig_max(right - m, e - H);
                     c = AT(Hp, t) + (ai == win[j - 1] ? P.match : P.mismatch);
-                    if (t > tlo) { e = max(left - m, e - H); if (e > c) c = e; }
+                    if (e > c) c = e;
                     if (d > c) c = d;
                 }
-                if (c < 0) c = 0;
-                if (t == tlo) e = c - G;
-                left = c;
+                right = c;
                 AT(Hn, t) = c; AT(Dn, t) = d;
-                if (c > best) { best = c; endi = i; endj = j; }
+                cr++;
+                if (c == best) { starti = i; startj = j; found = true; break; }
             }
-            cf += thi - tlo + 1;
             int* tmp = Hp; Hp = Hn; Hn = tmp; tmp = Dp; Dp = Dn; Dn = tmp;
         }
-        // reverse (localalign.c:132-176)
-        int starti = 0, startj = 0; bool found = false;
-        if (best > 0) {
-            const int tend = (endj - endi) - low;
-            for (int t = -1; t <= band; t++) { AT(Hp, t) = kNeg; AT(Dp, t) = kNeg; }
-            {
-                const int tl = max(0, -endi - low);
-                AT(Hp, tend) = 0; AT(Dp, tend) = -G;
-                int acc = -G;
-                for (int t = tend - 1; t >= tl; t--) { acc -= H; AT(Hp, t) = acc; AT(Dp, t) = acc - G; }
-            }
-            for (int i = endi; i >= 1 && !found; i--) {
-                for (int t = -1; t <= band; t++) { AT(Hn, t) = kNeg; AT(Dn, t) = kNeg; }
-                const int thi = min(band - 1, tend + (endi - i) + 1);
-                const int tlo = max(0, 1 - i - low);
-                int e = kNeg, right = kNeg;
-                const uint8_t ai = read[i - 1];
-                for (int t = thi; t >= tlo; t--) {
-                    const int j = i + low + t;
-                    const int d = max(AT(Hp, t - 1) - m, AT(Dp, t - 1) - H);
-                    int c;
-                    if (t == thi) {
-                        c = (j <= N) ? AT(Hp, t) + (ai == win[j - 1] ? P.match : P.mismatch) : AT(Hp, t - 1) - m;
-                        if (d > c) c = d;
-                        e = c - G;
-                    } else {
-                        e = max(right - m, e - H);
-                        c = AT(Hp, t) + (ai == win[j - 1] ? P.match : P.mismatch);
-                        if (e > c) c = e;
-                        if (d > c) c = d;
-                    }
-                    right = c;
-                    AT(Hn, t) = c; AT(Dn, t) = d;
-                    cr++;
-                    if (c == best) { starti = i; startj = j; found = true; break; }
-                }
-                int* tmp = Hp; Hp = Hn; Hn = tmp; tmp = Dp; Dp = Dn; Dn = tmp;
-            }
-        }
-#undef AT
-        bool none = best <= 0 || !found || starti > M || startj > N ||
-                    endi - starti == 0 || endj - startj == 0;            // localalign.c:180-193
-        int n = 0;
-        if (!none) {
-            const int M2 = endi - starti + 1, N2 = endj - startj + 1;
-            x.A = read + starti - 1; x.B = win + startj - 1;
-            global_align_script(x, st, M2, N2, low - (startj - starti), up - (startj - starti));
-            n = script_to_cigar(x.A, x.B, M2, N2, x.S, starti, M, cig);
-        }
-        s_out[0] = none ? 0 : best;       // ALIGN's score equals the local optimum
-        s_out[1] = starti; s_out[2] = startj; s_out[3] = endi; s_out[4] = endj;
-        s_out[5] = n; s_out[6] = cf; s_out[7] = cr; s_out[8] = none ? 0 : x.cells;
-        s_out[9] = none ? 0 : x.ns;       // script entries, left at band_script_ptr()
     }
+#undef AT
+    const bool none = best <= 0 || !found || starti > M || startj > N ||
+                      endi - starti == 0 || endj - startj == 0;            // localalign.c:180-193
+    int n = 0;
+    if (!none) {
+        const int M2 = endi - starti + 1, N2 = endj - startj + 1;
+        x.A = read + starti - 1; x.B = win + startj - 1;
+        global_align_script(x, st, M2, N2, low - (startj - starti), up - (startj - starti));
+        n = script_to_cigar(x.A, x.B, M2, N2, x.S, starti, M, cig);
+    }
+    out[0] = none ? 0 : best;         // ALIGN's score equals the local optimum
+    out[1] = starti; out[2] = startj; out[3] = endi; out[4] = endj;
+    out[5] = n; out[6] = cf; out[7] = cr; out[8] = none ? 0 : x.cells;
+    out[9] = none ? 0 : x.ns;         // script entries, left at band_script_ptr()
+}
+
+#ifdef __CUDACC__
+// warp-wide entry.  Version 1: lane 0 runs the sweeps sequentially (exact by construction);
+// the other lanes wait.
+__device__ inline void align_banded(const DevParams& P, const BandScratch& scr, const uint8_t* read, int M,
+                                    const uint8_t* __restrict__ win, int N, int low, int up,
+                                    uint32_t* cig, int ops_cap, int* s_out)
+{
+    (void)ops_cap;
+    if ((threadIdx.x & 31) == 0)
+        align_banded_serial(P, scr.base + (long long)blockIdx.x * scr.stride, scr.max_band, scr.max_rows,
+                            read, M, win, N, low, up, cig, s_out);
     __syncwarp();
 }
+#endif
 
 }  // namespace indelgpu

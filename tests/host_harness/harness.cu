@@ -1,0 +1,26 @@
+// TEST ONLY: runs the serial (one-thread) pieces of the device source on the host so that the
+// divide-and-conquer control flow can be checked against the oracle without a GPU.  The library
+// itself never executes these functions on the CPU.
+#include <vector>
+
+#include "../../indelminer_b200/csrc/kernels.cuh"
+#include "../../indelminer_b200/csrc/band_dp.cuh"
+
+using namespace indelgpu;
+
+extern "C" int hh_band_align(const int* prm, const uint8_t* read, int M, const uint8_t* win, int N,
+                             int low, int up, int* out10, uint32_t* cig, int* script, int script_cap)
+{
+    DevParams P;
+    P.k = prm[0]; P.g = prm[1]; P.maxdel = prm[2]; P.ethr = prm[3];
+    P.match = prm[4]; P.mismatch = prm[5]; P.G = prm[6]; P.H = prm[7]; P.kmask = 0;
+    const int lo = low > -M ? low : -M, hi = up < N ? up : N;
+    const int band = hi - lo + 1;
+    if (band < 2) return -1;
+    const int mb = 2 * band;
+    std::vector<int> scratch((size_t)band_scratch_ints(mb, M));
+    align_banded_serial(P, scratch.data(), mb, M, read, M, win, N, lo, hi, cig, out10);
+    const int* S = scratch.data() + 8 * (mb + 4) + 8 * (M + 2);
+    for (int t = 0; t < out10[9] && t < script_cap; t++) script[t] = S[t];
+    return 0;
+}
