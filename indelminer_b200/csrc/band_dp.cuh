@@ -21,7 +21,7 @@ namespace indelgpu {
 IG_HD inline int ig_min(int a, int b) { return a < b ? a : b; }
 IG_HD inline int ig_max(int a, int b) { return a > b ? a : b; }
 
-// global-memory scratch, one slice per CTA (only warp 0 of a CTA aligns)
+// global-memory scratch, one slice per aligning warp
 struct BandScratch {
     int* base;
     long long stride;        // ints per CTA
@@ -35,9 +35,9 @@ __host__ __device__ inline long long band_scratch_ints(int max_band, int max_row
     return 8LL * (max_band + 4) + 8LL * (max_rows + 2) + (2LL * max_rows + max_band + 16) + 40 * 16;
 }
 
-__device__ __forceinline__ const int* band_script_ptr(const BandScratch& scr)
+__device__ __forceinline__ const int* band_script_ptr(const BandScratch& scr, int slot)
 {
-    return scr.base + (long long)blockIdx.x * scr.stride + 8 * (scr.max_band + 4) + 8 * (scr.max_rows + 2);
+    return scr.base + (long long)slot * scr.stride + 8 * (scr.max_band + 4) + 8 * (scr.max_rows + 2);
 }
 
 struct DcFrame {
@@ -391,13 +391,13 @@ IG_HD inline void align_banded_serial(const DevParams& P, int* base, int max_ban
 #ifdef __CUDACC__
 // warp-wide entry.  Version 1: lane 0 runs the sweeps sequentially (exact by construction);
 // the other lanes wait.
-__device__ inline void align_banded(const DevParams& P, const BandScratch& scr, const uint8_t* read, int M,
+__device__ inline void align_banded(const DevParams& P, const BandScratch& scr, int slot, const uint8_t* read, int M,
                                     const uint8_t* __restrict__ win, int N, int low, int up,
                                     uint32_t* cig, int ops_cap, int* s_out)
 {
     (void)ops_cap;
     if ((threadIdx.x & 31) == 0)
-        align_banded_serial(P, scr.base + (long long)blockIdx.x * scr.stride, scr.max_band, scr.max_rows,
+        align_banded_serial(P, scr.base + (long long)slot * scr.stride, scr.max_band, scr.max_rows,
                             read, M, win, N, low, up, cig, s_out);
     __syncwarp();
 }

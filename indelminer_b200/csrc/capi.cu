@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -216,6 +217,29 @@ extern "C" int64_t indelgpu_seg_bound(int32_t n, int64_t total_read_bases)
     return 2 * total_read_bases + 8LL * n + 16;
 }
 
+
+// Persistent warp-per-read kernels: pick the CTA size that puts the most warps on an SM given the
+// per-warp shared-memory slice.
+template <class Kern>
+static int plan_warps(indelgpu_ctx* c, Kern kern, int bytes_per_warp, int* warps_per_cta, int* ctas_per_sm)
+{
+    static const int cand[] = {16, 12, 8, 7, 6, 5, 4, 3, 2, 1};
+    int best = 0;
+    *warps_per_cta = 0; *ctas_per_sm = 0;
+    for (int w : cand) {
+        const long long smem = (long long)w * bytes_per_warp;
+        if (smem > c->max_smem_optin) continue;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, w * 32, (size_t)smem));
+        if (occ * w > best) { best = occ * w; *warps_per_cta = w; *ctas_per_sm = occ; }
+    }
+    if (best == 0) return fail(INDELGPU_ELIMIT, "window/read sizes need %d bytes of shared memory per warp (limit %d): range1 + maxdelsize or the read length is too large",
+                               bytes_per_warp, c->max_smem_optin);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, *warps_per_cta * bytes_per_warp));
+    return 0;
+}
+
 static int ensure_scratch(indelgpu_ctx* c, int blocks, int max_read, BandScratch* out)
 {
     out->base = nullptr; out->stride = 0; out->max_band = 0; out->max_rows = 0;
@@ -235,16 +259,14 @@ static int launch_realign(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_r
     const long long nd = 2LL * ((long long)max_range1 + c->P.maxdel) + max_read + 2;
     if (nd > (1 << 20)) return fail(INDELGPU_ELIMIT, "window of %lld diagonals exceeds the kernel limit", nd);
     const int max_numdiag = (int)nd;
-    const SmemLayout L = make_layout(max_read, max_numdiag);
-    if (L.total > c->max_smem_optin - 1024)
-        return fail(INDELGPU_ELIMIT, "window/read sizes need %d bytes of shared memory per CTA (limit %d): range1 + maxdelsize too large",
-                    L.total, c->max_smem_optin - 1024);
-    auto kern = c->P.g > 0 ? realign_kernel<true> : realign_kernel<false>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, L.total));
-    if (occ < 1) return fail(INDELGPU_ELIMIT, "realign kernel does not fit on an SM");
-    const int blocks = (int)std::min<long long>((long long)c->sms * occ, std::max(1, d_in->n));
+    const bool banded = c->P.g > 0;
+    const WarpLayout L = make_warp_layout(c->P, max_read, max_numdiag, banded ? 1 : 0);
+    auto kern = banded ? (L.direct ? realign_kernel<true, true> : realign_kernel<true, false>)
+                       : (L.direct ? realign_kernel<false, true> : realign_kernel<false, false>);
+    int wpc = 0, occ = 0;
+    if (int rc = plan_warps(c, kern, L.total, &wpc, &occ)) return rc;
+    const int blocks = (int)std::min<long long>((long long)c->sms * occ, std::max(1, (d_in->n + wpc - 1) / wpc));
+    if (((uintptr_t)d_in->read_bases & 15) != 0) return fail(INDELGPU_EINVAL, "read_bases must be 16-byte aligned on the device (TMA bulk copies)");
 
     RealignArgs a;
     a.P = c->P;
@@ -257,11 +279,11 @@ static int launch_realign(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_r
     a.detail = d_out->detail; a.cigar1 = d_out->cigar1; a.cigar2 = d_out->cigar2; a.cigar_stride = d_out->cigar_stride;
     a.work_counter = ctr_work(c); a.cell_totals = ctr_cells(c); a.error_flag = ctr_err(c);
     a.max_read = max_read; a.max_numdiag = max_numdiag;
-    if (ensure_scratch(c, blocks, max_read, &a.scratch)) return INDELGPU_ENOMEM;
+    if (ensure_scratch(c, blocks * wpc, max_read, &a.scratch)) return INDELGPU_ENOMEM;
 
     CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
     if (d_seg_count != ctr_segs(c)) CU(cudaMemsetAsync(d_seg_count, 0, 8, st));
-    kern<<<blocks, kThreads, L.total, st>>>(a);
+    kern<<<blocks, wpc * 32, (size_t)wpc * L.total, st>>>(a);
     c->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -357,6 +379,7 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
     unsigned long long segcount; int err;
     memcpy(&segcount, (char*)c->pinned_small + 8, 8);
     memcpy(&err, (char*)c->pinned_small + 40, 4);
+    if (err == 3) return fail(INDELGPU_ECUDA, "a TMA bulk copy never completed (mbarrier wait timed out)");
     if (err == 2 || (int64_t)segcount > segcap) return fail(INDELGPU_ELIMIT, "segment buffer too small: need %llu words, have %lld", segcount, (long long)segcap);
     o->seg_count = (int64_t)segcount;
     if (segcount) CU(cudaMemcpyAsync(o->segs, dout.segs, 4 * (size_t)segcount, cudaMemcpyDeviceToHost, st));
@@ -414,12 +437,10 @@ extern "C" int indelgpu_find_best_band_batch(indelgpu_ctx* c, int32_t n, const u
     if (pack_device(c, c->t_refs.as<uint8_t>(), c->t_packed.as<uint32_t>(), words)) return INDELGPU_ECUDA;
 
     const int max_numdiag = max_win + max_read + 4;
-    const SmemLayout L = make_layout(max_read, max_numdiag);
-    if (L.total > c->max_smem_optin - 1024) return fail(INDELGPU_ELIMIT, "window too large for shared memory (%d bytes)", L.total);
-    CU(cudaFuncSetAttribute(vote_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vote_tasks_kernel, kThreads, L.total));
-    if (occ < 1) return fail(INDELGPU_ELIMIT, "vote kernel does not fit on an SM");
+    const WarpLayout L = make_warp_layout(c->P, max_read, max_numdiag, 0);
+    auto vkern = L.direct ? vote_tasks_kernel<true> : vote_tasks_kernel<false>;
+    int wpc = 0, occ = 0;
+    if (int rc2 = plan_warps(c, vkern, L.total, &wpc, &occ)) return rc2;
     TaskArgs a; memset(&a, 0, sizeof(a));
     a.P = c->P; a.n = n;
     a.reads = c->t_reads.as<uint8_t>(); a.read_off = c->t_roff.as<int64_t>();
@@ -429,8 +450,8 @@ extern "C" int indelgpu_find_best_band_batch(indelgpu_ctx* c, int32_t n, const u
     a.work_counter = ctr_work(c); a.cell_totals = ctr_cells(c); a.error_flag = ctr_err(c);
     a.max_read = max_read; a.max_numdiag = max_numdiag;
     CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
-    const int blocks = (int)std::min<long long>((long long)c->sms * occ, n);
-    vote_tasks_kernel<<<blocks, kThreads, L.total, st>>>(a);
+    const int blocks = (int)std::min<long long>((long long)c->sms * occ, (n + wpc - 1) / wpc);
+    vkern<<<blocks, wpc * 32, (size_t)wpc * L.total, st>>>(a);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h_low, a.low, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -438,6 +459,7 @@ extern "C" int indelgpu_find_best_band_batch(indelgpu_ctx* c, int32_t n, const u
     CU(cudaMemcpyAsync(c->pinned_small, c->counters.p, 64, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     int err; memcpy(&err, (char*)c->pinned_small + 40, 4);
+    if (err == 3) return fail(INDELGPU_ECUDA, "a TMA bulk copy never completed (mbarrier wait timed out)");
     if (err) return fail(INDELGPU_ELIMIT, "find_best_band_batch: a task violates numdiagonals > numgaps (alignment.c:405) or a size limit");
     return 0;
 }

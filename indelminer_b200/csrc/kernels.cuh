@@ -1,13 +1,11 @@
 // Device code of libindelgpu.so: split-read realignment kernels for sm_100a.
 //
-// One persistent CTA realigns one read at a time (work taken from an atomic counter):
-//   round 1  vote (k-mer diagonal histogram)  ->  align on the voted band  ->  CIGAR
-//   plan     which window / read slice round 2 uses (attempt_diagonal_alignments' branches)
-//   round 2  vote -> align -> CIGAR
-//   combine  junction choice + segment stitching (update_readsegs)
+// Shared pieces: reference packing, the one-diagonal alignment (band 1), junction scoring and
+// segment stitching.  The warp-per-read pipeline that uses them is in realign_kernel.cuh, the
+// k-mer vote in warp_vote.cuh, the banded DP in band_dp.cuh.
 // Everything between the read bytes coming in and the segment words going out stays in
-// shared memory / registers; the reference windows are read from the resident 2-bit packed
-// copy (voting) and raw bytes (DP) in HBM/L2.
+// shared memory / registers; the reference windows come from the resident 2-bit packed copy
+// (voting, TMA-staged) and the raw bytes (DP) in HBM/L2.
 //
 // Reference behaviour reproduced (file:line of ratan-lab/indelMINER):
 //   find_best_band        src/alignment.c:393-447 (+ :29-181)
@@ -145,105 +143,6 @@ struct Aln {
     int low, up, score, r1, r2, q1, q2, n;
     int cells_fwd, cells_rev, cells_glob;
 };
-
-// ---------------------------------------------------------------------------------------
-// find_best_band: k-mer diagonal voting, CTA-wide
-// ---------------------------------------------------------------------------------------
-// Restated set-wise (SURVEY.md 8a''): for every window offset j whose k-mer equals a k-mer that
-// occurs exactly once in the read slice (at offset i): diag[j - i + (M-k+1)]++ ; then the
-// arg-max band with the reference's tie rule.  The reference builds chained position tables of
-// the WINDOW (alignment.c:29-68); here the (much smaller) READ side is indexed in a shared-memory
-// hash table and the window's packed 2-bit stream is scanned once with coalesced loads.
-//
-// All threads must call.  Returns low (up = low + g) to every thread; `ok` false when the
-// reference would have aborted (numdiagonals <= numgaps, alignment.c:405).
-__device__ int vote_band(const DevParams& P, Cta& S, const uint32_t* __restrict__ packed,
-                         int64_t wabs, int N, int zs2, int M, int anchor_rel, bool* ok,
-                         unsigned long long* s_red)
-{
-    const int tid = threadIdx.x;
-    const int k = P.k, g = P.g;
-    const int numdiag = (N - (k - 1)) + (M - (k - 1));           // alignment.c:403-404
-    *ok = numdiag > g;
-    if (!*ok) return 0;
-    if (M < k) return numdiag - 1;                               // alignment.c:408-412
-
-    // 1. index the read slice's k-mers: key -> (count << 16 | offset + 1)
-    const int ht_mask = S.L.ht_slots - 1;
-    for (int s = tid; s < S.L.ht_slots; s += kThreads) { S.keys[s] = kEmptyKey; S.vals[s] = 0; }
-    __syncthreads();
-    const uint8_t* r = S.read + zs2;
-    for (int i = tid; i + k <= M; i += kThreads) {
-        uint32_t code = 0;
-        for (int t = 0; t < k; t++) code |= base_code(r[i + t]) << (2 * t);
-        uint32_t slot = hash_slot(code, ht_mask);
-        while (true) {
-            uint32_t prev = atomicCAS(&S.keys[slot], kEmptyKey, code);
-            if (prev == kEmptyKey || prev == code) { atomicAdd(&S.vals[slot], (1u << 16) | (uint32_t)(i + 1)); break; }
-            slot = (slot + 1) & ht_mask;
-        }
-    }
-    __syncthreads();
-
-    // 2. scan the window: one packed word (16 bases) per thread per step
-    if (N >= k) {
-        const int64_t first = wabs, last = wabs + N - k;         // k-mer start positions, inclusive
-        const int64_t w0 = first >> 4, w1 = last >> 4;
-        const int shiftM = M - k + 1;
-        for (int64_t wi = w0 + tid; wi <= w1; wi += kThreads) {
-            const uint32_t lo = __ldg(packed + wi), hi = __ldg(packed + wi + 1);
-            const unsigned long long x = ((unsigned long long)hi << 32) | lo;
-            const int64_t pos0 = wi << 4;
-#pragma unroll
-            for (int p = 0; p < 16; p++) {
-                const int64_t pos = pos0 + p;
-                if (pos < first || pos > last) continue;
-                const uint32_t code = (uint32_t)(x >> (2 * p)) & P.kmask;
-                uint32_t slot = hash_slot(code, ht_mask);
-                while (true) {
-                    const uint32_t kk = S.keys[slot];
-                    if (kk == code) {
-                        const uint32_t v = S.vals[slot];
-                        if ((v >> 16) == 1u) {                   // unique in the read (alignment.c:97-98)
-                            const int idx = (int)(pos - first) - (int)((v & 0xFFFFu) - 1u) + shiftM;
-                            atomicAdd(&S.hist[idx >> 1], 1u << ((idx & 1) * 16));
-                        }
-                        break;
-                    }
-                    if (kk == kEmptyKey) break;
-                    slot = (slot + 1) & ht_mask;
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    // 3. bin_bands + select_band (alignment.c:130-181): arg-max by (count desc, |a - i| asc, i asc)
-    int a = anchor_rel;
-    a = a < -1 ? -1 : (a > numdiag ? numdiag : a);               // clamping keeps every comparison
-    unsigned long long best = 0;
-    const uint16_t* h16 = reinterpret_cast<const uint16_t*>(S.hist);
-    for (int i = tid; i < numdiag; i += kThreads) {
-        uint32_t b = 0;
-        if (i < numdiag - g) for (int j = 0; j <= g; j++) b += h16[i + j];
-        const uint32_t dist = (uint32_t)(a > i ? a - i : i - a);
-        const unsigned long long key = ((unsigned long long)b << 42) |
-                                       ((unsigned long long)(0x1FFFFFu - dist) << 21) |
-                                       (unsigned long long)(0x1FFFFFu - (uint32_t)i);
-        best = key > best ? key : best;
-    }
-    best = warp_max_u64(best);
-    if ((tid & 31) == 0) s_red[tid >> 5] = best;
-    __syncthreads();
-    best = s_red[0];
-#pragma unroll
-    for (int w = 1; w < kWarps; w++) best = s_red[w] > best ? s_red[w] : best;
-    // leave the histogram clean for the next use
-    for (int s = tid; s < (numdiag + 2) / 2 + 1; s += kThreads) S.hist[s] = 0;
-    __syncthreads();
-    const int idx = (int)(0x1FFFFFu - (uint32_t)(best & 0x1FFFFFu));
-    return idx - (M - k + 1);                                    // alignment.c:438
-}
 
 // ---------------------------------------------------------------------------------------
 // band of one diagonal: local_align degenerates to a max-segment scan (SURVEY.md 8a'),

@@ -1,8 +1,20 @@
-// The fused two-round realignment kernel (persistent CTAs, one read at a time per CTA).
+// The fused two-round realignment kernel: persistent warps, ONE WARP PER READ.
+//
+// Every warp owns a slice of shared memory (WarpLayout) and loops over reads taken from a global
+// counter.  While read i is being realigned, lane 0 has already issued the TMA bulk copies
+// (cp.async.bulk -> mbarrier) that stage read i+1's bytes and its packed reference window
+// [left2, right2) -- a superset of every window either round scans -- into the other half of the
+// warp's double buffer.  No CTA-wide barrier exists after start-up.
+//
+//   round 1  vote (k-mer diagonal histogram)  ->  align on the voted band  ->  CIGAR
+//   plan     which window / read slice round 2 uses (attempt_diagonal_alignments' branches)
+//   round 2  vote -> align -> CIGAR
+//   combine  junction choice + segment stitching (update_readsegs)
 #pragma once
 
 #include "kernels.cuh"
 #include "band_dp.cuh"
+#include "warp_vote.cuh"
 
 namespace indelgpu {
 
@@ -19,7 +31,7 @@ struct RealignArgs {
     unsigned long long* cell_totals;   // 3 words: fwd, rev, glob; word [4] = algorithmic bytes
     int* error_flag;                   // set non-zero on a limit violation
     int max_read, max_numdiag;
-    BandScratch scratch;               // global scratch for bands wider than one diagonal
+    BandScratch scratch;               // global scratch for bands wider than one diagonal (one slice per warp)
 };
 
 // round-2 plan produced by lane 0 after round 1 (alignment.c:568-717)
@@ -85,11 +97,11 @@ __device__ __forceinline__ void make_plan(const DevParams& P, const Aln& A1, con
     pl->go = 1;
 }
 
-// attempt_band_alignment (alignment.c:343-391) by warp 0: local_align + fetch_cigar + coordinate shift.
+// attempt_band_alignment (alignment.c:343-391) by one warp: local_align + fetch_cigar + coordinate shift.
 // BANDED = false is the default-flag build (-g 0): every band is one diagonal, so the banded DP
 // (and its registers) is compiled out.
 template <bool BANDED>
-__device__ void band_alignment_warp(const RealignArgs& a, Cta& S, int64_t cbase,
+__device__ void band_alignment_warp(const RealignArgs& a, Cta& S, int slot, int64_t cbase,
                                     uint32_t zs1, uint32_t e1, uint32_t zs2, uint32_t e2,
                                     int low, int up, uint32_t* cig, Aln* out, int* s_tmp)
 {
@@ -97,7 +109,7 @@ __device__ void band_alignment_warp(const RealignArgs& a, Cta& S, int64_t cbase,
     const uint8_t* win = a.ref.raw + cbase + zs1;
     const int lo = max(-M, low), hi = min(N, up);                // localalign.c:70-71
     if (!BANDED || hi - lo + 1 == 1) align_diag1(a.P, S, win, N, (int)zs2, M, lo, cig, s_tmp);
-    else align_banded(a.P, a.scratch, S.read + zs2, M, win, N, lo, hi, cig, S.L.ops_cap, s_tmp);
+    else align_banded(a.P, a.scratch, slot, S.read + zs2, M, win, N, lo, hi, cig, S.L.ops_cap, s_tmp);
     if ((threadIdx.x & 31) == 0) {
         const int score = s_tmp[0];
         out->low = low; out->up = up; out->score = score;
@@ -112,190 +124,222 @@ __device__ void band_alignment_warp(const RealignArgs& a, Cta& S, int64_t cbase,
     __syncwarp();
 }
 
-template <bool BANDED>
-__global__ void __launch_bounds__(kThreads)
+// everything the kernel derives from one batch entry (alignment.c:764-783 + the forceasserts :548-553)
+struct ReadCtx {
+    int64_t roff; int readlen;
+    int64_t cbase;
+    int32_t position, left1, right1, left2, right2;
+    bool bad;
+};
+
+__device__ __forceinline__ ReadCtx load_read_ctx(const RealignArgs& a, int idx)
+{
+    ReadCtx c;
+    c.roff = a.read_off[idx];
+    c.readlen = (int)(a.read_off[idx + 1] - c.roff);
+    const int32_t ctg = a.tid[idx];
+    c.position = a.position[idx];
+    const int32_t range1 = a.range1[idx];
+    bool bad = c.readlen <= 0 || c.readlen > a.max_read || ctg < 0 || ctg >= a.ref.ncontigs || c.position < 0 || range1 < 0;
+    c.cbase = 0; int32_t reflength = 0;
+    if (!bad) {
+        c.cbase = a.ref.contig_off[ctg];
+        const int64_t cl = a.ref.contig_len[ctg];
+        reflength = (int32_t)cl;
+        bad = cl > 0x7FFFFFFF;
+    }
+    const int32_t position = c.position;
+    int32_t distance = range1;                                   // windows: alignment.c:774-783
+    c.left1  = position >= distance ? position - distance : 0;
+    c.right1 = reflength < (position + distance) ? reflength : position + distance;
+    distance = (int32_t)((unsigned)range1 + (unsigned)a.P.maxdel);
+    c.left2  = position >= distance ? position - distance : 0;
+    c.right2 = reflength < (position + distance) ? reflength : position + distance;
+    bad = bad || !(position >= c.left1 && position >= c.left2 && position <= c.right1 && position <= c.right2 && c.right2 > 0);
+    bad = bad || (c.right2 - c.left2) + c.readlen + 2 > a.max_numdiag;
+    c.bad = bad;
+    return c;
+}
+
+// lane 0: register the expected bytes and issue the two bulk copies of one batch entry
+__device__ __forceinline__ void stage_read(const RealignArgs& a, WarpView& V, const ReadCtx& c, int buf)
+{
+    uint64_t* bar = V.bar + buf;
+    if (c.bad) { mbar_arrive(bar); return; }
+    const int64_t r0 = c.roff & ~(int64_t)15;
+    const uint32_t rbytes = (uint32_t)(((c.roff + c.readlen - r0) + 15) / 16 * 16);
+    int64_t sw0;
+    const uint32_t wbytes = window_span_bytes(c.cbase + c.left2, c.cbase + c.right2, &sw0);
+    mbar_arrive_expect_tx(bar, rbytes + wbytes);
+    bulk_g2s(V.rbuf[buf], a.reads + r0, rbytes, bar);
+    bulk_g2s(V.win[buf], a.ref.packed + sw0, wbytes, bar);
+}
+
+template <bool BANDED, bool DIRECT>
+__global__ void __launch_bounds__(512)
 realign_kernel(const __grid_constant__ RealignArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_idx;
-    __shared__ unsigned long long s_red[kWarps];
-    __shared__ Aln s_a1, s_a2;
-    __shared__ Plan s_plan;
-    __shared__ int s_tmp[16];
-    __shared__ int s_final[4];     // status, nseg, rstart, index
-    __shared__ long long s_segoff;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
+    const WarpLayout L = make_warp_layout(a.P, a.max_read, a.max_numdiag, BANDED ? 1 : 0);
+    WarpView V;
+    bind_warp(V, smem + (size_t)warp * L.total, L);
+    Cta& S = V.S;
+    init_warp_tables(V);
+    if (lane == 0) { mbar_init(V.bar + 0, 1); mbar_init(V.bar + 1, 1); mbar_fence_init(); }
+    __syncwarp();
 
-    Cta S;
-    S.L = make_layout(a.max_read, a.max_numdiag);
-    S.keys = reinterpret_cast<uint32_t*>(smem + S.L.off_keys);
-    S.vals = reinterpret_cast<uint32_t*>(smem + S.L.off_vals);
-    S.hist = reinterpret_cast<uint32_t*>(smem + S.L.off_hist);
-    S.read = smem + S.L.off_read;
-    S.bits = reinterpret_cast<uint32_t*>(smem + S.L.off_bits);
-    S.psum = reinterpret_cast<int*>(smem + S.L.off_psum);
-    S.cig1 = reinterpret_cast<uint32_t*>(smem + S.L.off_cig1);
-    S.cig2 = reinterpret_cast<uint32_t*>(smem + S.L.off_cig2);
-    S.segs = reinterpret_cast<uint32_t*>(smem + S.L.off_segs);
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int s = tid; s < S.L.hist_words; s += kThreads) S.hist[s] = 0;
+    Aln*  s_a1   = reinterpret_cast<Aln*>(V.misc);               // 11 ints
+    Aln*  s_a2   = reinterpret_cast<Aln*>(V.misc + 12);
+    Plan* s_plan = reinterpret_cast<Plan*>(V.misc + 24);         // 11 ints
+    int*  s_tmp  = V.misc + 36;                                  // 16 ints
+    int*  s_final = V.misc + 52;                                 // status, nseg, rstart, index
+    const int slot = blockIdx.x * warps_per_cta + warp;
     unsigned long long cells[4] = {0, 0, 0, 0};
+    uint32_t phase[2] = {0, 0};
 
-    while (true) {
-        __syncthreads();
-        if (tid == 0) s_idx = atomicAdd(a.work_counter, 1);
-        __syncthreads();
-        const int idx = s_idx;
-        if (idx >= a.n) break;
+    int cur = 0;
+    if (lane == 0) cur = atomicAdd(a.work_counter, 1);
+    cur = __shfl_sync(0xFFFFFFFFu, cur, 0);
+    if (cur < a.n && lane == 0) { const ReadCtx c0 = load_read_ctx(a, cur); stage_read(a, V, c0, 0); }
 
-        const int64_t roff = a.read_off[idx];
-        const int readlen = (int)(a.read_off[idx + 1] - roff);
-        const int32_t ctg = a.tid[idx];
-        const int32_t position = a.position[idx];
-        const int32_t range1 = a.range1[idx];
-        bool bad = readlen <= 0 || readlen > a.max_read || ctg < 0 || ctg >= a.ref.ncontigs || position < 0;
-        int64_t cbase = 0; int32_t reflength = 0;
-        if (!bad) {
-            cbase = a.ref.contig_off[ctg];
-            const int64_t cl = a.ref.contig_len[ctg];
-            reflength = (int32_t)cl;
-            bad = cl > 0x7FFFFFFF;
+    for (int it = 0; cur < a.n; it++) {
+        const int buf = it & 1;
+        int nxt = 0;
+        if (lane == 0) {
+            nxt = atomicAdd(a.work_counter, 1);
+            if (nxt < a.n) { const ReadCtx cn = load_read_ctx(a, nxt); stage_read(a, V, cn, buf ^ 1); }
         }
-        // windows: alignment.c:774-783
-        int32_t distance = range1;
-        const int32_t left1  = position >= distance ? position - distance : 0;
-        const int32_t right1 = reflength < (position + distance) ? reflength : position + distance;
-        distance = (int32_t)((unsigned)range1 + (unsigned)a.P.maxdel);
-        const int32_t left2  = position >= distance ? position - distance : 0;
-        const int32_t right2 = reflength < (position + distance) ? reflength : position + distance;
-        const int32_t anchor = position;
-        // forceasserts of alignment.c:548-553
-        bad = bad || !(anchor >= left1 && anchor >= left2 && anchor <= right1 && anchor <= right2 && right2 > 0);
-        bad = bad || (right2 - left2) + readlen + 2 > a.max_numdiag;
-        if (bad) {
-            if (tid == 0) {
+        nxt = __shfl_sync(0xFFFFFFFFu, nxt, 0);
+        const int idx = cur;
+        cur = nxt;
+
+        const ReadCtx c = load_read_ctx(a, idx);
+        if (!mbar_wait(V.bar + buf, phase[buf])) { if (lane == 0) atomicExch(a.error_flag, 3); break; }
+        phase[buf] ^= 1u;
+        if (c.bad) {
+            if (lane == 0) {
                 a.status[idx] = ST_ASSERT; a.nseg[idx] = 0; a.rstart[idx] = 0; a.seg_off[idx] = 0;
                 if (a.detail) memset(&a.detail[idx], 0, sizeof(indelgpu_detail));
                 atomicExch(a.error_flag, 1);
             }
             continue;
         }
-        for (int t = tid; t < readlen; t += kThreads) S.read[t] = a.reads[roff + t];
-        if (tid == 0) {
-            s_a2.low = s_a2.up = s_a2.score = s_a2.r1 = s_a2.r2 = s_a2.q1 = s_a2.q2 = s_a2.n = 0;
-            s_a2.cells_fwd = s_a2.cells_rev = s_a2.cells_glob = 0;
+        const int readlen = c.readlen;
+        const int32_t anchor = c.position, left1 = c.left1, right1 = c.right1, left2 = c.left2, right2 = c.right2;
+        const int64_t cbase = c.cbase;
+        S.read = V.rbuf[buf] + (int)(c.roff & 15);
+        const uint32_t* swin = V.win[buf];
+        const int64_t sw0 = ((cbase + left2) & ~(int64_t)63) >> 4;
+        pack_read_warp(V, S.read, readlen);
+        if (lane == 0) {
+            s_a2->low = s_a2->up = s_a2->score = s_a2->r1 = s_a2->r2 = s_a2->q1 = s_a2->q2 = s_a2->n = 0;
+            s_a2->cells_fwd = s_a2->cells_rev = s_a2->cells_glob = 0;
             s_final[0] = 0; s_final[1] = 0; s_final[2] = 0; s_final[3] = -1;
         }
-        __syncthreads();
+        __syncwarp();
 
         // ---------------- round 1 (alignment.c:555-566)
         bool ok;
-        const int low1 = vote_band(a.P, S, a.ref.packed, cbase + left1, right1 - left1, 0, readlen,
-                                   (int)((uint32_t)anchor - (uint32_t)left1), &ok, s_red);
-        if (warp == 0) {
-            if (!ok) {
-                if (lane == 0) { s_plan.go = 0; s_plan.status = ST_ASSERT; s_a1 = s_a2; }
-            } else {
-                band_alignment_warp<BANDED>(a, S, cbase, (uint32_t)left1, (uint32_t)right1, 0, (uint32_t)readlen,
-                                    low1, low1 + a.P.g, S.cig1, &s_a1, s_tmp);
-                if (lane == 0) make_plan(a.P, s_a1, S.cig1, anchor, left2, right2, (unsigned)readlen, &s_plan);
-            }
+        const int low1 = vote_band_dispatch<DIRECT>(a.P, V, swin, sw0, cbase + left1, right1 - left1, 0, readlen,
+                                                    (int)((uint32_t)anchor - (uint32_t)left1), &ok);
+        if (!ok) {
+            if (lane == 0) { s_plan->go = 0; s_plan->status = ST_ASSERT; *s_a1 = *s_a2; }
+        } else {
+            band_alignment_warp<BANDED>(a, S, slot, cbase, (uint32_t)left1, (uint32_t)right1, 0, (uint32_t)readlen,
+                                        low1, low1 + a.P.g, S.cig1, s_a1, s_tmp);
+            if (lane == 0) make_plan(a.P, *s_a1, S.cig1, anchor, left2, right2, (unsigned)readlen, s_plan);
         }
-        __syncthreads();
+        __syncwarp();
 
         // ---------------- round 2 (alignment.c:601-717)
-        if (s_plan.go) {
-            const Plan pl = s_plan;
-            const int low2 = vote_band(a.P, S, a.ref.packed, cbase + pl.zs1, (int)(pl.e1 - pl.zs1),
-                                       (int)pl.zs2, (int)(pl.e2 - pl.zs2), (int)(pl.anc - pl.zs1), &ok, s_red);
-            if (warp == 0) {
-                if (!ok) { if (lane == 0) s_final[0] = ST_ASSERT; }
+        if (s_plan->go) {
+            const Plan pl = *s_plan;
+            const int low2 = vote_band_dispatch<DIRECT>(a.P, V, swin, sw0, cbase + pl.zs1, (int)(pl.e1 - pl.zs1),
+                                                        (int)pl.zs2, (int)(pl.e2 - pl.zs2), (int)(pl.anc - pl.zs1), &ok);
+            if (!ok) { if (lane == 0) s_final[0] = ST_ASSERT; }
+            else {
+                band_alignment_warp<BANDED>(a, S, slot, cbase, pl.zs1, pl.e1, pl.zs2, pl.e2,
+                                            low2, low2 + a.P.g, S.cig2, s_a2, s_tmp);
+                const int q1 = s_a1->q1, q2 = s_a1->q2, r1 = s_a1->r1, r2 = s_a1->r2, n1 = s_a1->n;
+                const int q3 = s_a2->q1, q4 = s_a2->q2, r3 = s_a2->r1, r4 = s_a2->r2;
+                int n2 = s_a2->n;
+                const bool fail = pl.tail ? (q4 != readlen || q3 == q4) : (q3 != 0 || q3 == q4);
+                if (fail) { if (lane == 0) s_final[0] = INDELGPU_ST_R2FAIL; }
                 else {
-                    band_alignment_warp<BANDED>(a, S, cbase, pl.zs1, pl.e1, pl.zs2, pl.e2,
-                                        low2, low2 + a.P.g, S.cig2, &s_a2, s_tmp);
-                    const int q1 = s_a1.q1, q2 = s_a1.q2, r1 = s_a1.r1, r2 = s_a1.r2, n1 = s_a1.n;
-                    const int q3 = s_a2.q1, q4 = s_a2.q2, r3 = s_a2.r1, r4 = s_a2.r2;
-                    int n2 = s_a2.n;
-                    bool fail = pl.tail ? (q4 != readlen || q3 == q4) : (q3 != 0 || q3 == q4);
-                    if (fail) { if (lane == 0) s_final[0] = INDELGPU_ST_R2FAIL; }
-                    else {
-                        if (lane == 0) {                 // add_prefix/suffix_soft_clip (:478-532)
-                            if (pl.tail && pl.f_nonmatch) {
-                                if (cig_op(S.cig2[0]) == OP_SOFT) S.cig2[0] = ((uint32_t)(cig_len(S.cig2[0]) + (int)pl.f_nonmatch) << 4) | OP_SOFT;
-                                else { for (int t = n2; t > 0; t--) S.cig2[t] = S.cig2[t - 1]; S.cig2[0] = (pl.f_nonmatch << 4) | OP_SOFT; n2++; }
-                            } else if (!pl.tail && pl.l_nonmatch) {
-                                if (cig_op(S.cig2[n2 - 1]) == OP_SOFT) S.cig2[n2 - 1] = ((uint32_t)(cig_len(S.cig2[n2 - 1]) + (int)pl.l_nonmatch) << 4) | OP_SOFT;
-                                else { S.cig2[n2] = (pl.l_nonmatch << 4) | OP_SOFT; n2++; }
-                            }
-                            s_a2.n = n2;
+                    if (lane == 0) {                 // add_prefix/suffix_soft_clip (:478-532)
+                        if (pl.tail && pl.f_nonmatch) {
+                            if (cig_op(S.cig2[0]) == OP_SOFT) S.cig2[0] = ((uint32_t)(cig_len(S.cig2[0]) + (int)pl.f_nonmatch) << 4) | OP_SOFT;
+                            else { for (int t = n2; t > 0; t--) S.cig2[t] = S.cig2[t - 1]; S.cig2[0] = (pl.f_nonmatch << 4) | OP_SOFT; n2++; }
+                        } else if (!pl.tail && pl.l_nonmatch) {
+                            if (cig_op(S.cig2[n2 - 1]) == OP_SOFT) S.cig2[n2 - 1] = ((uint32_t)(cig_len(S.cig2[n2 - 1]) + (int)pl.l_nonmatch) << 4) | OP_SOFT;
+                            else { S.cig2[n2] = (pl.l_nonmatch << 4) | OP_SOFT; n2++; }
                         }
-                        n2 = __shfl_sync(0xFFFFFFFFu, n2, 0);
-                        __syncwarp();
-                        // combine (:719-758)
-                        int mode = 0, index = -1;
-                        if (q1 > q3 && q1 <= q4)      { mode = 1; index = best_junction_warp(q3, q4, S.cig2, n2, q1, q2, S.cig1, n1); }
-                        else if (q3 > q1 && q3 <= q2) { mode = 2; index = best_junction_warp(q1, q2, S.cig1, n1, q3, q4, S.cig2, n2); }
-                        else if (q1 > q4 && r1 == r4) { mode = 3; index = q4; }
-                        else if (q3 > q2 && r2 == r3) { mode = 4; index = q2; }
-                        if (lane == 0) {
-                            if (mode == 0) s_final[0] = INDELGPU_ST_NOCOMBINE;
-                            else {
-                                int ns;
-                                if (mode == 1 || mode == 3) { ns = stitch_segments(S.segs, r3, S.cig2, n2, index, q1, r1, S.cig1, n1); s_final[2] = r3; }
-                                else                        { ns = stitch_segments(S.segs, r1, S.cig1, n1, index, q3, r3, S.cig2, n2); s_final[2] = r1; }
-                                s_final[0] = INDELGPU_ST_SPLIT; s_final[1] = ns; s_final[3] = index;
-                            }
+                        s_a2->n = n2;
+                    }
+                    n2 = __shfl_sync(0xFFFFFFFFu, n2, 0);
+                    __syncwarp();
+                    // combine (:719-758)
+                    int mode = 0, index = -1;
+                    if (q1 > q3 && q1 <= q4)      { mode = 1; index = best_junction_warp(q3, q4, S.cig2, n2, q1, q2, S.cig1, n1); }
+                    else if (q3 > q1 && q3 <= q2) { mode = 2; index = best_junction_warp(q1, q2, S.cig1, n1, q3, q4, S.cig2, n2); }
+                    else if (q1 > q4 && r1 == r4) { mode = 3; index = q4; }
+                    else if (q3 > q2 && r2 == r3) { mode = 4; index = q2; }
+                    if (lane == 0) {
+                        if (mode == 0) s_final[0] = INDELGPU_ST_NOCOMBINE;
+                        else {
+                            int ns;
+                            if (mode == 1 || mode == 3) { ns = stitch_segments(S.segs, r3, S.cig2, n2, index, q1, r1, S.cig1, n1); s_final[2] = r3; }
+                            else                        { ns = stitch_segments(S.segs, r1, S.cig1, n1, index, q3, r3, S.cig2, n2); s_final[2] = r1; }
+                            s_final[0] = INDELGPU_ST_SPLIT; s_final[1] = ns; s_final[3] = index;
                         }
                     }
                 }
             }
-        } else if (warp == 0 && lane == 0) {
-            s_final[0] = s_plan.status;
-            if (s_plan.status == INDELGPU_ST_WHOLE) {            // :575-582
-                s_final[1] = stitch_segments(S.segs, s_a1.r1, S.cig1, s_a1.n, readlen, 0, -1, nullptr, 0);
-                s_final[2] = s_a1.r1; s_final[3] = readlen;
+        } else if (lane == 0) {
+            s_final[0] = s_plan->status;
+            if (s_plan->status == INDELGPU_ST_WHOLE) {            // :575-582
+                s_final[1] = stitch_segments(S.segs, s_a1->r1, S.cig1, s_a1->n, readlen, 0, -1, nullptr, 0);
+                s_final[2] = s_a1->r1; s_final[3] = readlen;
             }
         }
+        __syncwarp();
 
         // ---------------- results
-        if (warp == 0) {
-            __syncwarp();
-            const int ns = s_final[1];
-            if (lane == 0) {
-                long long off = 0;
-                if (ns > 0) off = (long long)atomicAdd(a.seg_count, (unsigned long long)ns);
-                if (off + ns > a.seg_capacity) { atomicExch(a.error_flag, 2); off = -1; }
-                s_segoff = off;
-                a.status[idx] = s_final[0]; a.nseg[idx] = off < 0 ? 0 : ns;
-                a.rstart[idx] = s_final[2]; a.seg_off[idx] = off < 0 ? 0 : off;
-                cells[0] += (unsigned long long)(s_a1.cells_fwd + s_a2.cells_fwd);
-                cells[1] += (unsigned long long)(s_a1.cells_rev + s_a2.cells_rev);
-                cells[2] += (unsigned long long)(s_a1.cells_glob + s_a2.cells_glob);
-                // algorithmic bytes: N + M in, 4 * (6 + ncigar) out, per alignment
-                cells[3] += (unsigned long long)((right1 - left1) + readlen + 4 * (6 + s_a1.n));
-                if (s_plan.go) cells[3] += (unsigned long long)((int)(s_plan.e1 - s_plan.zs1) + (int)(s_plan.e2 - s_plan.zs2) + 4 * (6 + s_a2.n));
-                if (a.detail) {
-                    indelgpu_detail d;
-                    d.low1 = s_a1.low; d.up1 = s_a1.up; d.r1 = s_a1.r1; d.r2 = s_a1.r2; d.q1 = s_a1.q1; d.q2 = s_a1.q2;
-                    d.n1 = s_a1.n; d.score1 = s_a1.score;
-                    d.low2 = s_a2.low; d.up2 = s_a2.up; d.r3 = s_a2.r1; d.r4 = s_a2.r2; d.q3 = s_a2.q1; d.q4 = s_a2.q2;
-                    d.n2 = s_a2.n; d.score2 = s_a2.score;
-                    d.index = s_final[3];
-                    d.cells_fwd = s_a1.cells_fwd + s_a2.cells_fwd;
-                    d.cells_rev = s_a1.cells_rev + s_a2.cells_rev;
-                    d.cells_glob = s_a1.cells_glob + s_a2.cells_glob;
-                    a.detail[idx] = d;
-                }
+        const int ns = s_final[1];
+        long long off = 0;
+        if (lane == 0) {
+            if (ns > 0) off = (long long)atomicAdd(a.seg_count, (unsigned long long)ns);
+            if (off + ns > a.seg_capacity) { atomicExch(a.error_flag, 2); off = -1; }
+            a.status[idx] = s_final[0]; a.nseg[idx] = off < 0 ? 0 : ns;
+            a.rstart[idx] = s_final[2]; a.seg_off[idx] = off < 0 ? 0 : off;
+            cells[0] += (unsigned long long)(s_a1->cells_fwd + s_a2->cells_fwd);
+            cells[1] += (unsigned long long)(s_a1->cells_rev + s_a2->cells_rev);
+            cells[2] += (unsigned long long)(s_a1->cells_glob + s_a2->cells_glob);
+            // algorithmic bytes: N + M in, 4 * (6 + ncigar) out, per alignment
+            cells[3] += (unsigned long long)((right1 - left1) + readlen + 4 * (6 + s_a1->n));
+            if (s_plan->go) cells[3] += (unsigned long long)((int)(s_plan->e1 - s_plan->zs1) + (int)(s_plan->e2 - s_plan->zs2) + 4 * (6 + s_a2->n));
+            if (a.detail) {
+                indelgpu_detail d;
+                d.low1 = s_a1->low; d.up1 = s_a1->up; d.r1 = s_a1->r1; d.r2 = s_a1->r2; d.q1 = s_a1->q1; d.q2 = s_a1->q2;
+                d.n1 = s_a1->n; d.score1 = s_a1->score;
+                d.low2 = s_a2->low; d.up2 = s_a2->up; d.r3 = s_a2->r1; d.r4 = s_a2->r2; d.q3 = s_a2->q1; d.q4 = s_a2->q2;
+                d.n2 = s_a2->n; d.score2 = s_a2->score;
+                d.index = s_final[3];
+                d.cells_fwd = s_a1->cells_fwd + s_a2->cells_fwd;
+                d.cells_rev = s_a1->cells_rev + s_a2->cells_rev;
+                d.cells_glob = s_a1->cells_glob + s_a2->cells_glob;
+                a.detail[idx] = d;
             }
-            __syncwarp();
-            const long long off = s_segoff;
-            if (off >= 0) for (int t = lane; t < ns; t += 32) a.segs[off + t] = S.segs[t];
-            if (a.cigar1) for (int t = lane; t < min(s_a1.n, a.cigar_stride); t += 32) a.cigar1[(int64_t)idx * a.cigar_stride + t] = S.cig1[t];
-            if (a.cigar2) for (int t = lane; t < min(s_a2.n, a.cigar_stride); t += 32) a.cigar2[(int64_t)idx * a.cigar_stride + t] = S.cig2[t];
         }
+        off = __shfl_sync(0xFFFFFFFFu, off, 0);
+        if (off >= 0) for (int t = lane; t < ns; t += 32) a.segs[off + t] = S.segs[t];
+        if (a.cigar1) for (int t = lane; t < min(s_a1->n, a.cigar_stride); t += 32) a.cigar1[(int64_t)idx * a.cigar_stride + t] = S.cig1[t];
+        if (a.cigar2) for (int t = lane; t < min(s_a2->n, a.cigar_stride); t += 32) a.cigar2[(int64_t)idx * a.cigar_stride + t] = S.cig2[t];
+        __syncwarp();
     }
-    if (tid == 0 && (cells[0] | cells[1] | cells[2] | cells[3])) {
+    if (lane == 0 && (cells[0] | cells[1] | cells[2] | cells[3])) {
         atomicAdd(a.cell_totals + 0, cells[0]);
         atomicAdd(a.cell_totals + 1, cells[1]);
         atomicAdd(a.cell_totals + 2, cells[2]);

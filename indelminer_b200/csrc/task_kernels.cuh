@@ -4,6 +4,7 @@
 
 #include "kernels.cuh"
 #include "band_dp.cuh"
+#include "warp_vote.cuh"
 
 namespace indelgpu {
 
@@ -38,37 +39,48 @@ __device__ __forceinline__ void bind_smem(Cta& S, unsigned char* smem, int max_r
     S.segs = reinterpret_cast<uint32_t*>(smem + S.L.off_segs);
 }
 
-// find_best_band over n tasks (alignment.c:393-447 with zstart1 = zstart2 = 0)
-__global__ void __launch_bounds__(kThreads)
+// find_best_band over n tasks (alignment.c:393-447 with zstart1 = zstart2 = 0), one warp per task;
+// the packed window is staged by a TMA bulk copy like in the fused kernel
+template <bool DIRECT>
+__global__ void __launch_bounds__(512)
 vote_tasks_kernel(const __grid_constant__ TaskArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_idx;
-    __shared__ unsigned long long s_red[kWarps];
-    Cta S;
-    bind_smem(S, smem, a.max_read, a.max_numdiag);
-    const int tid = threadIdx.x;
-    for (int s = tid; s < S.L.hist_words; s += kThreads) S.hist[s] = 0;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const WarpLayout L = make_warp_layout(a.P, a.max_read, a.max_numdiag, 0);
+    WarpView V;
+    bind_warp(V, smem + (size_t)warp * L.total, L);
+    init_warp_tables(V);
+    if (lane == 0) { mbar_init(V.bar, 1); mbar_fence_init(); }
+    __syncwarp();
+    uint32_t phase = 0;
     while (true) {
-        __syncthreads();
-        if (tid == 0) s_idx = atomicAdd(a.work_counter, 1);
-        __syncthreads();
-        const int idx = s_idx;
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(a.work_counter, 1);
+        idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
         if (idx >= a.n) break;
         const int64_t roff = a.read_off[idx], woff = a.ref_off[idx];
         const int M = (int)(a.read_off[idx + 1] - roff), N = (int)(a.ref_off[idx + 1] - woff);
-        if (M <= 0 || M > a.max_read || N + M + 2 > a.max_numdiag) {
-            if (tid == 0) { a.low[idx] = 0; a.up[idx] = 0; atomicExch(a.error_flag, 1); }
+        if (M <= 0 || M > a.max_read || N <= 0 || N + M + 2 > a.max_numdiag) {
+            if (lane == 0) { a.low[idx] = 0; a.up[idx] = 0; atomicExch(a.error_flag, 1); }
             continue;
         }
-        for (int t = tid; t < M; t += kThreads) S.read[t] = a.reads[roff + t];
-        __syncthreads();
+        int64_t sw0;
+        const uint32_t wbytes = window_span_bytes(woff, woff + N, &sw0);
+        if (lane == 0) { mbar_arrive_expect_tx(V.bar, wbytes); bulk_g2s(V.win[0], a.packed + sw0, wbytes, V.bar); }
+        uint8_t* rd = V.rbuf[0];
+        for (int t = lane; t < M; t += 32) rd[t] = a.reads[roff + t];
+        __syncwarp();
+        pack_read_warp(V, rd, M);
+        if (!mbar_wait(V.bar, phase)) { if (lane == 0) atomicExch(a.error_flag, 3); break; }
+        phase ^= 1u;
         bool ok;
-        const int low = vote_band(a.P, S, a.packed, woff, N, 0, M, a.anchor_rel[idx], &ok, s_red);
-        if (tid == 0) {
+        const int low = vote_band_dispatch<DIRECT>(a.P, V, V.win[0], sw0, woff, N, 0, M, a.anchor_rel[idx], &ok);
+        if (lane == 0) {
             if (!ok) { a.low[idx] = 0; a.up[idx] = 0; atomicExch(a.error_flag, 1); }
             else { a.low[idx] = low; a.up[idx] = low + (M < a.P.k ? 0 : a.P.g); }
         }
+        __syncwarp();
     }
 }
 
@@ -76,7 +88,7 @@ vote_tasks_kernel(const __grid_constant__ TaskArgs a)
 __global__ void __launch_bounds__(32)
 align_tasks_kernel(const __grid_constant__ TaskArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int s_idx;
     __shared__ int s_tmp[16];
     Cta S;
@@ -103,7 +115,7 @@ align_tasks_kernel(const __grid_constant__ TaskArgs a)
         __syncwarp();
         const uint8_t* win = a.refs + woff;
         if (band == 1) align_diag1(a.P, S, win, N, 0, M, lo, S.cig1, s_tmp);
-        else align_banded(a.P, a.scratch, S.read, M, win, N, lo, hi, S.cig1, S.L.ops_cap, s_tmp);
+        else align_banded(a.P, a.scratch, blockIdx.x, S.read, M, win, N, lo, hi, S.cig1, S.L.ops_cap, s_tmp);
         const int score = s_tmp[0], n = s_tmp[5];
         if (lane == 0) {
             a.score[idx] = score;
@@ -116,7 +128,7 @@ align_tasks_kernel(const __grid_constant__ TaskArgs a)
             int32_t* out = a.script + (int64_t)idx * a.script_stride;
             if (band == 1) { const int len = s_tmp[3] - s_tmp[1] + 1; for (int t = lane; t < min(len, a.script_stride); t += 32) out[t] = 0; if (lane == 0 && len < a.script_stride) out[len] = 0x7FFFFFFF; }
             else {
-                const int* Sg = band_script_ptr(a.scratch);
+                const int* Sg = band_script_ptr(a.scratch, blockIdx.x);
                 const int len = s_tmp[9];
                 for (int t = lane; t < min(len, a.script_stride); t += 32) out[t] = Sg[t];
                 if (lane == 0 && len < a.script_stride) out[len] = 0x7FFFFFFF;

@@ -1,0 +1,367 @@
+// Warp-level building blocks of the realignment kernels (sm_100a):
+//   * per-warp shared-memory layout (one read is realigned by one warp, no CTA barriers)
+//   * TMA bulk copies (cp.async.bulk + mbarrier) that stage the packed reference window and the
+//     read bytes of the NEXT read while the current one is being realigned
+//   * find_best_band (src/alignment.c:393-447 with :29-181) as a warp-wide k-mer diagonal vote
+#pragma once
+
+#include "kernels.cuh"
+
+namespace indelgpu {
+
+// ---------------------------------------------------------------------------------------
+// per-warp shared-memory slice, computed identically on host and device
+// ---------------------------------------------------------------------------------------
+struct WarpLayout {
+    int direct;          // 1: direct-address table of 4^k uint16 entries; 0: open-addressing hash
+    int hash_slots;      // power of two (hash only)
+    int hist_bits;       // 8 or 16 bits per diagonal counter
+    int hist_words;      // uint32 words of the histogram (multiple of 4)
+    int win_bytes;       // bytes of one staged packed window (multiple of 16)
+    int read_bytes;      // bytes of one staged read (multiple of 16, includes 16 bytes of misalignment)
+    int pk_words;        // packed read words
+    int ops_cap;         // words per CIGAR buffer
+    int off_tab, off_hist, off_win0, off_win1, off_read0, off_read1, off_pk, off_psum, off_bits,
+        off_cig1, off_cig2, off_segs, off_bar, off_misc;
+    int total;           // bytes per warp (multiple of 128)
+};
+
+__host__ __device__ inline int cigar_cap(const DevParams& P, int max_read, int banded)
+{
+    // A positive-scoring ungapped local segment with x mismatches has x * |mismatch| < (M - x) * match,
+    // so at most 2x + 1 runs; + 2 soft clips + 1 for the clip round 2 may insert (alignment.c:478-532).
+    if (!banded && P.match > 0 && P.mismatch < 0) {
+        const long long x = ((long long)max_read * P.match) / ((long long)P.match - P.mismatch);
+        const long long cap = 2 * x + 8;
+        if (cap < max_read + 4) return (int)cap;
+    }
+    return max_read + 4;
+}
+
+__host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int max_read, int max_numdiag, int banded)
+{
+    WarpLayout L;
+    L.direct = P.k <= 6;
+    int hs = 256;
+    while (hs < 4 * max_read) hs <<= 1;
+    L.hash_slots = L.direct ? 0 : hs;
+    const int tab_bytes = L.direct ? (2 << (2 * P.k)) : hs * 8;
+    L.hist_bits = (max_read - P.k + 1 <= 255) ? 8 : 16;
+    L.hist_words = round_up((max_numdiag + 4) * (L.hist_bits / 8), 16) / 4;
+    L.win_bytes = round_up(max_numdiag / 4 + 64, 16);             // window <= max_numdiag bases, 64-base aligned start, hi word
+    L.read_bytes = round_up(max_read + 16, 16);
+    L.pk_words = max_read / 16 + 3;
+    L.ops_cap = cigar_cap(P, max_read, banded);
+    int o = 0;
+    L.off_tab = o;   o += round_up(tab_bytes < 16 ? 16 : tab_bytes, 16);
+    L.off_hist = o;  o += L.hist_words * 4;
+    L.off_win0 = o;  o += L.win_bytes;
+    L.off_win1 = o;  o += L.win_bytes;
+    L.off_read0 = o; o += L.read_bytes;
+    L.off_read1 = o; o += L.read_bytes;
+    L.off_pk = o;    o += round_up(L.pk_words * 4, 16);
+    L.off_psum = o;  o += round_up((max_read + 2) * 4, 16);
+    L.off_bits = o;  o += round_up((max_read / 32 + 2) * 4, 16);
+    L.off_cig1 = o;  o += round_up(L.ops_cap * 4, 16);
+    L.off_cig2 = o;  o += round_up(L.ops_cap * 4, 16);
+    L.off_segs = o;  o += round_up((2 * L.ops_cap + 4) * 4, 16);
+    L.off_bar = o;   o += 16;                                      // two mbarriers
+    L.off_misc = o;  o += 256;                                     // Aln x 2, Plan, scalars
+    L.total = round_up(o, 128);
+    return L;
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------
+// TMA bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a copy that never lands is a bug, not something to hang the GPU on
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    for (int spin = 0; spin < (1 << 24); spin++) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------
+// per-warp views
+// ---------------------------------------------------------------------------------------
+struct WarpView {
+    WarpLayout L;
+    uint16_t* tab16; uint32_t* keys; uint32_t* vals;
+    uint32_t* hist;
+    uint32_t* win[2]; uint8_t* rbuf[2];
+    uint32_t* pk;
+    uint64_t* bar;        // [2]
+    int* misc;
+    Cta S;                // psum / bits / cig1 / cig2 / segs views used by the scalar pieces (kernels.cuh)
+};
+
+__device__ __forceinline__ void bind_warp(WarpView& V, unsigned char* base, const WarpLayout& L)
+{
+    V.L = L;
+    V.tab16 = reinterpret_cast<uint16_t*>(base + L.off_tab);
+    V.keys = reinterpret_cast<uint32_t*>(base + L.off_tab);
+    V.vals = V.keys + L.hash_slots;
+    V.hist = reinterpret_cast<uint32_t*>(base + L.off_hist);
+    V.win[0] = reinterpret_cast<uint32_t*>(base + L.off_win0);
+    V.win[1] = reinterpret_cast<uint32_t*>(base + L.off_win1);
+    V.rbuf[0] = base + L.off_read0;
+    V.rbuf[1] = base + L.off_read1;
+    V.pk = reinterpret_cast<uint32_t*>(base + L.off_pk);
+    V.bar = reinterpret_cast<uint64_t*>(base + L.off_bar);
+    V.misc = reinterpret_cast<int*>(base + L.off_misc);
+    V.S.keys = nullptr; V.S.vals = nullptr; V.S.hist = nullptr;
+    V.S.read = nullptr;
+    V.S.bits = reinterpret_cast<uint32_t*>(base + L.off_bits);
+    V.S.psum = reinterpret_cast<int*>(base + L.off_psum);
+    V.S.cig1 = reinterpret_cast<uint32_t*>(base + L.off_cig1);
+    V.S.cig2 = reinterpret_cast<uint32_t*>(base + L.off_cig2);
+    V.S.segs = reinterpret_cast<uint32_t*>(base + L.off_segs);
+    V.S.L.ops_cap = L.ops_cap;
+}
+
+// zero the table and the histogram once; every vote leaves both clean again
+__device__ __forceinline__ void init_warp_tables(WarpView& V)
+{
+    const int lane = threadIdx.x & 31;
+    const int tabw = (V.L.off_hist - V.L.off_tab) / 4;
+    uint32_t* t = reinterpret_cast<uint32_t*>(V.tab16);
+    for (int s = lane; s < tabw; s += 32) t[s] = V.L.direct ? 0u : kEmptyKey;
+    if (!V.L.direct) for (int s = lane; s < V.L.hash_slots; s += 32) V.vals[s] = 0;
+    for (int s = lane; s < V.L.hist_words; s += 32) V.hist[s] = 0;
+    __syncwarp();
+}
+
+// 2-bit pack of the staged read (codes of base_code; bases 16 per word, base j of a word in bits 2j..2j+1)
+__device__ __forceinline__ void pack_read_warp(WarpView& V, const uint8_t* read, int M)
+{
+    const int lane = threadIdx.x & 31;
+    const int chunks = (M + 31) >> 5;
+    for (int c = 0; c < chunks; c++) {
+        const int i = (c << 5) + lane;
+        const uint32_t q = i < M ? base_code(read[i]) : 0u;
+        const uint32_t v = q << (2 * (lane & 15));
+        const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, lane < 16 ? v : 0u);
+        const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, lane < 16 ? 0u : v);
+        if (lane == 0) { V.pk[2 * c] = lo; V.pk[2 * c + 1] = hi; }
+    }
+    if (lane == 0) { V.pk[2 * chunks] = 0; V.pk[2 * chunks + 1] = 0; }
+    __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t kmer_at(const uint32_t* pk, int i, uint32_t kmask)
+{
+    const int w = i >> 4;
+    return __funnelshift_r(pk[w], pk[w + 1], 2 * (i & 15)) & kmask;
+}
+
+template <int HB>
+__device__ __forceinline__ void hist_add(uint32_t* hist, int idx, uint32_t cnt)
+{
+    if (HB == 8) atomicAdd(&hist[idx >> 2], cnt << ((idx & 3) * 8));
+    else         atomicAdd(&hist[idx >> 1], cnt << ((idx & 1) * 16));
+}
+
+// ---------------------------------------------------------------------------------------
+// find_best_band for one (window, read slice) pair, executed by one warp.
+//   swin / sw0  staged packed window: swin[w - sw0] is packed word w of the reference
+//   wabs, N     absolute base offset (in packed-reference coordinates) and length of the window
+//   zs2, M      read slice inside the packed read V.pk
+// Restated set-wise (SURVEY.md 8a''): for every window offset j whose k-mer equals a k-mer that occurs
+// exactly once in the slice (at offset i): diag[j - i + (M-k+1)]++ ; then the arg-max band with the
+// reference's tie rule (count desc, |anchor_rel - index| asc, index asc).
+// Returns low (up = low + g); *ok false when the reference would have aborted (alignment.c:405).
+// ---------------------------------------------------------------------------------------
+template <bool DIRECT, int HB>
+__device__ int vote_band_warp(const DevParams& P, WarpView& V, const uint32_t* swin, int64_t sw0,
+                              int64_t wabs, int N, int zs2, int M, int anchor_rel, bool* ok)
+{
+    const int lane = threadIdx.x & 31;
+    const int k = P.k, g = P.g;
+    const int numdiag = (N - (k - 1)) + (M - (k - 1));            // alignment.c:403-404
+    *ok = numdiag > g;
+    if (!*ok) return 0;
+    if (M < k) return numdiag - 1;                                // alignment.c:408-412
+    const uint32_t kmask = P.kmask;
+    const int nk = M - k + 1;
+
+    // 1. index the k-mers of the slice: table[code] = offset + 1 if unique, 0xFFFF if repeated
+    if (DIRECT) {
+        for (int i = lane; i < nk; i += 32) V.tab16[kmer_at(V.pk, zs2 + i, kmask)] = (uint16_t)(i + 1);
+        __syncwarp();
+        for (int i = lane; i < nk; i += 32) {
+            const uint32_t c = kmer_at(V.pk, zs2 + i, kmask);
+            if (V.tab16[c] != (uint16_t)(i + 1)) V.tab16[c] = 0xFFFFu;      // somebody else owns this code too
+        }
+    } else {
+        const int hm = V.L.hash_slots - 1;
+        for (int i = lane; i < nk; i += 32) {
+            const uint32_t code = kmer_at(V.pk, zs2 + i, kmask);
+            uint32_t slot = hash_slot(code, hm);
+            while (true) {
+                const uint32_t prev = atomicCAS(&V.keys[slot], kEmptyKey, code);
+                if (prev == kEmptyKey || prev == code) { atomicAdd(&V.vals[slot], (1u << 16) | (uint32_t)(i + 1)); break; }
+                slot = (slot + 1) & hm;
+            }
+        }
+    }
+    __syncwarp();
+
+    // 2. scan the window: one packed word (16 k-mer starts) per lane per step
+    if (N >= k) {
+        const int64_t first = wabs, last = wabs + N - k;          // k-mer start positions, inclusive
+        const int64_t w0 = first >> 4, w1 = last >> 4;
+        const int shiftM = M - k + 1;
+        for (int64_t wi = w0 + lane; wi <= w1; wi += 32) {
+            const uint32_t lo = swin[wi - sw0], hi = swin[wi - sw0 + 1];
+            const int rel0 = (int)((wi << 4) - first);            // window offset of position 0 of this word
+            const int plo = rel0 < 0 ? -rel0 : 0;
+            const int phi = (wi == w1) ? (int)(last - (wi << 4)) : 15;
+            int cur = -1; uint32_t cnt = 0;                       // run of consecutive votes for one diagonal
+#pragma unroll
+            for (int p = 0; p < 16; p++) {
+                const uint32_t code = __funnelshift_r(lo, hi, 2 * p) & kmask;
+                uint32_t off;                                     // offset + 1 of the unique read k-mer, else 0
+                if (DIRECT) {
+                    const uint32_t v = V.tab16[code];
+                    off = (v == 0xFFFFu) ? 0u : v;
+                } else {
+                    const int hm = V.L.hash_slots - 1;
+                    uint32_t slot = hash_slot(code, hm);
+                    off = 0;
+                    while (true) {
+                        const uint32_t kk = V.keys[slot];
+                        if (kk == code) { const uint32_t v = V.vals[slot]; if ((v >> 16) == 1u) off = v & 0xFFFFu; break; }
+                        if (kk == kEmptyKey) break;
+                        slot = (slot + 1) & hm;
+                    }
+                }
+                if (off != 0 && p >= plo && p <= phi) {           // unique in the read (alignment.c:97-98)
+                    const int idx = rel0 + p - (int)(off - 1u) + shiftM;
+                    if (idx != cur) {
+                        if (cnt) hist_add<HB>(V.hist, cur, cnt);
+                        cur = idx; cnt = 0;
+                    }
+                    cnt++;
+                }
+            }
+            if (cnt) hist_add<HB>(V.hist, cur, cnt);
+        }
+    }
+    __syncwarp();
+
+    // 3. bin_bands + select_band (alignment.c:130-181); the histogram is zeroed as it is read
+    int a = anchor_rel;
+    a = a < -1 ? -1 : (a > numdiag ? numdiag : a);                // clamping keeps every comparison
+    unsigned long long best = 0;
+    if (g == 0) {
+        constexpr int PER = 32 / HB;                              // counters per word
+        const int nwords = (numdiag + PER - 1) / PER;
+        uint4* h4 = reinterpret_cast<uint4*>(V.hist);
+        for (int q = lane; q * 4 < nwords; q += 32) {
+            const uint4 v = h4[q];
+            if ((v.x | v.y | v.z | v.w) == 0u) continue;
+            h4[q] = make_uint4(0, 0, 0, 0);
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (w4[u] == 0u) continue;
+#pragma unroll
+                for (int s = 0; s < PER; s++) {
+                    const uint32_t b = (w4[u] >> (s * HB)) & ((1u << HB) - 1u);
+                    const int i = (q * 4 + u) * PER + s;
+                    if (b == 0u || i >= numdiag) continue;
+                    const uint32_t dist = (uint32_t)(a > i ? a - i : i - a);
+                    const unsigned long long key = ((unsigned long long)b << 42) |
+                                                   ((unsigned long long)(0x1FFFFFu - dist) << 21) |
+                                                   (unsigned long long)(0x1FFFFFu - (uint32_t)i);
+                    best = key > best ? key : best;
+                }
+            }
+        }
+        best = warp_max_u64(best);
+        if (best == 0) {                                          // no vote at all: the index nearest to a
+            const int i = a < 0 ? 0 : (a > numdiag - 1 ? numdiag - 1 : a);
+            best = (unsigned long long)(0x1FFFFFu - (uint32_t)i);
+        }
+    } else {
+        for (int i = lane; i < numdiag; i += 32) {
+            uint32_t b = 0;
+            if (i < numdiag - g)
+                for (int j = 0; j <= g; j++) {
+                    const int t = i + j;
+                    b += (HB == 8) ? ((V.hist[t >> 2] >> ((t & 3) * 8)) & 0xFFu) : ((V.hist[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu);
+                }
+            const uint32_t dist = (uint32_t)(a > i ? a - i : i - a);
+            const unsigned long long key = ((unsigned long long)b << 42) |
+                                           ((unsigned long long)(0x1FFFFFu - dist) << 21) |
+                                           (unsigned long long)(0x1FFFFFu - (uint32_t)i);
+            best = key > best ? key : best;
+        }
+        best = warp_max_u64(best);
+        __syncwarp();
+        constexpr int PER = 32 / HB;
+        for (int s = lane; s < (numdiag + PER - 1) / PER + 1 && s < V.L.hist_words; s += 32) V.hist[s] = 0;
+    }
+
+    // 4. leave the table clean for the next vote
+    if (DIRECT) {
+        for (int i = lane; i < nk; i += 32) V.tab16[kmer_at(V.pk, zs2 + i, kmask)] = 0;
+    } else {
+        for (int s = lane; s < V.L.hash_slots; s += 32) { V.keys[s] = kEmptyKey; V.vals[s] = 0; }
+    }
+    __syncwarp();
+    const int idx = (int)(0x1FFFFFu - (uint32_t)(best & 0x1FFFFFu));
+    return idx - (M - k + 1);                                     // alignment.c:438
+}
+
+template <bool DIRECT>
+__device__ __forceinline__ int vote_band_dispatch(const DevParams& P, WarpView& V, const uint32_t* swin, int64_t sw0,
+                                                  int64_t wabs, int N, int zs2, int M, int anchor_rel, bool* ok)
+{
+    if (V.L.hist_bits == 8) return vote_band_warp<DIRECT, 8>(P, V, swin, sw0, wabs, N, zs2, M, anchor_rel, ok);
+    return vote_band_warp<DIRECT, 16>(P, V, swin, sw0, wabs, N, zs2, M, anchor_rel, ok);
+}
+
+// Stage `bytes` (multiple of 16) of a packed window starting at packed word sw0 into smem with one
+// bulk copy; returns the byte count it registered on the barrier.
+__device__ __forceinline__ uint32_t window_span_bytes(int64_t first_base, int64_t end_base, int64_t* sw0)
+{
+    const int64_t a0 = first_base & ~(int64_t)63;                 // 64 bases = 16 bytes of packed reference
+    *sw0 = a0 >> 4;
+    const int64_t lastw = (end_base >> 4) + 1;                    // hi word of the last k-mer start
+    const int64_t words = lastw - *sw0 + 1;
+    return (uint32_t)(((words * 4 + 15) / 16) * 16);
+}
+#endif  // __CUDACC__
+
+}  // namespace indelgpu
