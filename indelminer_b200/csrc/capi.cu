@@ -223,7 +223,7 @@ extern "C" int64_t indelgpu_seg_bound(int32_t n, int64_t total_read_bases)
 template <class Kern>
 static int plan_warps(indelgpu_ctx* c, Kern kern, int bytes_per_warp, int* warps_per_cta, int* ctas_per_sm)
 {
-    static const int cand[] = {16, 12, 8, 7, 6, 5, 4, 3, 2, 1};
+    static const int cand[] = {8, 7, 6, 5, 4, 3, 2, 1};       // __launch_bounds__(256)
     int best = 0;
     *warps_per_cta = 0; *ctas_per_sm = 0;
     for (int w : cand) {
@@ -261,8 +261,13 @@ static int launch_realign(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_r
     const int max_numdiag = (int)nd;
     const bool banded = c->P.g > 0;
     const WarpLayout L = make_warp_layout(c->P, max_read, max_numdiag, banded ? 1 : 0);
-    auto kern = banded ? (L.direct ? realign_kernel<true, true> : realign_kernel<true, false>)
-                       : (L.direct ? realign_kernel<false, true> : realign_kernel<false, false>);
+    void (*kern)(RealignArgs);
+    if (L.hist_bits == 8)
+        kern = banded ? (L.direct ? realign_kernel<true, true, 8> : realign_kernel<true, false, 8>)
+                      : (L.direct ? realign_kernel<false, true, 8> : realign_kernel<false, false, 8>);
+    else
+        kern = banded ? (L.direct ? realign_kernel<true, true, 16> : realign_kernel<true, false, 16>)
+                      : (L.direct ? realign_kernel<false, true, 16> : realign_kernel<false, false, 16>);
     int wpc = 0, occ = 0;
     if (int rc = plan_warps(c, kern, L.total, &wpc, &occ)) return rc;
     const int blocks = (int)std::min<long long>((long long)c->sms * occ, std::max(1, (d_in->n + wpc - 1) / wpc));
@@ -438,7 +443,9 @@ extern "C" int indelgpu_find_best_band_batch(indelgpu_ctx* c, int32_t n, const u
 
     const int max_numdiag = max_win + max_read + 4;
     const WarpLayout L = make_warp_layout(c->P, max_read, max_numdiag, 0);
-    auto vkern = L.direct ? vote_tasks_kernel<true> : vote_tasks_kernel<false>;
+    void (*vkern)(TaskArgs);
+    if (L.hist_bits == 8) vkern = L.direct ? vote_tasks_kernel<true, 8> : vote_tasks_kernel<false, 8>;
+    else                  vkern = L.direct ? vote_tasks_kernel<true, 16> : vote_tasks_kernel<false, 16>;
     int wpc = 0, occ = 0;
     if (int rc2 = plan_warps(c, vkern, L.total, &wpc, &occ)) return rc2;
     TaskArgs a; memset(&a, 0, sizeof(a));

@@ -174,9 +174,7 @@ __device__ void align_diag1(const DevParams& P, Cta& S, const uint8_t* __restric
         mn = min(mn, carryMin);
         const int run = valid ? p - mn : -1;                     // max(0, run + w) recursion, localalign.c:100-131
         if (valid) S.psum[i - si] = p;
-        int cmax = run;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, o));
+        const int cmax = __reduce_max_sync(0xFFFFFFFFu, run);
         if (cmax > best) {                                       // strict: the first maximum wins
             const uint32_t who = __ballot_sync(0xFFFFFFFFu, run == cmax);
             best = cmax; endi = base + __ffs(who);

@@ -171,12 +171,16 @@ __device__ __forceinline__ void stage_read(const RealignArgs& a, WarpView& V, co
     int64_t sw0;
     const uint32_t wbytes = window_span_bytes(c.cbase + c.left2, c.cbase + c.right2, &sw0);
     mbar_arrive_expect_tx(bar, rbytes + wbytes);
-    bulk_g2s(V.rbuf[buf], a.reads + r0, rbytes, bar);
-    bulk_g2s(V.win[buf], a.ref.packed + sw0, wbytes, bar);
+    bulk_g2s(read_buf(V, buf), a.reads + r0, rbytes, bar);
+    bulk_g2s(win_buf(V, buf), a.ref.packed + sw0, wbytes, bar);
 }
 
-template <bool BANDED, bool DIRECT>
-__global__ void __launch_bounds__(512)
+// BANDED: numgaps > 0 (bands of g+1 diagonals); DIRECT: direct-address k-mer table (k <= 6);
+// HB: bits per histogram counter (8 when no diagonal can collect more than 255 votes).
+// The two rounds are ONE loop body so that the vote and the alignment exist once in the instruction
+// stream: warps of a CTA are in different phases and the kernel has to stay instruction-cache friendly.
+template <bool BANDED, bool DIRECT, int HB>
+__global__ void __launch_bounds__(256)
 realign_kernel(const __grid_constant__ RealignArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -190,160 +194,161 @@ realign_kernel(const __grid_constant__ RealignArgs a)
     if (lane == 0) { mbar_init(V.bar + 0, 1); mbar_init(V.bar + 1, 1); mbar_fence_init(); }
     __syncwarp();
 
-    Aln*  s_a1   = reinterpret_cast<Aln*>(V.misc);               // 11 ints
-    Aln*  s_a2   = reinterpret_cast<Aln*>(V.misc + 12);
-    Plan* s_plan = reinterpret_cast<Plan*>(V.misc + 24);         // 11 ints
+    Aln*  s_aln  = reinterpret_cast<Aln*>(V.misc);               // 2 x 12 ints (round 1, round 2)
+    Plan* s_plan = reinterpret_cast<Plan*>(V.misc + 24);         // 10 ints
     int*  s_tmp  = V.misc + 36;                                  // 16 ints
     int*  s_final = V.misc + 52;                                 // status, nseg, rstart, index
     const int slot = blockIdx.x * warps_per_cta + warp;
-    unsigned long long cells[4] = {0, 0, 0, 0};
-    uint32_t phase[2] = {0, 0};
+    unsigned long long cells_f = 0, cells_r = 0, cells_g = 0, alg_bytes = 0;
+    uint32_t phase = 0;                                          // bit b = parity of buffer b's barrier
 
-    int cur = 0;
-    if (lane == 0) cur = atomicAdd(a.work_counter, 1);
-    cur = __shfl_sync(0xFFFFFFFFu, cur, 0);
-    if (cur < a.n && lane == 0) { const ReadCtx c0 = load_read_ctx(a, cur); stage_read(a, V, c0, 0); }
-
-    for (int it = 0; cur < a.n; it++) {
-        const int buf = it & 1;
+    int cur = -1, it = -1;
+    ReadCtx c;
+    c.bad = true;
+    while (true) {
+        // ---- fetch the next read and start staging it into the other buffer
         int nxt = 0;
-        if (lane == 0) {
-            nxt = atomicAdd(a.work_counter, 1);
-            if (nxt < a.n) { const ReadCtx cn = load_read_ctx(a, nxt); stage_read(a, V, cn, buf ^ 1); }
-        }
+        if (lane == 0) nxt = atomicAdd(a.work_counter, 1);
         nxt = __shfl_sync(0xFFFFFFFFu, nxt, 0);
-        const int idx = cur;
-        cur = nxt;
-
-        const ReadCtx c = load_read_ctx(a, idx);
-        if (!mbar_wait(V.bar + buf, phase[buf])) { if (lane == 0) atomicExch(a.error_flag, 3); break; }
-        phase[buf] ^= 1u;
-        if (c.bad) {
-            if (lane == 0) {
-                a.status[idx] = ST_ASSERT; a.nseg[idx] = 0; a.rstart[idx] = 0; a.seg_off[idx] = 0;
-                if (a.detail) memset(&a.detail[idx], 0, sizeof(indelgpu_detail));
-                atomicExch(a.error_flag, 1);
-            }
-            continue;
+        ReadCtx cn;
+        cn.bad = true;
+        if (nxt < a.n) {
+            cn = load_read_ctx(a, nxt);
+            if (lane == 0) stage_read(a, V, cn, (it + 1) & 1);
         }
-        const int readlen = c.readlen;
-        const int32_t anchor = c.position, left1 = c.left1, right1 = c.right1, left2 = c.left2, right2 = c.right2;
-        const int64_t cbase = c.cbase;
-        S.read = V.rbuf[buf] + (int)(c.roff & 15);
-        const uint32_t* swin = V.win[buf];
-        const int64_t sw0 = ((cbase + left2) & ~(int64_t)63) >> 4;
-        pack_read_warp(V, S.read, readlen);
-        if (lane == 0) {
-            s_a2->low = s_a2->up = s_a2->score = s_a2->r1 = s_a2->r2 = s_a2->q1 = s_a2->q2 = s_a2->n = 0;
-            s_a2->cells_fwd = s_a2->cells_rev = s_a2->cells_glob = 0;
-            s_final[0] = 0; s_final[1] = 0; s_final[2] = 0; s_final[3] = -1;
-        }
-        __syncwarp();
+        if (cur >= 0) {
+            const int idx = cur, buf = it & 1;
+            if (!mbar_wait(V.bar + buf, (phase >> buf) & 1u)) { if (lane == 0) atomicExch(a.error_flag, 3); break; }
+            phase ^= 1u << buf;
+            if (c.bad) {
+                if (lane == 0) {
+                    a.status[idx] = ST_ASSERT; a.nseg[idx] = 0; a.rstart[idx] = 0; a.seg_off[idx] = 0;
+                    if (a.detail) memset(&a.detail[idx], 0, sizeof(indelgpu_detail));
+                    atomicExch(a.error_flag, 1);
+                }
+            } else {
+                const int readlen = c.readlen;
+                const int32_t anchor = c.position, left2 = c.left2, right2 = c.right2;
+                const int64_t cbase = c.cbase;
+                S.read = read_buf(V, buf) + (int)(c.roff & 15);
+                const uint32_t* swin = win_buf(V, buf);
+                const int64_t sw0 = ((cbase + left2) & ~(int64_t)63) >> 4;
+                pack_read_warp(V, S.read, readlen);
+                if (lane < 24) V.misc[lane] = 0;                     // both Aln records
+                if (lane == 0) { s_final[0] = 0; s_final[1] = 0; s_final[2] = 0; s_final[3] = -1; s_plan->go = 0; s_plan->status = ST_ASSERT; }
+                __syncwarp();
 
-        // ---------------- round 1 (alignment.c:555-566)
-        bool ok;
-        const int low1 = vote_band_dispatch<DIRECT>(a.P, V, swin, sw0, cbase + left1, right1 - left1, 0, readlen,
-                                                    (int)((uint32_t)anchor - (uint32_t)left1), &ok);
-        if (!ok) {
-            if (lane == 0) { s_plan->go = 0; s_plan->status = ST_ASSERT; *s_a1 = *s_a2; }
-        } else {
-            band_alignment_warp<BANDED>(a, S, slot, cbase, (uint32_t)left1, (uint32_t)right1, 0, (uint32_t)readlen,
-                                        low1, low1 + a.P.g, S.cig1, s_a1, s_tmp);
-            if (lane == 0) make_plan(a.P, *s_a1, S.cig1, anchor, left2, right2, (unsigned)readlen, s_plan);
-        }
-        __syncwarp();
-
-        // ---------------- round 2 (alignment.c:601-717)
-        if (s_plan->go) {
-            const Plan pl = *s_plan;
-            const int low2 = vote_band_dispatch<DIRECT>(a.P, V, swin, sw0, cbase + pl.zs1, (int)(pl.e1 - pl.zs1),
-                                                        (int)pl.zs2, (int)(pl.e2 - pl.zs2), (int)(pl.anc - pl.zs1), &ok);
-            if (!ok) { if (lane == 0) s_final[0] = ST_ASSERT; }
-            else {
-                band_alignment_warp<BANDED>(a, S, slot, cbase, pl.zs1, pl.e1, pl.zs2, pl.e2,
-                                            low2, low2 + a.P.g, S.cig2, s_a2, s_tmp);
-                const int q1 = s_a1->q1, q2 = s_a1->q2, r1 = s_a1->r1, r2 = s_a1->r2, n1 = s_a1->n;
-                const int q3 = s_a2->q1, q4 = s_a2->q2, r3 = s_a2->r1, r4 = s_a2->r2;
-                int n2 = s_a2->n;
-                const bool fail = pl.tail ? (q4 != readlen || q3 == q4) : (q3 != 0 || q3 == q4);
-                if (fail) { if (lane == 0) s_final[0] = INDELGPU_ST_R2FAIL; }
-                else {
-                    if (lane == 0) {                 // add_prefix/suffix_soft_clip (:478-532)
-                        if (pl.tail && pl.f_nonmatch) {
-                            if (cig_op(S.cig2[0]) == OP_SOFT) S.cig2[0] = ((uint32_t)(cig_len(S.cig2[0]) + (int)pl.f_nonmatch) << 4) | OP_SOFT;
-                            else { for (int t = n2; t > 0; t--) S.cig2[t] = S.cig2[t - 1]; S.cig2[0] = (pl.f_nonmatch << 4) | OP_SOFT; n2++; }
-                        } else if (!pl.tail && pl.l_nonmatch) {
-                            if (cig_op(S.cig2[n2 - 1]) == OP_SOFT) S.cig2[n2 - 1] = ((uint32_t)(cig_len(S.cig2[n2 - 1]) + (int)pl.l_nonmatch) << 4) | OP_SOFT;
-                            else { S.cig2[n2] = (pl.l_nonmatch << 4) | OP_SOFT; n2++; }
-                        }
-                        s_a2->n = n2;
-                    }
-                    n2 = __shfl_sync(0xFFFFFFFFu, n2, 0);
+                // ---------------- round 1 (alignment.c:555-566), round 2 (:601-717)
+                uint32_t zs1 = (uint32_t)c.left1, e1 = (uint32_t)c.right1, zs2 = 0, e2 = (uint32_t)readlen, anc = (uint32_t)anchor;
+                bool done2 = false;
+#pragma unroll 1
+                for (int round = 0; round < 2; round++) {
+                    bool ok;
+                    const int low = vote_band_warp<DIRECT, HB>(a.P, V, swin, sw0, cbase + zs1, (int)(e1 - zs1), (int)zs2,
+                                                               (int)(e2 - zs2), (int)(anc - zs1), &ok);
+                    if (!ok) { if (lane == 0 && round == 1) s_final[0] = ST_ASSERT; break; }
+                    band_alignment_warp<BANDED>(a, S, slot, cbase, zs1, e1, zs2, e2, low, low + a.P.g,
+                                                round ? S.cig2 : S.cig1, s_aln + round, s_tmp);
+                    if (round == 1) { done2 = true; break; }
+                    if (lane == 0) make_plan(a.P, s_aln[0], S.cig1, anchor, left2, right2, (unsigned)readlen, s_plan);
                     __syncwarp();
-                    // combine (:719-758)
-                    int mode = 0, index = -1;
-                    if (q1 > q3 && q1 <= q4)      { mode = 1; index = best_junction_warp(q3, q4, S.cig2, n2, q1, q2, S.cig1, n1); }
-                    else if (q3 > q1 && q3 <= q2) { mode = 2; index = best_junction_warp(q1, q2, S.cig1, n1, q3, q4, S.cig2, n2); }
-                    else if (q1 > q4 && r1 == r4) { mode = 3; index = q4; }
-                    else if (q3 > q2 && r2 == r3) { mode = 4; index = q2; }
-                    if (lane == 0) {
-                        if (mode == 0) s_final[0] = INDELGPU_ST_NOCOMBINE;
-                        else {
-                            int ns;
-                            if (mode == 1 || mode == 3) { ns = stitch_segments(S.segs, r3, S.cig2, n2, index, q1, r1, S.cig1, n1); s_final[2] = r3; }
-                            else                        { ns = stitch_segments(S.segs, r1, S.cig1, n1, index, q3, r3, S.cig2, n2); s_final[2] = r1; }
-                            s_final[0] = INDELGPU_ST_SPLIT; s_final[1] = ns; s_final[3] = index;
+                    if (!s_plan->go) break;
+                    zs1 = s_plan->zs1; e1 = s_plan->e1; zs2 = s_plan->zs2; e2 = s_plan->e2; anc = s_plan->anc;
+                }
+                const Aln* s_a1 = s_aln; const Aln* s_a2 = s_aln + 1;
+
+                if (done2) {
+                    const Plan pl = *s_plan;
+                    const int q1 = s_a1->q1, q2 = s_a1->q2, r1 = s_a1->r1, r2 = s_a1->r2, n1 = s_a1->n;
+                    const int q3 = s_a2->q1, q4 = s_a2->q2, r3 = s_a2->r1, r4 = s_a2->r2;
+                    int n2 = s_a2->n;
+                    const bool fail = pl.tail ? (q4 != readlen || q3 == q4) : (q3 != 0 || q3 == q4);
+                    if (fail) { if (lane == 0) s_final[0] = INDELGPU_ST_R2FAIL; }
+                    else {
+                        if (lane == 0) {                 // add_prefix/suffix_soft_clip (:478-532)
+                            if (pl.tail && pl.f_nonmatch) {
+                                if (cig_op(S.cig2[0]) == OP_SOFT) S.cig2[0] = ((uint32_t)(cig_len(S.cig2[0]) + (int)pl.f_nonmatch) << 4) | OP_SOFT;
+                                else { for (int t = n2; t > 0; t--) S.cig2[t] = S.cig2[t - 1]; S.cig2[0] = (pl.f_nonmatch << 4) | OP_SOFT; n2++; }
+                            } else if (!pl.tail && pl.l_nonmatch) {
+                                if (cig_op(S.cig2[n2 - 1]) == OP_SOFT) S.cig2[n2 - 1] = ((uint32_t)(cig_len(S.cig2[n2 - 1]) + (int)pl.l_nonmatch) << 4) | OP_SOFT;
+                                else { S.cig2[n2] = (pl.l_nonmatch << 4) | OP_SOFT; n2++; }
+                            }
+                            s_aln[1].n = n2;
                         }
+                        n2 = __shfl_sync(0xFFFFFFFFu, n2, 0);
+                        __syncwarp();
+                        // combine (:719-758).  "first" = the segment earlier on the read.
+                        int mode = 0;
+                        if (q1 > q3 && q1 <= q4)      mode = 1;
+                        else if (q3 > q1 && q3 <= q2) mode = 2;
+                        else if (q1 > q4 && r1 == r4) mode = 3;
+                        else if (q3 > q2 && r2 == r3) mode = 4;
+                        if (mode == 0) { if (lane == 0) s_final[0] = INDELGPU_ST_NOCOMBINE; }
+                        else {
+                            const bool second_first = (mode == 1 || mode == 3);      // round-2 segment precedes round-1's
+                            const uint32_t* cA = second_first ? S.cig2 : S.cig1; const int nA = second_first ? n2 : n1;
+                            const uint32_t* cB = second_first ? S.cig1 : S.cig2; const int nB = second_first ? n1 : n2;
+                            const int qA1 = second_first ? q3 : q1, qA2 = second_first ? q4 : q2, rA1 = second_first ? r3 : r1;
+                            const int qB1 = second_first ? q1 : q3, qB2 = second_first ? q2 : q4, rB1 = second_first ? r1 : r3;
+                            int index = qA2;                                         // abutting on the reference (:740-749)
+                            if (mode <= 2) index = best_junction_warp(qA1, qA2, cA, nA, qB1, qB2, cB, nB);
+                            if (lane == 0) {
+                                s_final[1] = stitch_segments(S.segs, rA1, cA, nA, index, qB1, rB1, cB, nB);
+                                s_final[0] = INDELGPU_ST_SPLIT; s_final[2] = rA1; s_final[3] = index;
+                            }
+                        }
+                    }
+                } else if (lane == 0 && s_final[0] != ST_ASSERT) {
+                    s_final[0] = s_plan->status;
+                    if (s_plan->status == INDELGPU_ST_WHOLE) {            // :575-582
+                        s_final[1] = stitch_segments(S.segs, s_a1->r1, S.cig1, s_a1->n, readlen, 0, -1, nullptr, 0);
+                        s_final[2] = s_a1->r1; s_final[3] = readlen;
                     }
                 }
-            }
-        } else if (lane == 0) {
-            s_final[0] = s_plan->status;
-            if (s_plan->status == INDELGPU_ST_WHOLE) {            // :575-582
-                s_final[1] = stitch_segments(S.segs, s_a1->r1, S.cig1, s_a1->n, readlen, 0, -1, nullptr, 0);
-                s_final[2] = s_a1->r1; s_final[3] = readlen;
-            }
-        }
-        __syncwarp();
+                __syncwarp();
 
-        // ---------------- results
-        const int ns = s_final[1];
-        long long off = 0;
-        if (lane == 0) {
-            if (ns > 0) off = (long long)atomicAdd(a.seg_count, (unsigned long long)ns);
-            if (off + ns > a.seg_capacity) { atomicExch(a.error_flag, 2); off = -1; }
-            a.status[idx] = s_final[0]; a.nseg[idx] = off < 0 ? 0 : ns;
-            a.rstart[idx] = s_final[2]; a.seg_off[idx] = off < 0 ? 0 : off;
-            cells[0] += (unsigned long long)(s_a1->cells_fwd + s_a2->cells_fwd);
-            cells[1] += (unsigned long long)(s_a1->cells_rev + s_a2->cells_rev);
-            cells[2] += (unsigned long long)(s_a1->cells_glob + s_a2->cells_glob);
-            // algorithmic bytes: N + M in, 4 * (6 + ncigar) out, per alignment
-            cells[3] += (unsigned long long)((right1 - left1) + readlen + 4 * (6 + s_a1->n));
-            if (s_plan->go) cells[3] += (unsigned long long)((int)(s_plan->e1 - s_plan->zs1) + (int)(s_plan->e2 - s_plan->zs2) + 4 * (6 + s_a2->n));
-            if (a.detail) {
-                indelgpu_detail d;
-                d.low1 = s_a1->low; d.up1 = s_a1->up; d.r1 = s_a1->r1; d.r2 = s_a1->r2; d.q1 = s_a1->q1; d.q2 = s_a1->q2;
-                d.n1 = s_a1->n; d.score1 = s_a1->score;
-                d.low2 = s_a2->low; d.up2 = s_a2->up; d.r3 = s_a2->r1; d.r4 = s_a2->r2; d.q3 = s_a2->q1; d.q4 = s_a2->q2;
-                d.n2 = s_a2->n; d.score2 = s_a2->score;
-                d.index = s_final[3];
-                d.cells_fwd = s_a1->cells_fwd + s_a2->cells_fwd;
-                d.cells_rev = s_a1->cells_rev + s_a2->cells_rev;
-                d.cells_glob = s_a1->cells_glob + s_a2->cells_glob;
-                a.detail[idx] = d;
+                // ---------------- results
+                const int ns = s_final[1];
+                long long off = 0;
+                if (lane == 0) {
+                    if (ns > 0) off = (long long)atomicAdd(a.seg_count, (unsigned long long)ns);
+                    if (off + ns > a.seg_capacity) { atomicExch(a.error_flag, 2); off = -1; }
+                    a.status[idx] = s_final[0]; a.nseg[idx] = off < 0 ? 0 : ns;
+                    a.rstart[idx] = s_final[2]; a.seg_off[idx] = off < 0 ? 0 : off;
+                    cells_f += (unsigned long long)(s_a1->cells_fwd + s_a2->cells_fwd);
+                    cells_r += (unsigned long long)(s_a1->cells_rev + s_a2->cells_rev);
+                    cells_g += (unsigned long long)(s_a1->cells_glob + s_a2->cells_glob);
+                    // algorithmic bytes: N + M in, 4 * (6 + ncigar) out, per alignment
+                    alg_bytes += (unsigned long long)((c.right1 - c.left1) + readlen + 4 * (6 + s_a1->n));
+                    if (s_plan->go) alg_bytes += (unsigned long long)((int)(s_plan->e1 - s_plan->zs1) + (int)(s_plan->e2 - s_plan->zs2) + 4 * (6 + s_a2->n));
+                    if (a.detail) {
+                        indelgpu_detail d;
+                        d.low1 = s_a1->low; d.up1 = s_a1->up; d.r1 = s_a1->r1; d.r2 = s_a1->r2; d.q1 = s_a1->q1; d.q2 = s_a1->q2;
+                        d.n1 = s_a1->n; d.score1 = s_a1->score;
+                        d.low2 = s_a2->low; d.up2 = s_a2->up; d.r3 = s_a2->r1; d.r4 = s_a2->r2; d.q3 = s_a2->q1; d.q4 = s_a2->q2;
+                        d.n2 = s_a2->n; d.score2 = s_a2->score;
+                        d.index = s_final[3];
+                        d.cells_fwd = s_a1->cells_fwd + s_a2->cells_fwd;
+                        d.cells_rev = s_a1->cells_rev + s_a2->cells_rev;
+                        d.cells_glob = s_a1->cells_glob + s_a2->cells_glob;
+                        a.detail[idx] = d;
+                    }
+                }
+                off = __shfl_sync(0xFFFFFFFFu, off, 0);
+                if (off >= 0) for (int t = lane; t < ns; t += 32) a.segs[off + t] = S.segs[t];
+                if (a.cigar1) for (int t = lane; t < min(s_a1->n, a.cigar_stride); t += 32) a.cigar1[(int64_t)idx * a.cigar_stride + t] = S.cig1[t];
+                if (a.cigar2) for (int t = lane; t < min(s_a2->n, a.cigar_stride); t += 32) a.cigar2[(int64_t)idx * a.cigar_stride + t] = S.cig2[t];
+                __syncwarp();
             }
         }
-        off = __shfl_sync(0xFFFFFFFFu, off, 0);
-        if (off >= 0) for (int t = lane; t < ns; t += 32) a.segs[off + t] = S.segs[t];
-        if (a.cigar1) for (int t = lane; t < min(s_a1->n, a.cigar_stride); t += 32) a.cigar1[(int64_t)idx * a.cigar_stride + t] = S.cig1[t];
-        if (a.cigar2) for (int t = lane; t < min(s_a2->n, a.cigar_stride); t += 32) a.cigar2[(int64_t)idx * a.cigar_stride + t] = S.cig2[t];
-        __syncwarp();
+        if (nxt >= a.n) break;
+        cur = nxt; c = cn; it++;
     }
-    if (lane == 0 && (cells[0] | cells[1] | cells[2] | cells[3])) {
-        atomicAdd(a.cell_totals + 0, cells[0]);
-        atomicAdd(a.cell_totals + 1, cells[1]);
-        atomicAdd(a.cell_totals + 2, cells[2]);
-        atomicAdd(a.cell_totals + 4, cells[3]);
+    if (lane == 0 && (cells_f | cells_r | cells_g | alg_bytes)) {
+        atomicAdd(a.cell_totals + 0, cells_f);
+        atomicAdd(a.cell_totals + 1, cells_r);
+        atomicAdd(a.cell_totals + 2, cells_g);
+        atomicAdd(a.cell_totals + 4, alg_bytes);
     }
 }
 

@@ -41,8 +41,8 @@ __device__ __forceinline__ void bind_smem(Cta& S, unsigned char* smem, int max_r
 
 // find_best_band over n tasks (alignment.c:393-447 with zstart1 = zstart2 = 0), one warp per task;
 // the packed window is staged by a TMA bulk copy like in the fused kernel
-template <bool DIRECT>
-__global__ void __launch_bounds__(512)
+template <bool DIRECT, int HB>
+__global__ void __launch_bounds__(256)
 vote_tasks_kernel(const __grid_constant__ TaskArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -67,15 +67,15 @@ vote_tasks_kernel(const __grid_constant__ TaskArgs a)
         }
         int64_t sw0;
         const uint32_t wbytes = window_span_bytes(woff, woff + N, &sw0);
-        if (lane == 0) { mbar_arrive_expect_tx(V.bar, wbytes); bulk_g2s(V.win[0], a.packed + sw0, wbytes, V.bar); }
-        uint8_t* rd = V.rbuf[0];
+        if (lane == 0) { mbar_arrive_expect_tx(V.bar, wbytes); bulk_g2s(V.win0, a.packed + sw0, wbytes, V.bar); }
+        uint8_t* rd = V.rbuf0;
         for (int t = lane; t < M; t += 32) rd[t] = a.reads[roff + t];
         __syncwarp();
         pack_read_warp(V, rd, M);
         if (!mbar_wait(V.bar, phase)) { if (lane == 0) atomicExch(a.error_flag, 3); break; }
         phase ^= 1u;
         bool ok;
-        const int low = vote_band_dispatch<DIRECT>(a.P, V, V.win[0], sw0, woff, N, 0, M, a.anchor_rel[idx], &ok);
+        const int low = vote_band_warp<DIRECT, HB>(a.P, V, V.win0, sw0, woff, N, 0, M, a.anchor_rel[idx], &ok);
         if (lane == 0) {
             if (!ok) { a.low[idx] = 0; a.up[idx] = 0; atomicExch(a.error_flag, 1); }
             else { a.low[idx] = low; a.up[idx] = low + (M < a.P.k ? 0 : a.P.g); }

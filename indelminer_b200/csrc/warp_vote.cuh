@@ -45,8 +45,8 @@ __host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int m
     int hs = 256;
     while (hs < 4 * max_read) hs <<= 1;
     L.hash_slots = L.direct ? 0 : hs;
-    const int tab_bytes = L.direct ? (2 << (2 * P.k)) : hs * 8;
     L.hist_bits = (max_read - P.k + 1 <= 255) ? 8 : 16;
+    const int tab_bytes = L.direct ? ((L.hist_bits / 8) << (2 * P.k)) : hs * 8;
     L.hist_words = round_up((max_numdiag + 4) * (L.hist_bits / 8), 16) / 4;
     L.win_bytes = round_up(max_numdiag / 4 + 64, 16);             // window <= max_numdiag bases, 64-base aligned start, hi word
     L.read_bytes = round_up(max_read + 16, 16);
@@ -114,16 +114,23 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity)
 // ---------------------------------------------------------------------------------------
 // per-warp views
 // ---------------------------------------------------------------------------------------
+struct WarpView;
+__device__ __forceinline__ uint32_t* win_buf(const WarpView& V, int b);
+__device__ __forceinline__ uint8_t* read_buf(const WarpView& V, int b);
+
 struct WarpView {
     WarpLayout L;
     uint16_t* tab16; uint32_t* keys; uint32_t* vals;
     uint32_t* hist;
-    uint32_t* win[2]; uint8_t* rbuf[2];
+    uint32_t* win0; uint8_t* rbuf0;      // double buffers: buffer b at win0 + b * win_bytes / rbuf0 + b * read_bytes
     uint32_t* pk;
     uint64_t* bar;        // [2]
     int* misc;
     Cta S;                // psum / bits / cig1 / cig2 / segs views used by the scalar pieces (kernels.cuh)
 };
+
+__device__ __forceinline__ uint32_t* win_buf(const WarpView& V, int b) { return V.win0 + b * (V.L.win_bytes / 4); }
+__device__ __forceinline__ uint8_t* read_buf(const WarpView& V, int b) { return V.rbuf0 + b * V.L.read_bytes; }
 
 __device__ __forceinline__ void bind_warp(WarpView& V, unsigned char* base, const WarpLayout& L)
 {
@@ -132,10 +139,8 @@ __device__ __forceinline__ void bind_warp(WarpView& V, unsigned char* base, cons
     V.keys = reinterpret_cast<uint32_t*>(base + L.off_tab);
     V.vals = V.keys + L.hash_slots;
     V.hist = reinterpret_cast<uint32_t*>(base + L.off_hist);
-    V.win[0] = reinterpret_cast<uint32_t*>(base + L.off_win0);
-    V.win[1] = reinterpret_cast<uint32_t*>(base + L.off_win1);
-    V.rbuf[0] = base + L.off_read0;
-    V.rbuf[1] = base + L.off_read1;
+    V.win0 = reinterpret_cast<uint32_t*>(base + L.off_win0);
+    V.rbuf0 = base + L.off_read0;
     V.pk = reinterpret_cast<uint32_t*>(base + L.off_pk);
     V.bar = reinterpret_cast<uint64_t*>(base + L.off_bar);
     V.misc = reinterpret_cast<int*>(base + L.off_misc);
@@ -191,6 +196,33 @@ __device__ __forceinline__ void hist_add(uint32_t* hist, int idx, uint32_t cnt)
     else         atomicAdd(&hist[idx >> 1], cnt << ((idx & 1) * 16));
 }
 
+// table entry: offset + 1 of the read k-mer if it occurs exactly once in the slice, else 0.
+// Direct tables hold one entry per possible k-mer, HB/8 bytes wide (HB == 8 iff the slice has at most
+// 255 k-mers, so the same width serves the table and the histogram counters).
+template <bool DIRECT, int HB>
+__device__ __forceinline__ uint32_t kmer_lookup(const WarpView& V, uint32_t code)
+{
+    if (DIRECT) {
+        if (HB == 8) return reinterpret_cast<const uint8_t*>(V.tab16)[code];
+        return V.tab16[code];
+    }
+    const int hm = V.L.hash_slots - 1;
+    uint32_t slot = hash_slot(code, hm);
+    while (true) {
+        const uint32_t kk = V.keys[slot];
+        if (kk == code) { const uint32_t v = V.vals[slot]; return (v >> 16) == 1u ? (v & 0xFFFFu) : 0u; }
+        if (kk == kEmptyKey) return 0u;
+        slot = (slot + 1) & hm;
+    }
+}
+
+template <int HB>
+__device__ __forceinline__ void tab_store(WarpView& V, uint32_t code, uint32_t v)
+{
+    if (HB == 8) reinterpret_cast<uint8_t*>(V.tab16)[code] = (uint8_t)v;
+    else V.tab16[code] = (uint16_t)v;
+}
+
 // ---------------------------------------------------------------------------------------
 // find_best_band for one (window, read slice) pair, executed by one warp.
 //   swin / sw0  staged packed window: swin[w - sw0] is packed word w of the reference
@@ -202,7 +234,7 @@ __device__ __forceinline__ void hist_add(uint32_t* hist, int idx, uint32_t cnt)
 // Returns low (up = low + g); *ok false when the reference would have aborted (alignment.c:405).
 // ---------------------------------------------------------------------------------------
 template <bool DIRECT, int HB>
-__device__ int vote_band_warp(const DevParams& P, WarpView& V, const uint32_t* swin, int64_t sw0,
+__device__ __forceinline__ int vote_band_warp(const DevParams& P, WarpView& V, const uint32_t* swin, int64_t sw0,
                               int64_t wabs, int N, int zs2, int M, int anchor_rel, bool* ok)
 {
     const int lane = threadIdx.x & 31;
@@ -214,13 +246,14 @@ __device__ int vote_band_warp(const DevParams& P, WarpView& V, const uint32_t* s
     const uint32_t kmask = P.kmask;
     const int nk = M - k + 1;
 
-    // 1. index the k-mers of the slice: table[code] = offset + 1 if unique, 0xFFFF if repeated
+    // 1. index the k-mers of the slice.  Direct table, no atomics: everybody stores its offset, then whoever
+    //    does not find its own offset back knows the code is shared and zeroes the entry.
     if (DIRECT) {
-        for (int i = lane; i < nk; i += 32) V.tab16[kmer_at(V.pk, zs2 + i, kmask)] = (uint16_t)(i + 1);
+        for (int i = lane; i < nk; i += 32) tab_store<HB>(V, kmer_at(V.pk, zs2 + i, kmask), (uint32_t)(i + 1));
         __syncwarp();
         for (int i = lane; i < nk; i += 32) {
             const uint32_t c = kmer_at(V.pk, zs2 + i, kmask);
-            if (V.tab16[c] != (uint16_t)(i + 1)) V.tab16[c] = 0xFFFFu;      // somebody else owns this code too
+            if (kmer_lookup<true, HB>(V, c) != (uint32_t)(i + 1)) tab_store<HB>(V, c, 0u);
         }
     } else {
         const int hm = V.L.hash_slots - 1;
@@ -236,7 +269,9 @@ __device__ int vote_band_warp(const DevParams& P, WarpView& V, const uint32_t* s
     }
     __syncwarp();
 
-    // 2. scan the window: one packed word (16 k-mer starts) per lane per step
+    // 2. scan the window: one packed word (16 k-mer starts) per lane per step.
+    //    Pass A is branch-free: which of the 16 positions hit a unique read k-mer.  Pass B visits only the
+    //    hits and merges consecutive votes for one diagonal (the true alignment) into a single atomic.
     if (N >= k) {
         const int64_t first = wabs, last = wabs + N - k;          // k-mer start positions, inclusive
         const int64_t w0 = first >> 4, w1 = last >> 4;
@@ -244,35 +279,27 @@ __device__ int vote_band_warp(const DevParams& P, WarpView& V, const uint32_t* s
         for (int64_t wi = w0 + lane; wi <= w1; wi += 32) {
             const uint32_t lo = swin[wi - sw0], hi = swin[wi - sw0 + 1];
             const int rel0 = (int)((wi << 4) - first);            // window offset of position 0 of this word
-            const int plo = rel0 < 0 ? -rel0 : 0;
-            const int phi = (wi == w1) ? (int)(last - (wi << 4)) : 15;
-            int cur = -1; uint32_t cnt = 0;                       // run of consecutive votes for one diagonal
+            uint32_t hits = 0;
 #pragma unroll
             for (int p = 0; p < 16; p++) {
                 const uint32_t code = __funnelshift_r(lo, hi, 2 * p) & kmask;
-                uint32_t off;                                     // offset + 1 of the unique read k-mer, else 0
-                if (DIRECT) {
-                    const uint32_t v = V.tab16[code];
-                    off = (v == 0xFFFFu) ? 0u : v;
-                } else {
-                    const int hm = V.L.hash_slots - 1;
-                    uint32_t slot = hash_slot(code, hm);
-                    off = 0;
-                    while (true) {
-                        const uint32_t kk = V.keys[slot];
-                        if (kk == code) { const uint32_t v = V.vals[slot]; if ((v >> 16) == 1u) off = v & 0xFFFFu; break; }
-                        if (kk == kEmptyKey) break;
-                        slot = (slot + 1) & hm;
-                    }
+                if (kmer_lookup<DIRECT, HB>(V, code) != 0u) hits |= 1u << p;
+            }
+            const int plo = rel0 < 0 ? -rel0 : 0;
+            const int phi = (wi == w1) ? (int)(last - (wi << 4)) : 15;
+            hits &= (0xFFFFu << plo) & (0xFFFFu >> (15 - phi));
+            int cur = -1; uint32_t cnt = 0;
+#pragma unroll 1
+            while (hits) {
+                const int p = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const uint32_t off = kmer_lookup<DIRECT, HB>(V, __funnelshift_r(lo, hi, 2 * p) & kmask);
+                const int idx = rel0 + p - (int)(off - 1u) + shiftM;
+                if (idx != cur) {
+                    if (cnt) hist_add<HB>(V.hist, cur, cnt);
+                    cur = idx; cnt = 0;
                 }
-                if (off != 0 && p >= plo && p <= phi) {           // unique in the read (alignment.c:97-98)
-                    const int idx = rel0 + p - (int)(off - 1u) + shiftM;
-                    if (idx != cur) {
-                        if (cnt) hist_add<HB>(V.hist, cur, cnt);
-                        cur = idx; cnt = 0;
-                    }
-                    cnt++;
-                }
+                cnt++;
             }
             if (cnt) hist_add<HB>(V.hist, cur, cnt);
         }
@@ -282,38 +309,54 @@ __device__ int vote_band_warp(const DevParams& P, WarpView& V, const uint32_t* s
     // 3. bin_bands + select_band (alignment.c:130-181); the histogram is zeroed as it is read
     int a = anchor_rel;
     a = a < -1 ? -1 : (a > numdiag ? numdiag : a);                // clamping keeps every comparison
-    unsigned long long best = 0;
+    int idx;
+    constexpr int PER = 32 / HB;                                  // counters per word
     if (g == 0) {
-        constexpr int PER = 32 / HB;                              // counters per word
-        const int nwords = (numdiag + PER - 1) / PER;
+        // pass 1: the largest count (per-byte / per-halfword SIMD max); pass 2: among the diagonals that
+        // reach it, the one nearest to a, the lower index on equal distance.  For a fixed a the pair
+        // (distance, side) orders exactly like 2 * distance + (i > a).
+        const int nq = ((numdiag + PER - 1) / PER + 3) / 4;       // uint4 chunks
         uint4* h4 = reinterpret_cast<uint4*>(V.hist);
-        for (int q = lane; q * 4 < nwords; q += 32) {
+        uint32_t m = 0;
+        for (int q = lane; q < nq; q += 32) {
             const uint4 v = h4[q];
-            if ((v.x | v.y | v.z | v.w) == 0u) continue;
-            h4[q] = make_uint4(0, 0, 0, 0);
-            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (w4[u] == 0u) continue;
-#pragma unroll
-                for (int s = 0; s < PER; s++) {
-                    const uint32_t b = (w4[u] >> (s * HB)) & ((1u << HB) - 1u);
-                    const int i = (q * 4 + u) * PER + s;
-                    if (b == 0u || i >= numdiag) continue;
-                    const uint32_t dist = (uint32_t)(a > i ? a - i : i - a);
-                    const unsigned long long key = ((unsigned long long)b << 42) |
-                                                   ((unsigned long long)(0x1FFFFFu - dist) << 21) |
-                                                   (unsigned long long)(0x1FFFFFu - (uint32_t)i);
-                    best = key > best ? key : best;
+            if (HB == 8) m = __vmaxu4(m, __vmaxu4(__vmaxu4(v.x, v.y), __vmaxu4(v.z, v.w)));
+            else         m = __vmaxu2(m, __vmaxu2(__vmaxu2(v.x, v.y), __vmaxu2(v.z, v.w)));
+        }
+        if (HB == 8) { m = __vmaxu4(m, m >> 16); m = max(m & 0xFFu, (m >> 8) & 0xFFu); }
+        else         { m = max(m & 0xFFFFu, m >> 16); }
+        const uint32_t cmax = __reduce_max_sync(0xFFFFFFFFu, m);
+        uint32_t bestkey = 0xFFFFFFFFu;
+        if (cmax == 0u) {                                         // no vote at all: the index nearest to a
+            idx = a < 0 ? 0 : (a > numdiag - 1 ? numdiag - 1 : a);
+        } else {
+            const uint32_t rep = (HB == 8) ? cmax * 0x01010101u : cmax * 0x00010001u;
+            for (int q = lane; q < nq; q += 32) {
+                const uint4 v = h4[q];
+                h4[q] = make_uint4(0u, 0u, 0u, 0u);
+                uint32_t e0, e1, e2, e3;
+                if (HB == 8) { e0 = __vcmpeq4(v.x, rep); e1 = __vcmpeq4(v.y, rep); e2 = __vcmpeq4(v.z, rep); e3 = __vcmpeq4(v.w, rep); }
+                else         { e0 = __vcmpeq2(v.x, rep); e1 = __vcmpeq2(v.y, rep); e2 = __vcmpeq2(v.z, rep); e3 = __vcmpeq2(v.w, rep); }
+                if ((e0 | e1 | e2 | e3) == 0u) continue;
+#pragma unroll 1
+                for (int u = 0; u < 4; u++) {
+                    uint32_t e = u == 0 ? e0 : (u == 1 ? e1 : (u == 2 ? e2 : e3));
+                    while (e) {
+                        const int s = (__ffs(e) - 1) / HB;
+                        e &= ~(((HB == 8) ? 0xFFu : 0xFFFFu) << (s * HB));
+                        const int i = (q * 4 + u) * PER + s;
+                        if (i >= numdiag) continue;
+                        const uint32_t dist = (uint32_t)(a > i ? a - i : i - a);
+                        const uint32_t key = 2u * dist + (i > a ? 1u : 0u);
+                        bestkey = min(bestkey, key);
+                    }
                 }
             }
-        }
-        best = warp_max_u64(best);
-        if (best == 0) {                                          // no vote at all: the index nearest to a
-            const int i = a < 0 ? 0 : (a > numdiag - 1 ? numdiag - 1 : a);
-            best = (unsigned long long)(0x1FFFFFu - (uint32_t)i);
+            bestkey = __reduce_min_sync(0xFFFFFFFFu, bestkey);
+            idx = (bestkey & 1u) ? a + (int)(bestkey >> 1) : a - (int)(bestkey >> 1);
         }
     } else {
+        unsigned long long best = 0;
         for (int i = lane; i < numdiag; i += 32) {
             uint32_t b = 0;
             if (i < numdiag - g)
@@ -329,27 +372,18 @@ __device__ int vote_band_warp(const DevParams& P, WarpView& V, const uint32_t* s
         }
         best = warp_max_u64(best);
         __syncwarp();
-        constexpr int PER = 32 / HB;
         for (int s = lane; s < (numdiag + PER - 1) / PER + 1 && s < V.L.hist_words; s += 32) V.hist[s] = 0;
+        idx = (int)(0x1FFFFFu - (uint32_t)(best & 0x1FFFFFu));
     }
 
     // 4. leave the table clean for the next vote
     if (DIRECT) {
-        for (int i = lane; i < nk; i += 32) V.tab16[kmer_at(V.pk, zs2 + i, kmask)] = 0;
+        for (int i = lane; i < nk; i += 32) tab_store<HB>(V, kmer_at(V.pk, zs2 + i, kmask), 0u);
     } else {
         for (int s = lane; s < V.L.hash_slots; s += 32) { V.keys[s] = kEmptyKey; V.vals[s] = 0; }
     }
     __syncwarp();
-    const int idx = (int)(0x1FFFFFu - (uint32_t)(best & 0x1FFFFFu));
     return idx - (M - k + 1);                                     // alignment.c:438
-}
-
-template <bool DIRECT>
-__device__ __forceinline__ int vote_band_dispatch(const DevParams& P, WarpView& V, const uint32_t* swin, int64_t sw0,
-                                                  int64_t wabs, int N, int zs2, int M, int anchor_rel, bool* ok)
-{
-    if (V.L.hist_bits == 8) return vote_band_warp<DIRECT, 8>(P, V, swin, sw0, wabs, N, zs2, M, anchor_rel, ok);
-    return vote_band_warp<DIRECT, 16>(P, V, swin, sw0, wabs, N, zs2, M, anchor_rel, ok);
 }
 
 // Stage `bytes` (multiple of 16) of a packed window starting at packed word sw0 into smem with one
