@@ -283,7 +283,7 @@ static int launch_realign(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_r
     a.segs = d_out->segs; a.seg_capacity = d_out->seg_capacity; a.seg_count = d_seg_count;
     a.detail = d_out->detail; a.cigar1 = d_out->cigar1; a.cigar2 = d_out->cigar2; a.cigar_stride = d_out->cigar_stride;
     a.work_counter = ctr_work(c); a.cell_totals = ctr_cells(c); a.error_flag = ctr_err(c);
-    a.max_read = max_read; a.max_numdiag = max_numdiag;
+    a.max_read = max_read; a.max_numdiag = max_numdiag; a.L = L;
     if (ensure_scratch(c, blocks * wpc, max_read, &a.scratch)) return INDELGPU_ENOMEM;
 
     CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
@@ -455,7 +455,7 @@ extern "C" int indelgpu_find_best_band_batch(indelgpu_ctx* c, int32_t n, const u
     a.packed = c->t_packed.as<uint32_t>(); a.anchor_rel = c->t_anchor.as<int32_t>();
     a.low = c->t_low.as<int32_t>(); a.up = c->t_up.as<int32_t>();
     a.work_counter = ctr_work(c); a.cell_totals = ctr_cells(c); a.error_flag = ctr_err(c);
-    a.max_read = max_read; a.max_numdiag = max_numdiag;
+    a.max_read = max_read; a.max_numdiag = max_numdiag; a.L = L;
     CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
     const int blocks = (int)std::min<long long>((long long)c->sms * occ, (n + wpc - 1) / wpc);
     vkern<<<blocks, wpc * 32, (size_t)wpc * L.total, st>>>(a);

@@ -61,17 +61,18 @@ __host__ __device__ inline SmemLayout make_layout(int max_read, int max_numdiag)
 {
     SmemLayout L;
     int ht = 256;
+    #pragma unroll 1
     while (ht < 4 * max_read) ht <<= 1;
     L.ht_slots = ht;
     L.hist_words = round_up(max_numdiag + 2, 8) / 2 + 4;
-    L.read_bytes = round_up(max_read + 16, 16);
+    L.read_bytes = round_up(max_read + 32, 16);
     L.ops_cap = max_read + 4;
     int o = 0;
     L.off_keys = o; o += ht * 4;
     L.off_vals = o; o += ht * 4;
     L.off_hist = o; o += round_up(L.hist_words * 4, 16);
     L.off_read = o; o += L.read_bytes;
-    L.off_bits = o; o += round_up((max_read / 32 + 2) * 4, 16);
+    L.off_bits = o; o += round_up(((max_read + 127) / 128 * 4 + 4) * 4, 16);
     L.off_psum = o; o += round_up((max_read + 2) * 4, 16);
     L.off_cig1 = o; o += round_up(L.ops_cap * 4, 16);
     L.off_cig2 = o; o += round_up(L.ops_cap * 4, 16);
@@ -99,6 +100,7 @@ __global__ void pack_reference_kernel(const uint8_t* __restrict__ raw, uint32_t*
 {
     int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    #pragma unroll 1
     for (; w < nwords; w += stride) {
         const uint4 v = reinterpret_cast<const uint4*>(raw)[w];
         const uint32_t q[4] = {v.x, v.y, v.z, v.w};
@@ -154,32 +156,66 @@ __device__ void align_diag1(const DevParams& P, Cta& S, const uint8_t* __restric
     const int lane = threadIdx.x & 31;
     const uint8_t* r = S.read + zs2;
     const int si = max(0, -d), ei = min(M, N - d);               // localalign.c:86-87
+    // Forward sweep (localalign.c:100-131) as a prefix-sum problem: run_i = P_i - min_{j<=i} P_j.
+    // Four consecutive rows per lane: 128 rows per step, one warp scan of the lane totals and one of
+    // the lane minima.
     int best = 0, endi = si;
     int carryP = 0, carryMin = 0;
     if (lane == 0) S.psum[0] = 0;
-    for (int base = si; base < ei; base += 32) {
-        const int i = base + 1 + lane;                           // 1-based read row
-        const bool valid = i <= ei;
-        bool eq = false;
-        if (valid) eq = r[i - 1] == __ldg(win + (i + d - 1));
-        const uint32_t mbits = __ballot_sync(0xFFFFFFFFu, eq);
-        if (lane == 0) S.bits[(base - si) >> 5] = mbits;
-        int p = valid ? (eq ? P.match : P.mismatch) : 0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, p, o); if (lane >= o) p += t; }
-        p += carryP;                                             // prefix sum P_i
-        int mn = p;                                              // min_{j<=i} P_j  (P_si = 0 included)
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, mn, o); if (lane >= o) mn = min(mn, t); }
-        mn = min(mn, carryMin);
-        const int run = valid ? p - mn : -1;                     // max(0, run + w) recursion, localalign.c:100-131
-        if (valid) S.psum[i - si] = p;
-        const int cmax = __reduce_max_sync(0xFFFFFFFFu, run);
-        if (cmax > best) {                                       // strict: the first maximum wins
-            const uint32_t who = __ballot_sync(0xFFFFFFFFu, run == cmax);
-            best = cmax; endi = base + __ffs(who);
+    const int rows = ei - si;
+    #pragma unroll 1
+    for (int base = 0; base < rows; base += 128) {
+        const int t0 = base + 4 * lane;                          // row index of this lane's first cell (row i = si + 1 + t)
+        const int nval = min(4, max(0, rows - t0));
+        uint32_t x = 0xFFFFFFFFu;                                // read bytes XOR window bytes
+        if (nval > 0) {
+            const uintptr_t ra = reinterpret_cast<uintptr_t>(r + si + t0), wa = reinterpret_cast<uintptr_t>(win + si + d + t0);
+            const uint32_t* rp = reinterpret_cast<const uint32_t*>(ra & ~(uintptr_t)3);
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(wa & ~(uintptr_t)3);
+            const uint32_t rv = __funnelshift_r(rp[0], rp[1], 8 * (int)(ra & 3));
+            const uint32_t wv = __funnelshift_r(__ldg(wp), __ldg(wp + 1), 8 * (int)(wa & 3));
+            x = rv ^ wv;
         }
-        carryP = __shfl_sync(0xFFFFFFFFu, p, 31);
+        int p[4]; uint32_t nib = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool eq = ((x >> (8 * j)) & 0xFFu) == 0u;
+            const int w = j < nval ? (eq ? P.match : P.mismatch) : 0;
+            if (eq && j < nval) nib |= 1u << j;
+            p[j] = (j ? p[j - 1] : 0) + w;
+        }
+        int tot = p[3];                                          // inclusive scan of the lane totals
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, tot, o); if (lane >= o) tot += t; }
+        const int offs = carryP + tot - p[3];
+#pragma unroll
+        for (int j = 0; j < 4; j++) p[j] += offs;                // prefix sums P_i
+        int mn = min(min(p[0], p[1]), min(p[2], p[3]));          // inclusive scan of the lane minima
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, mn, o); if (lane >= o) mn = min(mn, t); }
+        int prev = __shfl_up_sync(0xFFFFFFFFu, mn, 1);
+        prev = lane ? min(prev, carryMin) : carryMin;            // min over everything before this lane (P_si = 0 included)
+        int lrun = -1, lj = 0, m = prev;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            m = min(m, p[j]);
+            const int run = j < nval ? p[j] - m : -1;            // max(0, run + w) recursion
+            if (run > lrun) { lrun = run; lj = j; }
+            if (j < nval) S.psum[t0 + j + 1] = p[j];
+        }
+        const int cmax = __reduce_max_sync(0xFFFFFFFFu, lrun);
+        if (cmax > best) {                                       // strict: the first maximum wins
+            const uint32_t who = __ballot_sync(0xFFFFFFFFu, lrun == cmax);
+            const int src = __ffs(who) - 1;
+            best = cmax; endi = si + base + 4 * src + __shfl_sync(0xFFFFFFFFu, lj, src) + 1;
+        }
+        const uint32_t v = nib << (4 * (lane & 7));
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const uint32_t word = __reduce_or_sync(0xFFFFFFFFu, (lane >> 3) == w ? v : 0u);
+            if (lane == 0) S.bits[(base >> 5) + w] = word;
+        }
+        carryP = __shfl_sync(0xFFFFFFFFu, p[3], 31);
         carryMin = min(carryMin, __shfl_sync(0xFFFFFFFFu, mn, 31));
     }
     __syncwarp();
@@ -187,6 +223,7 @@ __device__ void align_diag1(const DevParams& P, Cta& S, const uint8_t* __restric
     if (best > 0) {
         // reverse sweep (localalign.c:144-176): first row, walking down from endi, whose suffix sum equals best
         const int target = S.psum[endi - si] - best;
+        #pragma unroll 1
         for (int base = endi; base > si; base -= 32) {
             const int i = base - lane;
             const bool hit = i > si && S.psum[i - 1 - si] == target;
@@ -201,11 +238,13 @@ __device__ void align_diag1(const DevParams& P, Cta& S, const uint8_t* __restric
             // fetch_cigar (globalalign.c:507-604) on an all-REP script
             if (starti - 1 > 0) cig[n++] = ((uint32_t)(starti - 1) << 4) | OP_SOFT;
             int pos = starti - 1 - si, end = endi - 1 - si;      // bit positions in S.bits
+            #pragma unroll 1
             while (pos <= end) {
                 const uint32_t word = S.bits[pos >> 5];
                 const int bit = (word >> (pos & 31)) & 1;
                 // length of the run starting at pos
                 int q = pos;
+                #pragma unroll 1
                 while (true) {
                     const uint32_t wq = S.bits[q >> 5];
                     uint32_t diff = (bit ? ~wq : wq) >> (q & 31);   // 1 where the run is broken
@@ -244,6 +283,7 @@ __device__ int count_matches(const uint32_t* c1, int n1, int q1, int q2,
                              const uint32_t* c2, int n2, int q3, int q4, int* pmm)
 {
     int i, j, matches = 0, mm = 0;
+    #pragma unroll 1
     for (i = 0, j = q1; i < n1; i++) {
         const int len = cig_len(c1[i]), op = cig_op(c1[i]);
         if (op != OP_DEL) j += len;
@@ -253,6 +293,7 @@ __device__ int count_matches(const uint32_t* c1, int n1, int q1, int q2,
             break;
         }
     }
+    #pragma unroll 1
     for (i = 0, j = 0; i < n2; i++) {
         const int len = cig_len(c2[i]), op = cig_op(c2[i]);
         if (op != OP_DEL) j += len;
@@ -261,6 +302,7 @@ __device__ int count_matches(const uint32_t* c1, int n1, int q1, int q2,
             i++; break;
         }
     }
+    #pragma unroll 1
     for (; i < n2; i++) {
         const int len = cig_len(c2[i]), op = cig_op(c2[i]);
         if (op != OP_DEL) j += len;
@@ -281,6 +323,7 @@ __device__ int best_junction_warp(int q1, int q2, const uint32_t* c1, int n1,
 {
     const int lane = threadIdx.x & 31;
     unsigned long long best = 0;
+    #pragma unroll 1
     for (int base = q3; base <= q2; base += 32) {
         const int i = base + lane;
         unsigned long long key = 0;
@@ -315,6 +358,7 @@ __device__ int stitch_segments(uint32_t* segs, int r1, const uint32_t* c1, int n
 {
     SegWriter w{segs, 0, r1, 0};
     int i, j;
+    #pragma unroll 1
     for (i = 0, j = 0; i < n1; i++) {
         const int op = cig_op(c1[i]), len = cig_len(c1[i]);
         if (op != OP_DEL) j += len;
@@ -328,6 +372,7 @@ __device__ int stitch_segments(uint32_t* segs, int r1, const uint32_t* c1, int n
     int rindex = r2, nextindex = index;
     if (index >= q2) {
         int offset = 0;
+        #pragma unroll 1
         for (i = 0, j = 0; i < n2; i++) {
             const int op = cig_op(c2[i]), len = cig_len(c2[i]);
             if (op != OP_DEL) j += len;
@@ -344,11 +389,13 @@ __device__ int stitch_segments(uint32_t* segs, int r1, const uint32_t* c1, int n
         nextindex += q2 - index;
     }
     if (w.refindx < rindex) w.emit(((uint32_t)(rindex - w.refindx) << 4) | OP_DEL);
+    #pragma unroll 1
     for (i = 0, j = 0; i < n2; i++) {
         const int op = cig_op(c2[i]), len = cig_len(c2[i]);
         if (op != OP_DEL) j += len;
         if (j > nextindex) { w.emit(((uint32_t)(j - nextindex) << 4) | (uint32_t)op); i++; break; }
     }
+    #pragma unroll 1
     for (; i < n2; i++) w.emit(c2[i]);
     return w.n;
 }

@@ -31,6 +31,7 @@ struct RealignArgs {
     unsigned long long* cell_totals;   // 3 words: fwd, rev, glob; word [4] = algorithmic bytes
     int* error_flag;                   // set non-zero on a limit violation
     int max_read, max_numdiag;
+    WarpLayout L;                      // per-warp shared-memory slice, computed by the host
     BandScratch scratch;               // global scratch for bands wider than one diagonal (one slice per warp)
 };
 
@@ -55,6 +56,7 @@ __device__ __forceinline__ void make_plan(const DevParams& P, const Aln& A1, con
     unsigned f_nonmatch, l_nonmatch;                                            // :584-599
     {
         int i, j;
+        #pragma unroll 1
         for (i = 0, j = 0; i < n1; i++) {
             const int op = cig_op(cig1[i]);
             if (i == 0 && op == OP_SOFT) continue;
@@ -62,6 +64,7 @@ __device__ __forceinline__ void make_plan(const DevParams& P, const Aln& A1, con
             j += cig_len(cig1[i]);
         }
         f_nonmatch = (unsigned)j;
+        #pragma unroll 1
         for (i = n1 - 1, j = 0; i >= 0; i--) {
             const int op = cig_op(cig1[i]);
             if (i == n1 - 1 && op == OP_SOFT) continue;
@@ -175,6 +178,8 @@ __device__ __forceinline__ void stage_read(const RealignArgs& a, WarpView& V, co
     bulk_g2s(win_buf(V, buf), a.ref.packed + sw0, wbytes, bar);
 }
 
+constexpr int kWorkChunk = 8;
+
 // BANDED: numgaps > 0 (bands of g+1 diagonals); DIRECT: direct-address k-mer table (k <= 6);
 // HB: bits per histogram counter (8 when no diagonal can collect more than 255 votes).
 // The two rounds are ONE loop body so that the vote and the alignment exist once in the instruction
@@ -186,9 +191,8 @@ realign_kernel(const __grid_constant__ RealignArgs a)
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int warps_per_cta = blockDim.x >> 5;
-    const WarpLayout L = make_warp_layout(a.P, a.max_read, a.max_numdiag, BANDED ? 1 : 0);
     WarpView V;
-    bind_warp(V, smem + (size_t)warp * L.total, L);
+    bind_warp(V, smem + (size_t)warp * a.L.total, a.L);
     Cta& S = V.S;
     init_warp_tables(V);
     if (lane == 0) { mbar_init(V.bar + 0, 1); mbar_init(V.bar + 1, 1); mbar_fence_init(); }
@@ -203,12 +207,18 @@ realign_kernel(const __grid_constant__ RealignArgs a)
     uint32_t phase = 0;                                          // bit b = parity of buffer b's barrier
 
     int cur = -1, it = -1;
+    int wnext = 0, wend = 0;                                     // lane 0: the chunk of batch entries this warp owns
+    long long pend_off = 0; int pend_ns = 0, pend_idx = -1;      // segment words of the previous read, not yet written out
     ReadCtx c;
     c.bad = true;
+    #pragma unroll 1
     while (true) {
         // ---- fetch the next read and start staging it into the other buffer
         int nxt = 0;
-        if (lane == 0) nxt = atomicAdd(a.work_counter, 1);
+        if (lane == 0) {                                         // reads are taken kWorkChunk at a time
+            if (wnext == wend) { wnext = atomicAdd(a.work_counter, kWorkChunk); wend = wnext + kWorkChunk; }
+            nxt = wnext++;
+        }
         nxt = __shfl_sync(0xFFFFFFFFu, nxt, 0);
         ReadCtx cn;
         cn.bad = true;
@@ -237,6 +247,17 @@ realign_kernel(const __grid_constant__ RealignArgs a)
                 if (lane < 24) V.misc[lane] = 0;                     // both Aln records
                 if (lane == 0) { s_final[0] = 0; s_final[1] = 0; s_final[2] = 0; s_final[3] = -1; s_plan->go = 0; s_plan->status = ST_ASSERT; }
                 __syncwarp();
+
+                // The previous read's segment words are still in S.segs; the offset its atomicAdd returned has
+                // had a whole read's worth of time to arrive.  Write them out before anything stitches again.
+                if (pend_idx >= 0) {
+                    const long long poff = __shfl_sync(0xFFFFFFFFu, pend_off, 0);
+                    if (poff + pend_ns <= a.seg_capacity) for (int t = lane; t < pend_ns; t += 32) a.segs[poff + t] = S.segs[t];
+                    else if (lane == 0) atomicExch(a.error_flag, 2);
+                    if (lane == 0) a.seg_off[pend_idx] = poff;
+                    pend_idx = -1;
+                    __syncwarp();
+                }
 
                 // ---------------- round 1 (alignment.c:555-566), round 2 (:601-717)
                 uint32_t zs1 = (uint32_t)c.left1, e1 = (uint32_t)c.right1, zs2 = 0, e2 = (uint32_t)readlen, anc = (uint32_t)anchor;
@@ -309,12 +330,13 @@ realign_kernel(const __grid_constant__ RealignArgs a)
 
                 // ---------------- results
                 const int ns = s_final[1];
-                long long off = 0;
+                if (ns > 0) {
+                    pend_idx = idx; pend_ns = ns;
+                    if (lane == 0) pend_off = (long long)atomicAdd(a.seg_count, (unsigned long long)ns);
+                }
                 if (lane == 0) {
-                    if (ns > 0) off = (long long)atomicAdd(a.seg_count, (unsigned long long)ns);
-                    if (off + ns > a.seg_capacity) { atomicExch(a.error_flag, 2); off = -1; }
-                    a.status[idx] = s_final[0]; a.nseg[idx] = off < 0 ? 0 : ns;
-                    a.rstart[idx] = s_final[2]; a.seg_off[idx] = off < 0 ? 0 : off;
+                    a.status[idx] = s_final[0]; a.nseg[idx] = ns;
+                    a.rstart[idx] = s_final[2]; if (ns == 0) a.seg_off[idx] = 0;
                     cells_f += (unsigned long long)(s_a1->cells_fwd + s_a2->cells_fwd);
                     cells_r += (unsigned long long)(s_a1->cells_rev + s_a2->cells_rev);
                     cells_g += (unsigned long long)(s_a1->cells_glob + s_a2->cells_glob);
@@ -334,8 +356,6 @@ realign_kernel(const __grid_constant__ RealignArgs a)
                         a.detail[idx] = d;
                     }
                 }
-                off = __shfl_sync(0xFFFFFFFFu, off, 0);
-                if (off >= 0) for (int t = lane; t < ns; t += 32) a.segs[off + t] = S.segs[t];
                 if (a.cigar1) for (int t = lane; t < min(s_a1->n, a.cigar_stride); t += 32) a.cigar1[(int64_t)idx * a.cigar_stride + t] = S.cig1[t];
                 if (a.cigar2) for (int t = lane; t < min(s_a2->n, a.cigar_stride); t += 32) a.cigar2[(int64_t)idx * a.cigar_stride + t] = S.cig2[t];
                 __syncwarp();
@@ -343,6 +363,12 @@ realign_kernel(const __grid_constant__ RealignArgs a)
         }
         if (nxt >= a.n) break;
         cur = nxt; c = cn; it++;
+    }
+    if (pend_idx >= 0) {
+        const long long poff = __shfl_sync(0xFFFFFFFFu, pend_off, 0);
+        if (poff + pend_ns <= a.seg_capacity) for (int t = lane; t < pend_ns; t += 32) a.segs[poff + t] = S.segs[t];
+        else if (lane == 0) atomicExch(a.error_flag, 2);
+        if (lane == 0) a.seg_off[pend_idx] = poff;
     }
     if (lane == 0 && (cells_f | cells_r | cells_g | alg_bytes)) {
         atomicAdd(a.cell_totals + 0, cells_f);

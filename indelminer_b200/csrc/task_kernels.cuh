@@ -22,6 +22,7 @@ struct TaskArgs {
     unsigned long long* cell_totals;
     int* error_flag;
     int max_read, max_numdiag;
+    WarpLayout L;                      // vote kernel only
     BandScratch scratch;
 };
 
@@ -47,9 +48,8 @@ vote_tasks_kernel(const __grid_constant__ TaskArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const WarpLayout L = make_warp_layout(a.P, a.max_read, a.max_numdiag, 0);
     WarpView V;
-    bind_warp(V, smem + (size_t)warp * L.total, L);
+    bind_warp(V, smem + (size_t)warp * a.L.total, a.L);
     init_warp_tables(V);
     if (lane == 0) { mbar_init(V.bar, 1); mbar_fence_init(); }
     __syncwarp();

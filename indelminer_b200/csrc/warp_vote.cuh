@@ -43,13 +43,14 @@ __host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int m
     WarpLayout L;
     L.direct = P.k <= 6;
     int hs = 256;
+    #pragma unroll 1
     while (hs < 4 * max_read) hs <<= 1;
     L.hash_slots = L.direct ? 0 : hs;
     L.hist_bits = (max_read - P.k + 1 <= 255) ? 8 : 16;
     const int tab_bytes = L.direct ? ((L.hist_bits / 8) << (2 * P.k)) : hs * 8;
     L.hist_words = round_up((max_numdiag + 4) * (L.hist_bits / 8), 16) / 4;
     L.win_bytes = round_up(max_numdiag / 4 + 64, 16);             // window <= max_numdiag bases, 64-base aligned start, hi word
-    L.read_bytes = round_up(max_read + 16, 16);
+    L.read_bytes = round_up(max_read + 32, 16);
     L.pk_words = max_read / 16 + 3;
     L.ops_cap = cigar_cap(P, max_read, banded);
     int o = 0;
@@ -61,7 +62,7 @@ __host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int m
     L.off_read1 = o; o += L.read_bytes;
     L.off_pk = o;    o += round_up(L.pk_words * 4, 16);
     L.off_psum = o;  o += round_up((max_read + 2) * 4, 16);
-    L.off_bits = o;  o += round_up((max_read / 32 + 2) * 4, 16);
+    L.off_bits = o;  o += round_up(((max_read + 127) / 128 * 4 + 4) * 4, 16);
     L.off_cig1 = o;  o += round_up(L.ops_cap * 4, 16);
     L.off_cig2 = o;  o += round_up(L.ops_cap * 4, 16);
     L.off_segs = o;  o += round_up((2 * L.ops_cap + 4) * 4, 16);
@@ -102,6 +103,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity)
 {
     const uint32_t addr = smem_u32(bar);
+    #pragma unroll 1
     for (int spin = 0; spin < (1 << 24); spin++) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -160,8 +162,10 @@ __device__ __forceinline__ void init_warp_tables(WarpView& V)
     const int lane = threadIdx.x & 31;
     const int tabw = (V.L.off_hist - V.L.off_tab) / 4;
     uint32_t* t = reinterpret_cast<uint32_t*>(V.tab16);
+    #pragma unroll 1
     for (int s = lane; s < tabw; s += 32) t[s] = V.L.direct ? 0u : kEmptyKey;
     if (!V.L.direct) for (int s = lane; s < V.L.hash_slots; s += 32) V.vals[s] = 0;
+    #pragma unroll 1
     for (int s = lane; s < V.L.hist_words; s += 32) V.hist[s] = 0;
     __syncwarp();
 }
@@ -171,6 +175,7 @@ __device__ __forceinline__ void pack_read_warp(WarpView& V, const uint8_t* read,
 {
     const int lane = threadIdx.x & 31;
     const int chunks = (M + 31) >> 5;
+    #pragma unroll 1
     for (int c = 0; c < chunks; c++) {
         const int i = (c << 5) + lane;
         const uint32_t q = i < M ? base_code(read[i]) : 0u;
@@ -189,13 +194,6 @@ __device__ __forceinline__ uint32_t kmer_at(const uint32_t* pk, int i, uint32_t 
     return __funnelshift_r(pk[w], pk[w + 1], 2 * (i & 15)) & kmask;
 }
 
-template <int HB>
-__device__ __forceinline__ void hist_add(uint32_t* hist, int idx, uint32_t cnt)
-{
-    if (HB == 8) atomicAdd(&hist[idx >> 2], cnt << ((idx & 3) * 8));
-    else         atomicAdd(&hist[idx >> 1], cnt << ((idx & 1) * 16));
-}
-
 // table entry: offset + 1 of the read k-mer if it occurs exactly once in the slice, else 0.
 // Direct tables hold one entry per possible k-mer, HB/8 bytes wide (HB == 8 iff the slice has at most
 // 255 k-mers, so the same width serves the table and the histogram counters).
@@ -208,6 +206,7 @@ __device__ __forceinline__ uint32_t kmer_lookup(const WarpView& V, uint32_t code
     }
     const int hm = V.L.hash_slots - 1;
     uint32_t slot = hash_slot(code, hm);
+    #pragma unroll 1
     while (true) {
         const uint32_t kk = V.keys[slot];
         if (kk == code) { const uint32_t v = V.vals[slot]; return (v >> 16) == 1u ? (v & 0xFFFFu) : 0u; }
@@ -249,17 +248,21 @@ __device__ __forceinline__ int vote_band_warp(const DevParams& P, WarpView& V, c
     // 1. index the k-mers of the slice.  Direct table, no atomics: everybody stores its offset, then whoever
     //    does not find its own offset back knows the code is shared and zeroes the entry.
     if (DIRECT) {
+        #pragma unroll 1
         for (int i = lane; i < nk; i += 32) tab_store<HB>(V, kmer_at(V.pk, zs2 + i, kmask), (uint32_t)(i + 1));
         __syncwarp();
+        #pragma unroll 1
         for (int i = lane; i < nk; i += 32) {
             const uint32_t c = kmer_at(V.pk, zs2 + i, kmask);
             if (kmer_lookup<true, HB>(V, c) != (uint32_t)(i + 1)) tab_store<HB>(V, c, 0u);
         }
     } else {
         const int hm = V.L.hash_slots - 1;
+        #pragma unroll 1
         for (int i = lane; i < nk; i += 32) {
             const uint32_t code = kmer_at(V.pk, zs2 + i, kmask);
             uint32_t slot = hash_slot(code, hm);
+            #pragma unroll 1
             while (true) {
                 const uint32_t prev = atomicCAS(&V.keys[slot], kEmptyKey, code);
                 if (prev == kEmptyKey || prev == code) { atomicAdd(&V.vals[slot], (1u << 16) | (uint32_t)(i + 1)); break; }
@@ -272,13 +275,22 @@ __device__ __forceinline__ int vote_band_warp(const DevParams& P, WarpView& V, c
     // 2. scan the window: one packed word (16 k-mer starts) per lane per step.
     //    Pass A is branch-free: which of the 16 positions hit a unique read k-mer.  Pass B visits only the
     //    hits and merges consecutive votes for one diagonal (the true alignment) into a single atomic.
+    //    For one-diagonal bands (g == 0) select_band (alignment.c:142-181) rides along: an atomic that
+    //    returns the largest count ever seen is the LAST vote of its diagonal, so every lane keeps the
+    //    largest count its own atomics produced and, among those, the smallest tie key
+    //    2 * |a - i| + (i > a)   (nearest to a, the lower index on equal distance).
+    int a = anchor_rel;
+    a = a < -1 ? -1 : (a > numdiag ? numdiag : a);                // clamping keeps every comparison
+    uint32_t lbest = 0, lkey = 0xFFFFFFFFu;
     if (N >= k) {
-        const int64_t first = wabs, last = wabs + N - k;          // k-mer start positions, inclusive
-        const int64_t w0 = first >> 4, w1 = last >> 4;
+        const int fr = (int)(wabs - (sw0 << 4));                  // first k-mer start, relative to the staged buffer
+        const int lr = fr + N - k;                                // last k-mer start, inclusive
+        const int w0 = fr >> 4, w1 = lr >> 4;
         const int shiftM = M - k + 1;
-        for (int64_t wi = w0 + lane; wi <= w1; wi += 32) {
-            const uint32_t lo = swin[wi - sw0], hi = swin[wi - sw0 + 1];
-            const int rel0 = (int)((wi << 4) - first);            // window offset of position 0 of this word
+        #pragma unroll 1
+        for (int wi = w0 + lane; wi <= w1; wi += 32) {
+            const uint32_t lo = swin[wi], hi = swin[wi + 1];
+            const int rel0 = (wi << 4) - fr;                      // window offset of position 0 of this word
             uint32_t hits = 0;
 #pragma unroll
             for (int p = 0; p < 16; p++) {
@@ -286,80 +298,57 @@ __device__ __forceinline__ int vote_band_warp(const DevParams& P, WarpView& V, c
                 if (kmer_lookup<DIRECT, HB>(V, code) != 0u) hits |= 1u << p;
             }
             const int plo = rel0 < 0 ? -rel0 : 0;
-            const int phi = (wi == w1) ? (int)(last - (wi << 4)) : 15;
+            const int phi = (wi == w1) ? (lr - (wi << 4)) : 15;
             hits &= (0xFFFFu << plo) & (0xFFFFu >> (15 - phi));
             int cur = -1; uint32_t cnt = 0;
 #pragma unroll 1
-            while (hits) {
-                const int p = __ffs(hits) - 1;
-                hits &= hits - 1;
-                const uint32_t off = kmer_lookup<DIRECT, HB>(V, __funnelshift_r(lo, hi, 2 * p) & kmask);
-                const int idx = rel0 + p - (int)(off - 1u) + shiftM;
-                if (idx != cur) {
-                    if (cnt) hist_add<HB>(V.hist, cur, cnt);
-                    cur = idx; cnt = 0;
+            while (true) {
+                int idx = -1;
+                if (hits) {
+                    const int p = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const uint32_t off = kmer_lookup<DIRECT, HB>(V, __funnelshift_r(lo, hi, 2 * p) & kmask);
+                    idx = rel0 + p - (int)(off - 1u) + shiftM;
                 }
-                cnt++;
+                if (idx != cur && cnt) {                          // the run ended: one atomic for all of it
+                    constexpr int LG = (HB == 8) ? 2 : 1;
+                    const int sh = (cur & ((1 << LG) - 1)) * HB;
+                    const uint32_t old = atomicAdd(&V.hist[cur >> LG], cnt << sh);
+                    const uint32_t now = ((old >> sh) & ((1u << HB) - 1u)) + cnt;
+                    const uint32_t key = 2u * (uint32_t)(a > cur ? a - cur : cur - a) + (cur > a ? 1u : 0u);
+                    if (now > lbest) { lbest = now; lkey = key; }
+                    else if (now == lbest) lkey = min(lkey, key);
+                    cnt = 0;
+                }
+                if (idx < 0) break;
+                cur = idx; cnt++;
             }
-            if (cnt) hist_add<HB>(V.hist, cur, cnt);
         }
     }
     __syncwarp();
 
-    // 3. bin_bands + select_band (alignment.c:130-181); the histogram is zeroed as it is read
-    int a = anchor_rel;
-    a = a < -1 ? -1 : (a > numdiag ? numdiag : a);                // clamping keeps every comparison
+    // 3. bin_bands + select_band (alignment.c:130-181) and zeroing of the histogram
     int idx;
     constexpr int PER = 32 / HB;                                  // counters per word
     if (g == 0) {
-        // pass 1: the largest count (per-byte / per-halfword SIMD max); pass 2: among the diagonals that
-        // reach it, the one nearest to a, the lower index on equal distance.  For a fixed a the pair
-        // (distance, side) orders exactly like 2 * distance + (i > a).
-        const int nq = ((numdiag + PER - 1) / PER + 3) / 4;       // uint4 chunks
-        uint4* h4 = reinterpret_cast<uint4*>(V.hist);
-        uint32_t m = 0;
-        for (int q = lane; q < nq; q += 32) {
-            const uint4 v = h4[q];
-            if (HB == 8) m = __vmaxu4(m, __vmaxu4(__vmaxu4(v.x, v.y), __vmaxu4(v.z, v.w)));
-            else         m = __vmaxu2(m, __vmaxu2(__vmaxu2(v.x, v.y), __vmaxu2(v.z, v.w)));
-        }
-        if (HB == 8) { m = __vmaxu4(m, m >> 16); m = max(m & 0xFFu, (m >> 8) & 0xFFu); }
-        else         { m = max(m & 0xFFFFu, m >> 16); }
-        const uint32_t cmax = __reduce_max_sync(0xFFFFFFFFu, m);
-        uint32_t bestkey = 0xFFFFFFFFu;
+        const uint32_t cmax = __reduce_max_sync(0xFFFFFFFFu, lbest);
         if (cmax == 0u) {                                         // no vote at all: the index nearest to a
             idx = a < 0 ? 0 : (a > numdiag - 1 ? numdiag - 1 : a);
         } else {
-            const uint32_t rep = (HB == 8) ? cmax * 0x01010101u : cmax * 0x00010001u;
-            for (int q = lane; q < nq; q += 32) {
-                const uint4 v = h4[q];
-                h4[q] = make_uint4(0u, 0u, 0u, 0u);
-                uint32_t e0, e1, e2, e3;
-                if (HB == 8) { e0 = __vcmpeq4(v.x, rep); e1 = __vcmpeq4(v.y, rep); e2 = __vcmpeq4(v.z, rep); e3 = __vcmpeq4(v.w, rep); }
-                else         { e0 = __vcmpeq2(v.x, rep); e1 = __vcmpeq2(v.y, rep); e2 = __vcmpeq2(v.z, rep); e3 = __vcmpeq2(v.w, rep); }
-                if ((e0 | e1 | e2 | e3) == 0u) continue;
-#pragma unroll 1
-                for (int u = 0; u < 4; u++) {
-                    uint32_t e = u == 0 ? e0 : (u == 1 ? e1 : (u == 2 ? e2 : e3));
-                    while (e) {
-                        const int s = (__ffs(e) - 1) / HB;
-                        e &= ~(((HB == 8) ? 0xFFu : 0xFFFFu) << (s * HB));
-                        const int i = (q * 4 + u) * PER + s;
-                        if (i >= numdiag) continue;
-                        const uint32_t dist = (uint32_t)(a > i ? a - i : i - a);
-                        const uint32_t key = 2u * dist + (i > a ? 1u : 0u);
-                        bestkey = min(bestkey, key);
-                    }
-                }
-            }
-            bestkey = __reduce_min_sync(0xFFFFFFFFu, bestkey);
+            const uint32_t bestkey = __reduce_min_sync(0xFFFFFFFFu, lbest == cmax ? lkey : 0xFFFFFFFFu);
             idx = (bestkey & 1u) ? a + (int)(bestkey >> 1) : a - (int)(bestkey >> 1);
+            const int nq = ((numdiag + PER - 1) / PER + 3) / 4;   // uint4 chunks
+            uint4* h4 = reinterpret_cast<uint4*>(V.hist);
+            #pragma unroll 1
+            for (int q = lane; q < nq; q += 32) h4[q] = make_uint4(0u, 0u, 0u, 0u);
         }
     } else {
         unsigned long long best = 0;
+        #pragma unroll 1
         for (int i = lane; i < numdiag; i += 32) {
             uint32_t b = 0;
             if (i < numdiag - g)
+                #pragma unroll 1
                 for (int j = 0; j <= g; j++) {
                     const int t = i + j;
                     b += (HB == 8) ? ((V.hist[t >> 2] >> ((t & 3) * 8)) & 0xFFu) : ((V.hist[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu);
@@ -372,14 +361,17 @@ __device__ __forceinline__ int vote_band_warp(const DevParams& P, WarpView& V, c
         }
         best = warp_max_u64(best);
         __syncwarp();
+        #pragma unroll 1
         for (int s = lane; s < (numdiag + PER - 1) / PER + 1 && s < V.L.hist_words; s += 32) V.hist[s] = 0;
         idx = (int)(0x1FFFFFu - (uint32_t)(best & 0x1FFFFFu));
     }
 
     // 4. leave the table clean for the next vote
     if (DIRECT) {
+        #pragma unroll 1
         for (int i = lane; i < nk; i += 32) tab_store<HB>(V, kmer_at(V.pk, zs2 + i, kmask), 0u);
     } else {
+        #pragma unroll 1
         for (int s = lane; s < V.L.hash_slots; s += 32) { V.keys[s] = kEmptyKey; V.vals[s] = 0; }
     }
     __syncwarp();
