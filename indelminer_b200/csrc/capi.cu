@@ -73,6 +73,8 @@ struct indelgpu_ctx {
     int sms = 0;
     int max_smem_optin = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t st_in = nullptr, st_out = nullptr;   // H2D / D2H streams of the chunked host path
+    std::vector<cudaEvent_t> ev_in, ev_k;             // per chunk: inputs landed, kernel done
     indelgpu_params params;
     DevParams P;
     // reference
@@ -119,6 +121,8 @@ static int ctx_init(indelgpu_ctx* c, int device, const indelgpu_params* p)
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (prop.major < 10) return fail(INDELGPU_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
     c->params = *p;
     c->P.k = p->klength; c->P.g = p->numgaps; c->P.maxdel = p->maxdelsize; c->P.ethr = p->ethreshold;
     c->P.match = p->match; c->P.mismatch = p->mismatch; c->P.G = p->gapopen; c->P.H = p->gapextend;
@@ -144,6 +148,10 @@ extern "C" void indelgpu_destroy(indelgpu_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->st_in) { cudaStreamSynchronize(c->st_in); cudaStreamDestroy(c->st_in); }
+    if (c->st_out) { cudaStreamSynchronize(c->st_out); cudaStreamDestroy(c->st_out); }
+    for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
     DevBuf* all[] = {&c->ref_raw, &c->ref_packed, &c->ref_off, &c->ref_len, &c->in_reads, &c->in_off, &c->in_tid,
                      &c->in_pos, &c->in_rng, &c->out_status, &c->out_nseg, &c->out_rstart, &c->out_segoff,
                      &c->out_segs, &c->out_detail, &c->out_cig1, &c->out_cig2, &c->counters, &c->scratch,
@@ -251,8 +259,11 @@ static int ensure_scratch(indelgpu_ctx* c, int blocks, int max_read, BandScratch
     return 0;
 }
 
+// keep_totals: a later chunk of the same batch -- only the work counter is reset, the segment
+// counter, the cell totals and the error flag keep accumulating
 static int launch_realign(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_read, int max_range1,
-                          indelgpu_result* d_out, unsigned long long* d_seg_count, cudaStream_t st)
+                          indelgpu_result* d_out, unsigned long long* d_seg_count, cudaStream_t st,
+                          bool keep_totals = false)
 {
     if (c->ncontigs <= 0) return fail(INDELGPU_EINVAL, "realign: no reference uploaded (indelgpu_set_reference)");
     if (max_read <= 0 || max_read > 65000) return fail(INDELGPU_ELIMIT, "read length %d outside 1..65000", max_read);
@@ -286,8 +297,11 @@ static int launch_realign(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_r
     a.max_read = max_read; a.max_numdiag = max_numdiag; a.L = L;
     if (ensure_scratch(c, blocks * wpc, max_read, &a.scratch)) return INDELGPU_ENOMEM;
 
-    CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
-    if (d_seg_count != ctr_segs(c)) CU(cudaMemsetAsync(d_seg_count, 0, 8, st));
+    if (keep_totals) CU(cudaMemsetAsync(c->counters.p, 0, 4, st));
+    else {
+        CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
+        if (d_seg_count != ctr_segs(c)) CU(cudaMemsetAsync(d_seg_count, 0, 8, st));
+    }
     kern<<<blocks, wpc * 32, (size_t)wpc * L.total, st>>>(a);
     c->launches++;
     CU(cudaGetLastError());
@@ -352,14 +366,6 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
     if (o->cigar1 && c->out_cig1.ensure(cigbytes + 4)) return INDELGPU_ENOMEM;
     if (o->cigar2 && c->out_cig2.ensure(cigbytes + 4)) return INDELGPU_ENOMEM;
 
-    CU(cudaMemcpyAsync(c->in_reads.p, h->read_bases, (size_t)nbases, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->in_off.p, h->read_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->in_tid.p, h->tid, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->in_pos.p, h->position, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->in_rng.p, h->range1, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
-    if (o->cigar1) CU(cudaMemsetAsync(c->out_cig1.p, 0, cigbytes, st));
-    if (o->cigar2) CU(cudaMemsetAsync(c->out_cig2.p, 0, cigbytes, st));
-
     indelgpu_batch din = *h;
     din.read_bases = c->in_reads.as<uint8_t>(); din.read_off = c->in_off.as<int64_t>();
     din.tid = c->in_tid.as<int32_t>(); din.position = c->in_pos.as<int32_t>(); din.range1 = c->in_rng.as<int32_t>();
@@ -369,16 +375,63 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
     dout.detail = o->detail ? c->out_detail.as<indelgpu_detail>() : nullptr;
     dout.cigar1 = o->cigar1 ? c->out_cig1.as<uint32_t>() : nullptr;
     dout.cigar2 = o->cigar2 ? c->out_cig2.as<uint32_t>() : nullptr;
-    int rc = launch_realign(c, &din, max_read, max_range, &dout, ctr_segs(c), st);
-    if (rc) return rc;
 
-    CU(cudaMemcpyAsync(o->status, dout.status, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(o->nseg, dout.nseg, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(o->rstart, dout.rstart, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(o->seg_off, dout.seg_off, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (o->detail) CU(cudaMemcpyAsync(o->detail, dout.detail, sizeof(indelgpu_detail) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (o->cigar1) CU(cudaMemcpyAsync(o->cigar1, dout.cigar1, cigbytes, cudaMemcpyDeviceToHost, st));
-    if (o->cigar2) CU(cudaMemcpyAsync(o->cigar2, dout.cigar2, cigbytes, cudaMemcpyDeviceToHost, st));
+    // Large batches without debug outputs are cut into chunks so that the H2D copy of chunk i+1 and
+    // the D2H copy of chunk i-1 overlap the kernel of chunk i (three streams, two events per chunk).
+    // Chunks share the reference, the segment allocator and the counters; read offsets stay absolute.
+    const bool debug_out = o->detail || o->cigar1 || o->cigar2;
+    int kChunkReads = 1 << 17;
+    if (const char* e = getenv("INDELGPU_CHUNK_READS")) { const int v = atoi(e); if (v >= 64) kChunkReads = v; }
+    const int nchunks = (debug_out || n < 2 * kChunkReads) ? 1 : (n + kChunkReads - 1) / kChunkReads;
+    if (nchunks > 1) {
+        while ((int)c->ev_in.size() < nchunks) {
+            cudaEvent_t e1, e2;
+            CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            c->ev_in.push_back(e1); c->ev_k.push_back(e2);
+        }
+        CU(cudaMemcpyAsync(c->in_off.p, h->read_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->st_in));
+        for (int ch = 0; ch < nchunks; ch++) {
+            const int c0 = ch * kChunkReads, c1 = std::min(n, c0 + kChunkReads), m = c1 - c0;
+            const int64_t b0 = h->read_off[c0], b1 = h->read_off[c1];
+            CU(cudaMemcpyAsync(c->in_reads.as<uint8_t>() + b0, h->read_bases + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->st_in));
+            CU(cudaMemcpyAsync(c->in_tid.as<int32_t>() + c0, h->tid + c0, 4 * (size_t)m, cudaMemcpyHostToDevice, c->st_in));
+            CU(cudaMemcpyAsync(c->in_pos.as<int32_t>() + c0, h->position + c0, 4 * (size_t)m, cudaMemcpyHostToDevice, c->st_in));
+            CU(cudaMemcpyAsync(c->in_rng.as<int32_t>() + c0, h->range1 + c0, 4 * (size_t)m, cudaMemcpyHostToDevice, c->st_in));
+            CU(cudaEventRecord(c->ev_in[ch], c->st_in));
+            CU(cudaStreamWaitEvent(st, c->ev_in[ch], 0));
+            indelgpu_batch dc = din; dc.n = m;
+            dc.read_off = din.read_off + c0; dc.tid = din.tid + c0; dc.position = din.position + c0; dc.range1 = din.range1 + c0;
+            indelgpu_result rc2 = dout;
+            rc2.status = dout.status + c0; rc2.nseg = dout.nseg + c0; rc2.rstart = dout.rstart + c0; rc2.seg_off = dout.seg_off + c0;
+            int rcl = launch_realign(c, &dc, max_read, max_range, &rc2, ctr_segs(c), st, ch > 0);
+            if (rcl) return rcl;
+            CU(cudaEventRecord(c->ev_k[ch], st));
+            CU(cudaStreamWaitEvent(c->st_out, c->ev_k[ch], 0));
+            CU(cudaMemcpyAsync(o->status + c0, dout.status + c0, 4 * (size_t)m, cudaMemcpyDeviceToHost, c->st_out));
+            CU(cudaMemcpyAsync(o->nseg + c0, dout.nseg + c0, 4 * (size_t)m, cudaMemcpyDeviceToHost, c->st_out));
+            CU(cudaMemcpyAsync(o->rstart + c0, dout.rstart + c0, 4 * (size_t)m, cudaMemcpyDeviceToHost, c->st_out));
+            CU(cudaMemcpyAsync(o->seg_off + c0, dout.seg_off + c0, 8 * (size_t)m, cudaMemcpyDeviceToHost, c->st_out));
+        }
+        CU(cudaStreamSynchronize(c->st_out));
+    } else {
+        CU(cudaMemcpyAsync(c->in_reads.p, h->read_bases, (size_t)nbases, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->in_off.p, h->read_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->in_tid.p, h->tid, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->in_pos.p, h->position, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->in_rng.p, h->range1, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        if (o->cigar1) CU(cudaMemsetAsync(c->out_cig1.p, 0, cigbytes, st));
+        if (o->cigar2) CU(cudaMemsetAsync(c->out_cig2.p, 0, cigbytes, st));
+        int rc = launch_realign(c, &din, max_read, max_range, &dout, ctr_segs(c), st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(o->status, dout.status, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(o->nseg, dout.nseg, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(o->rstart, dout.rstart, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(o->seg_off, dout.seg_off, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (o->detail) CU(cudaMemcpyAsync(o->detail, dout.detail, sizeof(indelgpu_detail) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (o->cigar1) CU(cudaMemcpyAsync(o->cigar1, dout.cigar1, cigbytes, cudaMemcpyDeviceToHost, st));
+        if (o->cigar2) CU(cudaMemcpyAsync(o->cigar2, dout.cigar2, cigbytes, cudaMemcpyDeviceToHost, st));
+    }
     CU(cudaMemcpyAsync(c->pinned_small, c->counters.p, 64, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     unsigned long long segcount; int err;

@@ -339,3 +339,24 @@ def test_large_batch_properties(gpu, oracle):
     ndel = int(((a.status == 6)).sum())
     assert ndel > n // 4
     R.close()
+
+
+def test_chunked_host_path_equals_single_launch(gpu, monkeypatch):
+    """indelgpu_realign_batch cuts large batches into chunks whose copies overlap the kernels;
+    the results must not depend on the chunking."""
+    from indelminer_b200 import synth
+    ref = synth.make_reference(400_000, seed=21)
+    w = synth.make_candidates(ref, 6000, seed=22)
+    R = gpu.Realigner()
+    R.set_reference([ref.tobytes()])
+    args = (None, w["tid"], w["position"], w["range1"])
+    a = R.attempt_pe_alignment_batch(*args, packed=(w["read_bases"], w["read_off"]))
+    monkeypatch.setenv("INDELGPU_CHUNK_READS", "1000")
+    b = R.attempt_pe_alignment_batch(*args, packed=(w["read_bases"], w["read_off"]))
+    assert b.launches == 6 and a.launches == 1
+    assert np.array_equal(a.status, b.status) and np.array_equal(a.nseg, b.nseg) and np.array_equal(a.rstart, b.rstart)
+    assert a.seg_count == b.seg_count == int(a.nseg.sum())
+    assert a.cells == b.cells and a.alg_bytes == b.alg_bytes
+    for i in range(6000):
+        assert list(a.words(i)) == list(b.words(i)), i
+    R.close()
