@@ -153,6 +153,14 @@ int indelgpu_realign_batch_device(indelgpu_ctx* ctx, const indelgpu_batch* d_in,
  *   out[3]     algorithmic bytes: sum over alignments of N + M + 4 * (6 + ncigar) */
 int indelgpu_last_counters(indelgpu_ctx* ctx, int64_t out[4]);
 
+/* device time (CUDA events on the context's stream) of the kernel the last
+ * indelgpu_band_align_batch call launched, in ms; < 0 when nothing was timed */
+double indelgpu_last_kernel_ms(indelgpu_ctx* ctx);
+
+/* measured INT32 issue rate of this GPU in Gop/s (independent add + max chains): the denominator
+ * of the banded-DP roofline (it is not in MEASURED_PEAKS.json) */
+int indelgpu_int32_peak(indelgpu_ctx* ctx, double* gops);
+
 /* number of kernels the last indelgpu_realign_batch[_device] call launched */
 int indelgpu_last_launch_count(const indelgpu_ctx* ctx);
 

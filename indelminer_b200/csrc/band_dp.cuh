@@ -31,14 +31,24 @@ struct BandScratch {
 
 __host__ __device__ inline long long band_scratch_ints(int max_band, int max_rows)
 {
-    // cc dd cp dp | 2 x (hp dp) rolling rows | mp[3] fp | mt[3] ft | script | frames
-    return 8LL * (max_band + 4) + 8LL * (max_rows + 2) + (2LL * max_rows + max_band + 16) + 40 * 16;
+    // cc dd cp dp | 2 x (hp dp) rolling rows | mp[3] fp | mt[3] ft | script
+    return 8LL * (max_band + 4) + 8LL * (max_rows + 2) + (2LL * max_rows + max_band + 16);
 }
 
 __device__ __forceinline__ const int* band_script_ptr(const BandScratch& scr, int slot)
 {
     return scr.base + (long long)slot * scr.stride + 8 * (scr.max_band + 4) + 8 * (scr.max_rows + 2);
 }
+
+// int array view with an element stride: 1 = a plain array (one aligning lane per warp),
+// 32 = lane-interleaved scratch (element i of lane l at base[i * 32 + l]) so that the 32 alignments a
+// warp runs side by side -- one per thread -- touch one 128-byte line per access.
+template <int STRIDE>
+struct IArr {
+    int* p;
+    IG_HD int& operator[](int i) const { return p[(long long)i * STRIDE]; }
+    IG_HD IArr operator+(long long k) const { return IArr{p + k * STRIDE}; }
+};
 
 struct DcFrame {
     int a, b;                // offsets of the "1-based" views into read / window
@@ -47,38 +57,43 @@ struct DcFrame {
     int stage, k, l, kt, rmid, t2, t3, pad;
 };
 
+template <int STRIDE>
 struct DcCtx {
     const DevParams* P;
     const uint8_t* A;        // read slice, 0-based
     const uint8_t* B;        // window, 0-based
-    int *cc, *dd, *cp, *dp;
-    int *mp[3], *mt[3], *fp, *ft;
-    int* S; int ns; int last;
+    IArr<STRIDE> cc, dd, cp, dp;
+    IArr<STRIDE> mp[3], mt[3], fp, ft;
+    IArr<STRIDE> S; int ns; int last;
     int cells;
 };
 
-IG_HD inline void put_del(DcCtx& x, int k)      // globalalign.c:40-46
+template <int STRIDE>
+IG_HD inline void put_del(DcCtx<STRIDE>& x, int k)      // globalalign.c:40-46
 {
     if (x.last < 0) { x.S[x.ns - 1] -= k; x.last = x.S[x.ns - 1]; }
     else { x.S[x.ns++] = -k; x.last = -k; }
 }
-IG_HD inline void put_ins(DcCtx& x, int k)      // globalalign.c:48-54
+template <int STRIDE>
+IG_HD inline void put_ins(DcCtx<STRIDE>& x, int k)      // globalalign.c:48-54
 {
     if (x.last > 0) { x.S[x.ns - 1] += k; x.last = x.S[x.ns - 1]; }
     else { x.S[x.ns++] = k; x.last = k; }
 }
-IG_HD inline void put_rep(DcCtx& x) { x.S[x.ns++] = 0; x.last = 0; }
+template <int STRIDE>
+IG_HD inline void put_rep(DcCtx<STRIDE>& x) { x.S[x.ns++] = 0; x.last = 0; }
 
 // One sweep of align() (globalalign.c:95-258): fills the crossing list, returns through f the
 // first crossing row (k = r, or -1), its successor l and type kt.  a1/b1 index so that a1[1] is
 // the first symbol.
-IG_HD inline void dc_sweep(DcCtx& x, DcFrame& f)
+template <int STRIDE>
+IG_HD inline void dc_sweep(DcCtx<STRIDE>& x, DcFrame& f)
 {
     const int g = x.P->G, h = x.P->H, m = g + h;
     const uint8_t* a1 = x.A + f.a - 1;
     const uint8_t* b1 = x.B + f.b - 1;
     const int M = f.M, N = f.N, low = f.low, up = f.up, tb = f.tb, te = f.te;
-    int *CC = x.cc, *DD = x.dd, *CP = x.cp, *DP = x.dp;
+    const IArr<STRIDE> CC = x.cc, DD = x.dd, CP = x.cp, DP = x.dp;
     const int band = up - low + 1;
     const int midd = band / 2 + 1;
     const int rmid = low + midd - 1;
@@ -186,7 +201,8 @@ IG_HD inline void dc_push(DcFrame* st, int& sp, int a, int b, int M, int N,
 }
 
 // align() of globalalign.c:66-307 with the recursion unrolled into frames.
-IG_HD inline void dc_align(DcCtx& x, DcFrame* st, int a0, int b0, int M0, int N0, int low0, int up0)
+template <int STRIDE>
+IG_HD inline void dc_align(DcCtx<STRIDE>& x, DcFrame* st, int a0, int b0, int M0, int N0, int low0, int up0)
 {
     int sp = 0;
     dc_push(st, sp, a0, b0, M0, N0, low0, up0, 0, 0);
@@ -245,7 +261,8 @@ IG_HD inline void dc_align(DcCtx& x, DcFrame* st, int a0, int b0, int M0, int N0
 }
 
 // ALIGN (globalalign.c:333-401): A, B 0-based first symbols.  Returns the number of script entries.
-IG_HD inline int global_align_script(DcCtx& x, DcFrame* st, int M, int N, int low, int up)
+template <int STRIDE>
+IG_HD inline int global_align_script(DcCtx<STRIDE>& x, DcFrame* st, int M, int N, int low, int up)
 {
     x.ns = 0; x.last = 0;
     low = ig_min(ig_max(-M, low), ig_min(N - M, 0));                  // :347-348
@@ -258,18 +275,19 @@ IG_HD inline int global_align_script(DcCtx& x, DcFrame* st, int M, int N, int lo
 }
 
 // fetch_cigar (globalalign.c:507-604): A, B 0-based first ALIGNED symbols
-IG_HD inline int script_to_cigar(const uint8_t* A, const uint8_t* B, int M, int N, const int* S,
-                               int AP, int readlength, uint32_t* cig)
+template <class Script>
+IG_HD inline int script_to_cigar(const uint8_t* A, const uint8_t* B, int M, int N, const Script& S,
+                                 int AP, int readlength, uint32_t* cig)
 {
-    int n = 0, i = 0, j = 0;
+    int n = 0, i = 0, j = 0, k = 0;
     const int clip = AP - 1;
     if (clip > 0) cig[n++] = ((uint32_t)clip << 4) | OP_SOFT;
     int run_op = -1, run_len = 0, total = clip, pending = 0;
     while (i < M || j < N) {
         int op;
-        if (pending == 0 && *S == 0) { S++; op = (A[i] == B[j]) ? OP_EQ : OP_X; i++; j++; }
+        if (pending == 0 && S[k] == 0) { k++; op = (A[i] == B[j]) ? OP_EQ : OP_X; i++; j++; }
         else {
-            if (pending == 0) pending = *S++;
+            if (pending == 0) pending = S[k++];
             if (pending > 0) { pending--; j++; op = OP_DEL; }
             else             { pending++; i++; op = OP_INS; }
         }
@@ -284,22 +302,22 @@ IG_HD inline int script_to_cigar(const uint8_t* A, const uint8_t* B, int M, int 
 // local_align + ALIGN + fetch_cigar on a band of >= 2 diagonals, executed by ONE thread.
 // `low`/`up` are already clamped (localalign.c:70-71); `base` is this CTA's scratch slice.
 // out: score, q1, r1, q2, r2 (1-based inclusive, slice/window relative), ncigar, cells fwd, rev, glob, nscript
-IG_HD inline void align_banded_serial(const DevParams& P, int* base, int max_band, int max_rows,
+template <int STRIDE>
+IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> base, int max_band, int max_rows, DcFrame* st,
                                       const uint8_t* read, int M, const uint8_t* win, int N,
                                       int low, int up, uint32_t* cig, int* out)
 {
     const int G = P.G, H = P.H, m = G + H;
     const int band = up - low + 1;
     const int wb = max_band + 4, wr = max_rows + 2;
-    DcCtx x;
+    DcCtx<STRIDE> x;
     x.P = &P; x.A = read; x.B = win; x.cells = 0; x.ns = 0; x.last = 0;
     x.cc = base; x.dd = base + wb; x.cp = base + 2 * wb; x.dp = base + 3 * wb;
-    int* Hp = base + 4 * wb; int* Dp = base + 5 * wb; int* Hn = base + 6 * wb; int* Dn = base + 7 * wb;
-    int* rows = base + 8 * wb;
+    IArr<STRIDE> Hp = base + 4 * wb, Dp = base + 5 * wb, Hn = base + 6 * wb, Dn = base + 7 * wb;
+    const IArr<STRIDE> rows = base + 8 * wb;
     x.mp[0] = rows; x.mp[1] = rows + wr; x.mp[2] = rows + 2 * wr; x.fp = rows + 3 * wr;
     x.mt[0] = rows + 4 * wr; x.mt[1] = rows + 5 * wr; x.mt[2] = rows + 6 * wr; x.ft = rows + 7 * wr;
     x.S = rows + 8 * wr;
-    DcFrame* st = reinterpret_cast<DcFrame*>(x.S + (2 * max_rows + max_band + 16));
 #define AT(arr, t) ((arr)[(t) + 1])
     // forward (localalign.c:82-131)
     const int si = ig_max(0, -up), ei = ig_min(M, N - low);
@@ -331,7 +349,7 @@ IG_HD inline void align_banded_serial(const DevParams& P, int* base, int max_ban
             if (c > best) { best = c; endi = i; endj = j; }
         }
         cf += thi - tlo + 1;
-        int* tmp = Hp; Hp = Hn; Hn = tmp; tmp = Dp; Dp = Dn; Dn = tmp;
+        IArr<STRIDE> tmp = Hp; Hp = Hn; Hn = tmp; tmp = Dp; Dp = Dn; Dn = tmp;
     }
     // reverse (localalign.c:132-176)
     int starti = 0, startj = 0; bool found = false;
@@ -369,7 +387,7 @@ IG_HD inline void align_banded_serial(const DevParams& P, int* base, int max_ban
                 cr++;
                 if (c == best) { starti = i; startj = j; found = true; break; }
             }
-            int* tmp = Hp; Hp = Hn; Hn = tmp; tmp = Dp; Dp = Dn; Dn = tmp;
+            IArr<STRIDE> tmp = Hp; Hp = Hn; Hn = tmp; tmp = Dp; Dp = Dn; Dn = tmp;
         }
     }
 #undef AT
@@ -388,17 +406,22 @@ IG_HD inline void align_banded_serial(const DevParams& P, int* base, int max_ban
     out[9] = none ? 0 : x.ns;         // script entries, left at band_script_ptr()
 }
 
+constexpr int kDcFrames = 24;     // recursion depth <= log2(band) + 2 (every child band is at most half its parent's)
+
 #ifdef __CUDACC__
-// warp-wide entry.  Version 1: lane 0 runs the sweeps sequentially (exact by construction);
-// the other lanes wait.
+// warp-wide entry used by the fused realign kernel: lane 0 runs the sweeps sequentially (exact by
+// construction); the other lanes wait.  The throughput path for wide bands is band_tasks_kernel
+// (task_kernels.cuh): one alignment per THREAD on lane-interleaved scratch.
 __device__ inline void align_banded(const DevParams& P, const BandScratch& scr, int slot, const uint8_t* read, int M,
                                     const uint8_t* __restrict__ win, int N, int low, int up,
                                     uint32_t* cig, int ops_cap, int* s_out)
 {
     (void)ops_cap;
-    if ((threadIdx.x & 31) == 0)
-        align_banded_serial(P, scr.base + (long long)slot * scr.stride, scr.max_band, scr.max_rows,
-                            read, M, win, N, low, up, cig, s_out);
+    if ((threadIdx.x & 31) == 0) {
+        DcFrame st[kDcFrames];
+        align_banded_serial<1>(P, IArr<1>{scr.base + (long long)slot * scr.stride}, scr.max_band, scr.max_rows, st,
+                               read, M, win, N, low, up, cig, s_out);
+    }
     __syncwarp();
 }
 #endif

@@ -75,6 +75,8 @@ struct indelgpu_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t st_in = nullptr, st_out = nullptr;   // H2D / D2H streams of the chunked host path
     std::vector<cudaEvent_t> ev_in, ev_k;             // per chunk: inputs landed, kernel done
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;     // around the kernel(s) of the last batch call
+    bool timed = false;
     indelgpu_params params;
     DevParams P;
     // reference
@@ -121,6 +123,8 @@ static int ctx_init(indelgpu_ctx* c, int device, const indelgpu_params* p)
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (prop.major < 10) return fail(INDELGPU_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev_t0));
+    CU(cudaEventCreate(&c->ev_t1));
     CU(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
     c->params = *p;
@@ -150,6 +154,8 @@ extern "C" void indelgpu_destroy(indelgpu_ctx* c)
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     if (c->st_in) { cudaStreamSynchronize(c->st_in); cudaStreamDestroy(c->st_in); }
     if (c->st_out) { cudaStreamSynchronize(c->st_out); cudaStreamDestroy(c->st_out); }
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
     DevBuf* all[] = {&c->ref_raw, &c->ref_packed, &c->ref_off, &c->ref_len, &c->in_reads, &c->in_off, &c->in_tid,
@@ -319,6 +325,55 @@ extern "C" int indelgpu_realign_batch_device(indelgpu_ctx* c, const indelgpu_bat
     if (d_in->n == 0) return 0;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     return launch_realign(c, d_in, max_read_len, max_range1, d_out, reinterpret_cast<unsigned long long*>(d_seg_count), st);
+}
+
+extern "C" double indelgpu_last_kernel_ms(indelgpu_ctx* c)
+{
+    if (!c || !c->timed) return -1.0;
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaEventSynchronize(c->ev_t1) != cudaSuccess) return -1.0;
+    float ms = -1.0f;
+    if (cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+// INT32 issue-rate micro-benchmark (the denominator of the banded-DP roofline is
+// measured on the box, it is not in MEASURED_PEAKS.json): dependency-free add + max chains.
+__global__ void int32_peak_kernel(int iters, int seed, int* out)
+{
+    int v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = (int)threadIdx.x * (u + 1) + seed;
+    const int b = (int)blockIdx.x - seed;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = max(v[u] + b, i - u);        // one add and one max per statement
+    }
+    int r = 0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) r ^= v[u];
+    if (r == 0x7FFFFFFF) out[0] = r;
+}
+
+extern "C" int indelgpu_int32_peak(indelgpu_ctx* c, double* gops)
+{
+    if (!c || !gops) return fail(INDELGPU_EINVAL, "int32_peak: NULL argument");
+    CU(cudaSetDevice(c->device));
+    if (c->t_ncig.ensure(16)) return INDELGPU_ENOMEM;
+    const int iters = 1 << 14, blocks = c->sms * 16, threads = 256;
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(c->ev_t0, c->stream));
+        int32_peak_kernel<<<blocks, threads, 0, c->stream>>>(iters, rep, c->t_ncig.as<int>());
+        CU(cudaEventRecord(c->ev_t1, c->stream));
+        CU(cudaGetLastError());
+        CU(cudaEventSynchronize(c->ev_t1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+        const double ops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;   // add + max
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3) / 1e9);
+    }
+    *gops = best;
+    return 0;
 }
 
 extern "C" int indelgpu_last_counters(indelgpu_ctx* c, int64_t out[4])
@@ -557,13 +612,6 @@ extern "C" int indelgpu_band_align_batch(indelgpu_ctx* c, int32_t n, const uint8
     CU(cudaMemcpyAsync(c->t_low.p, h_low, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->t_up.p, h_up, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
 
-    const SmemLayout L = make_layout(max_read, 0);
-    if (L.total > c->max_smem_optin - 1024) return fail(INDELGPU_ELIMIT, "read too long for shared memory (%d bytes)", L.total);
-    CU(cudaFuncSetAttribute(align_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align_tasks_kernel, 32, L.total));
-    if (occ < 1) return fail(INDELGPU_ELIMIT, "align kernel does not fit on an SM");
-    const int blocks = (int)std::min<long long>((long long)c->sms * occ, n);
     TaskArgs a; memset(&a, 0, sizeof(a));
     a.P = c->P; a.n = n;
     a.reads = c->t_reads.as<uint8_t>(); a.read_off = c->t_roff.as<int64_t>();
@@ -575,15 +623,44 @@ extern "C" int indelgpu_band_align_batch(indelgpu_ctx* c, int32_t n, const uint8
     a.work_counter = ctr_work(c); a.cell_totals = ctr_cells(c); a.error_flag = ctr_err(c);
     a.max_read = max_read; a.max_numdiag = 0;
     a.scratch.base = nullptr; a.scratch.stride = 0; a.scratch.max_band = 0; a.scratch.max_rows = 0;
-    if (max_band > 1) {
-        const int mb = 2 * max_band;
-        const long long ints = band_scratch_ints(mb, max_read);
-        if (c->scratch.ensure((size_t)ints * 4 * (size_t)blocks)) return INDELGPU_ENOMEM;
-        a.scratch.base = c->scratch.as<int>(); a.scratch.stride = ints; a.scratch.max_band = mb; a.scratch.max_rows = max_read;
-    }
     CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
     if (h_cigar) CU(cudaMemsetAsync(c->t_cig.p, 0, 4 * (size_t)n * (size_t)cigar_stride, st));
-    align_tasks_kernel<<<blocks, 32, L.total, st>>>(a);
+    c->timed = false;
+    if (max_band > 1) {
+        // one alignment per thread on lane-interleaved scratch (band_tasks_kernel)
+        const int need = 2 * max_read + max_band + 4;
+        if (h_cigar && cigar_stride < need)
+            return fail(INDELGPU_EINVAL, "band_align_batch: cigar_stride %d too small for band %d (need %d)", cigar_stride, max_band, need);
+        if (!h_cigar) {                                  // the kernel always needs somewhere to build the CIGAR
+            if (c->t_cig.ensure(4 * (size_t)n * (size_t)need + 4)) return INDELGPU_ENOMEM;
+            a.cigar = c->t_cig.as<uint32_t>(); a.cigar_stride = need;
+        }
+        CU(cudaFuncSetAttribute(band_tasks_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, band_tasks_kernel, 128, 0));
+        if (occ < 1) return fail(INDELGPU_ELIMIT, "band kernel does not fit on an SM");
+        const int blocks = (int)std::min<long long>((long long)c->sms * occ, (n + 127) / 128);
+        const int mb = 2 * max_band;
+        const long long ints = band_scratch_ints(mb, max_read);
+        if (c->scratch.ensure((size_t)ints * 4 * 128 * (size_t)blocks)) return INDELGPU_ENOMEM;
+        a.scratch.base = c->scratch.as<int>(); a.scratch.stride = ints; a.scratch.max_band = mb; a.scratch.max_rows = max_read;
+        CU(cudaEventRecord(c->ev_t0, st));
+        band_tasks_kernel<<<blocks, 128, 0, st>>>(a);
+        CU(cudaEventRecord(c->ev_t1, st));
+        c->timed = true;
+    } else {
+        const SmemLayout L = make_layout(max_read, 0);
+        if (L.total > c->max_smem_optin - 1024) return fail(INDELGPU_ELIMIT, "read too long for shared memory (%d bytes)", L.total);
+        CU(cudaFuncSetAttribute(align_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align_tasks_kernel, 32, L.total));
+        if (occ < 1) return fail(INDELGPU_ELIMIT, "align kernel does not fit on an SM");
+        const int blocks = (int)std::min<long long>((long long)c->sms * occ, n);
+        CU(cudaEventRecord(c->ev_t0, st));
+        align_tasks_kernel<<<blocks, 32, L.total, st>>>(a);
+        CU(cudaEventRecord(c->ev_t1, st));
+        c->timed = true;
+    }
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h_score, a.score, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));

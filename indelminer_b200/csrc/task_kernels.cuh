@@ -142,22 +142,79 @@ align_tasks_kernel(const __grid_constant__ TaskArgs a)
     }
 }
 
+// local_align + ALIGN + fetch_cigar over n tasks, ONE THREAD PER TASK (inter-task parallelism).
+// At the band widths the caller produces (numgaps + 1 diagonals, typically <= 17) one anti-diagonal
+// of a band holds at most band/2 independent cells, so a wavefront inside one alignment would leave
+// most of a warp idle; 32 independent alignments per warp keep every lane busy, and the
+// lane-interleaved scratch (IArr<32>) turns the per-cell work-array traffic into full 128-byte lines
+// that stay in L1.  The exact divide-and-conquer of the reference runs unchanged per thread.
+__global__ void __launch_bounds__(128)
+band_tasks_kernel(const __grid_constant__ TaskArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    // scratch of warp w: [w * 32 * stride, (w + 1) * 32 * stride), lane l at element offset l
+    const IArr<32> base{a.scratch.base + (long long)gwarp * 32 * a.scratch.stride + lane};
+    unsigned long long cf = 0, cr = 0, cg = 0;
+    DcFrame st[kDcFrames];
+    for (int idx = gwarp * 32 + lane; idx < a.n; idx += nwarps * 32) {
+        const int64_t roff = a.read_off[idx], woff = a.ref_off[idx];
+        const int M = (int)(a.read_off[idx + 1] - roff), N = (int)(a.ref_off[idx + 1] - woff);
+        const int lo = max(-M, a.low[idx]), hi = min(N, a.up[idx]);       // localalign.c:70-71
+        const int band = hi - lo + 1;
+        const bool bad = M <= 0 || N <= 0 || band < 1 || 2 * band > a.scratch.max_band || M > a.scratch.max_rows ||
+                         (a.cigar && 2 * M + band + 4 > a.cigar_stride);
+        if (bad) {
+            a.score[idx] = 0; a.ncigar[idx] = 0;
+            for (int t = 0; t < 4; t++) a.ends[4 * idx + t] = 0;
+            atomicExch(a.error_flag, 1);
+            continue;
+        }
+        int out[10];
+        uint32_t* cig = a.cigar ? a.cigar + (int64_t)idx * a.cigar_stride : nullptr;
+        align_banded_serial<32>(a.P, base, a.scratch.max_band, a.scratch.max_rows, st,
+                                a.reads + roff, M, a.refs + woff, N, lo, hi, cig, out);
+        const int score = out[0];
+        a.score[idx] = score;
+        for (int t = 0; t < 4; t++) a.ends[4 * idx + t] = score > 0 ? out[1 + t] : 0;      // q1 r1 q2 r2
+        a.ncigar[idx] = score > 0 ? out[5] : 0;
+        cf += (unsigned long long)out[6]; cr += (unsigned long long)out[7]; cg += (unsigned long long)out[8];
+        if (score > 0 && a.script) {
+            int32_t* so = a.script + (int64_t)idx * a.script_stride;
+            const IArr<32> S = base + 8 * (a.scratch.max_band + 4) + 8 * (a.scratch.max_rows + 2);
+            const int len = out[9];
+            for (int t = 0; t < min(len, a.script_stride); t++) so[t] = S[t];
+            if (len < a.script_stride) so[len] = 0x7FFFFFFF;
+        }
+    }
+    // one atomic per warp and counter
+    cf = __reduce_add_sync(0xFFFFFFFFu, (unsigned)cf) + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(cf >> 32)) << 32);
+    cr = __reduce_add_sync(0xFFFFFFFFu, (unsigned)cr) + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(cr >> 32)) << 32);
+    cg = __reduce_add_sync(0xFFFFFFFFu, (unsigned)cg) + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(cg >> 32)) << 32);
+    if (lane == 0 && (cf | cr | cg)) {
+        atomicAdd(a.cell_totals + 0, cf);
+        atomicAdd(a.cell_totals + 1, cr);
+        atomicAdd(a.cell_totals + 2, cg);
+    }
+}
+
 // ALIGN (globalalign.c:333-401) for one pair; the score is the re-scored script
 // (CHECK_SCORE, globalalign.c:311-330, which the reference asserts equal to align()'s value)
 __global__ void global_align_one_kernel(DevParams P, BandScratch scr, const uint8_t* A, const uint8_t* B,
                                         int M, int N, int low, int up, int* out_script, int* out_meta)
 {
     if (threadIdx.x != 0) return;
-    int* base = scr.base;
+    const IArr<1> base{scr.base};
     const int wb = scr.max_band + 4, wr = scr.max_rows + 2;
-    DcCtx x;
+    DcCtx<1> x;
     x.P = &P; x.A = A; x.B = B; x.cells = 0;
     x.cc = base; x.dd = base + wb; x.cp = base + 2 * wb; x.dp = base + 3 * wb;
-    int* rows = base + 8 * wb;
+    const IArr<1> rows = base + 8 * wb;
     x.mp[0] = rows; x.mp[1] = rows + wr; x.mp[2] = rows + 2 * wr; x.fp = rows + 3 * wr;
     x.mt[0] = rows + 4 * wr; x.mt[1] = rows + 5 * wr; x.mt[2] = rows + 6 * wr; x.ft = rows + 7 * wr;
-    x.S = out_script;
-    DcFrame* st = reinterpret_cast<DcFrame*>(rows + 8 * wr + (2 * scr.max_rows + scr.max_band + 16));
+    x.S = IArr<1>{out_script};
+    DcFrame st[kDcFrames];
     const int ns = global_align_script(x, st, M, N, low, up);
     int score = 0, i = 0, j = 0;
     for (int t = 0; t < ns; t++) {

@@ -15,7 +15,7 @@ EXPORTS = [
     "indelgpu_create", "indelgpu_destroy", "indelgpu_device", "indelgpu_sm_count",
     "indelgpu_host_alloc", "indelgpu_host_free", "indelgpu_set_reference",
     "indelgpu_seg_bound", "indelgpu_realign_batch", "indelgpu_realign_batch_device",
-    "indelgpu_last_counters", "indelgpu_last_launch_count",
+    "indelgpu_last_counters", "indelgpu_last_launch_count", "indelgpu_last_kernel_ms", "indelgpu_int32_peak",
     "indelgpu_find_best_band_batch", "indelgpu_band_align_batch",
     "local_align", "ALIGN", "DISPLAY", "fetch_cigar",
 ]
@@ -77,6 +77,9 @@ def load():
                                                 C.POINTER(Result), C.c_void_p, C.c_void_p]
     L.indelgpu_last_counters.argtypes = [C.c_void_p, C.c_void_p]
     L.indelgpu_last_launch_count.argtypes = [C.c_void_p]
+    L.indelgpu_last_kernel_ms.restype = C.c_double
+    L.indelgpu_last_kernel_ms.argtypes = [C.c_void_p]
+    L.indelgpu_int32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.indelgpu_find_best_band_batch.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 7
     L.indelgpu_band_align_batch.argtypes = ([C.c_void_p, C.c_int32] + [C.c_void_p] * 10
                                             + [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p])

@@ -23,16 +23,21 @@ def harness():
                                "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO, SRC])
     L = C.CDLL(SO)
     L.hh_band_align.restype = C.c_int
+    L.hh_band_align_interleaved.restype = C.c_int
     return L
 
 
-def run(L, read, win, low, up, prm=(6, 0, 1000, 10, 1, -10, 10, 10)):
+def run(L, read, win, low, up, prm=(6, 0, 1000, 10, 1, -10, 10, 10), lane=None):
     read, win = read.encode(), win.encode()
     M, N = len(read), len(win)
     out = (C.c_int * 10)()
     cig = (C.c_uint32 * (2 * M + N + 8))()
     script = (C.c_int * (2 * M + N + 8))()
-    rc = L.hh_band_align((C.c_int * 8)(*prm), read, M, win, N, low, up, out, cig, script, len(script))
+    if lane is None:
+        rc = L.hh_band_align((C.c_int * 8)(*prm), read, M, win, N, low, up, out, cig, script, len(script))
+    else:
+        rc = L.hh_band_align_interleaved((C.c_int * 8)(*prm), read, M, win, N, low, up, out, cig, script,
+                                         len(script), lane)
     assert rc == 0
     return list(out), list(cig[:out[5]]), list(script[:out[9]])
 
@@ -74,3 +79,43 @@ def test_serial_banded_path_matches_oracle(harness, oracle):
             (_c, exp_cig, _s) = oracle.attempt_band_alignment(p, ref, 0, N, read, 0, M, low, up)
             assert cig == exp_cig, ctx
     assert npos > n // 2
+
+
+def test_interleaved_view_matches_oracle_incl_band_1(harness, oracle):
+    """the thread-per-alignment kernel runs this exact source on lane-interleaved scratch (IArr<32>),
+    also for bands of one diagonal"""
+    rng = make_rng(777)
+    p = oracle.default_params()
+    npos = 0
+    for it in range(1500):
+        alpha = rng.choice(["AC", "ACGT", "ACGTN"])
+        N = rng.randrange(8, 300)
+        ref = rseq(rng, N, alpha)
+        M = rng.randrange(1, 120)
+        if rng.random() < 0.8 and N > M + 2:
+            off = rng.randrange(0, N - M)
+            read = mutate(rng, ref[off:off + M], alpha, sub=rng.choice([0, 0.02, 0.1]),
+                          nindel=rng.randrange(0, 3), maxindel=12)
+            d = off + rng.randrange(-2, 3)
+        else:
+            read = rseq(rng, M, alpha)
+            d = rng.randrange(-M + 1, N)
+        M = len(read)
+        w = rng.choice([1, 1, 2, 5, 9, 17, 40])
+        low = d - w // 2
+        up = low + w - 1
+        if min(N, up) - max(-M, low) + 1 < 1:
+            continue
+        cells = oracle.Cells()
+        score, ends, script = oracle.local_align(p, read, ref, low, up, cells=cells)
+        out, cig, scr = run(harness, read, ref, low, up, lane=it % 32)
+        ctx = (read, ref, low, up)
+        assert out[0] == score, ctx
+        if score > 0:
+            npos += 1
+            assert tuple(out[1:5]) == ends, ctx
+            assert scr == script, ctx
+            (_c, exp_cig, _s) = oracle.attempt_band_alignment(p, ref, 0, N, read, 0, M, low, up)
+            assert cig == exp_cig, ctx
+            assert (out[6], out[7], out[8]) == (cells.fwd, cells.rev, cells.glob), ctx
+    assert npos > 500
