@@ -21,24 +21,21 @@ namespace indelgpu {
 IG_HD inline int ig_min(int a, int b) { return a < b ? a : b; }
 IG_HD inline int ig_max(int a, int b) { return a > b ? a : b; }
 
-// global-memory scratch, one slice per aligning warp
+// global-memory scratch of the thread-per-alignment kernels: per warp 32 * stride ints, lane-interleaved
 struct BandScratch {
     int* base;
-    long long stride;        // ints per CTA
+    long long stride;        // ints per thread (alignment)
     int max_band;            // widest band the slice was sized for (after ALIGN's widening)
     int max_rows;            // longest read
 };
 
 __host__ __device__ inline long long band_scratch_ints(int max_band, int max_rows)
 {
-    // cc dd cp dp | 2 x (hp dp) rolling rows | mp[3] fp | mt[3] ft | script
-    return 8LL * (max_band + 4) + 8LL * (max_rows + 2) + (2LL * max_rows + max_band + 16);
+    // band region: cc dd cp dp (ALIGN), aliased by the two rolling (H, D) rows of local_align
+    // rows region: mp[3] fp | mt[3] ft | script
+    return 4LL * (max_band + 4) + 8LL * (max_rows + 2) + (2LL * max_rows + max_band + 16);
 }
 
-__device__ __forceinline__ const int* band_script_ptr(const BandScratch& scr, int slot)
-{
-    return scr.base + (long long)slot * scr.stride + 8 * (scr.max_band + 4) + 8 * (scr.max_rows + 2);
-}
 
 // int array view with an element stride: 1 = a plain array (one aligning lane per warp),
 // 32 = lane-interleaved scratch (element i of lane l at base[i * 32 + l]) so that the 32 alignments a
@@ -302,8 +299,10 @@ IG_HD inline int script_to_cigar(const uint8_t* A, const uint8_t* B, int M, int 
 // local_align + ALIGN + fetch_cigar on a band of >= 2 diagonals, executed by ONE thread.
 // `low`/`up` are already clamped (localalign.c:70-71); `base` is this CTA's scratch slice.
 // out: score, q1, r1, q2, r2 (1-based inclusive, slice/window relative), ncigar, cells fwd, rev, glob, nscript
+// `bands`: 4 * (max_band + 4) ints (shared memory when it fits, else the head of the global slice);
+// `rowsb`: 8 * (max_rows + 2) ints + the script.
 template <int STRIDE>
-IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> base, int max_band, int max_rows, DcFrame* st,
+IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> bands, IArr<STRIDE> rowsb, int max_band, int max_rows, DcFrame* st,
                                       const uint8_t* read, int M, const uint8_t* win, int N,
                                       int low, int up, uint32_t* cig, int* out)
 {
@@ -312,16 +311,19 @@ IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> base, int
     const int wb = max_band + 4, wr = max_rows + 2;
     DcCtx<STRIDE> x;
     x.P = &P; x.A = read; x.B = win; x.cells = 0; x.ns = 0; x.last = 0;
-    x.cc = base; x.dd = base + wb; x.cp = base + 2 * wb; x.dp = base + 3 * wb;
-    IArr<STRIDE> Hp = base + 4 * wb, Dp = base + 5 * wb, Hn = base + 6 * wb, Dn = base + 7 * wb;
-    const IArr<STRIDE> rows = base + 8 * wb;
+    x.cc = bands; x.dd = bands + wb; x.cp = bands + 2 * wb; x.dp = bands + 3 * wb;
+    IArr<STRIDE> Hp = bands, Dp = bands + wb, Hn = bands + 2 * wb, Dn = bands + 3 * wb;    // done before ALIGN starts
+    const IArr<STRIDE> rows = rowsb;
     x.mp[0] = rows; x.mp[1] = rows + wr; x.mp[2] = rows + 2 * wr; x.fp = rows + 3 * wr;
     x.mt[0] = rows + 4 * wr; x.mt[1] = rows + 5 * wr; x.mt[2] = rows + 6 * wr; x.ft = rows + 7 * wr;
     x.S = rows + 8 * wr;
 #define AT(arr, t) ((arr)[(t) + 1])
     // forward (localalign.c:82-131)
     const int si = ig_max(0, -up), ei = ig_min(M, N - low);
-    for (int t = -1; t <= band; t++) { AT(Hp, t) = kNeg; AT(Dp, t) = kNeg; }
+    // Cells outside the band read as -infinity.  Row i+1 only reads row i inside [tlo(i) - 1, thi(i) + 1]
+    // (both limits move by at most one per row), so after one full fill it is enough to refresh the two
+    // entries just outside each row's range.
+    for (int t = -1; t <= band; t++) { AT(Hp, t) = kNeg; AT(Dp, t) = kNeg; AT(Hn, t) = kNeg; AT(Dn, t) = kNeg; }
     for (int t = 0; t < band; t++) {
         const int j = si + low + t;
         if (j >= 0 && j <= N) { AT(Hp, t) = 0; AT(Dp, t) = -G; }
@@ -329,7 +331,7 @@ IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> base, int
     int best = 0, endi = si, endj = si + low, cf = 0, cr = 0;
     for (int i = si + 1; i <= ei; i++) {
         const int tlo = ig_max(0, -i - low), thi = ig_min(band - 1, N - i - low);
-        for (int t = -1; t <= band; t++) { AT(Hn, t) = kNeg; AT(Dn, t) = kNeg; }
+        AT(Hn, tlo - 1) = kNeg; AT(Dn, tlo - 1) = kNeg; AT(Hn, thi + 1) = kNeg; AT(Dn, thi + 1) = kNeg;
         int e = kNeg, left = kNeg;
         const uint8_t ai = read[i - 1];
         for (int t = tlo; t <= thi; t++) {
@@ -355,7 +357,7 @@ IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> base, int
     int starti = 0, startj = 0; bool found = false;
     if (best > 0) {
         const int tend = (endj - endi) - low;
-        for (int t = -1; t <= band; t++) { AT(Hp, t) = kNeg; AT(Dp, t) = kNeg; }
+        for (int t = -1; t <= band; t++) { AT(Hp, t) = kNeg; AT(Dp, t) = kNeg; AT(Hn, t) = kNeg; AT(Dn, t) = kNeg; }
         {
             const int tl = ig_max(0, -endi - low);
             AT(Hp, tend) = 0; AT(Dp, tend) = -G;
@@ -363,9 +365,10 @@ IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> base, int
             for (int t = tend - 1; t >= tl; t--) { acc -= H; AT(Hp, t) = acc; AT(Dp, t) = acc - G; }
         }
         for (int i = endi; i >= 1 && !found; i--) {
-            for (int t = -1; t <= band; t++) { AT(Hn, t) = kNeg; AT(Dn, t) = kNeg; }
             const int thi = ig_min(band - 1, tend + (endi - i) + 1);
             const int tlo = ig_max(0, 1 - i - low);
+            if (tlo - 1 <= band) { AT(Hn, tlo - 1) = kNeg; AT(Dn, tlo - 1) = kNeg; }
+            if (thi + 1 <= band) { AT(Hn, thi + 1) = kNeg; AT(Dn, thi + 1) = kNeg; }
             int e = kNeg, right = kNeg;
             const uint8_t ai = read[i - 1];
             for (int t = thi; t >= tlo; t--) {
@@ -403,27 +406,10 @@ IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> base, int
     out[0] = none ? 0 : best;         // ALIGN's score equals the local optimum
     out[1] = starti; out[2] = startj; out[3] = endi; out[4] = endj;
     out[5] = n; out[6] = cf; out[7] = cr; out[8] = none ? 0 : x.cells;
-    out[9] = none ? 0 : x.ns;         // script entries, left at band_script_ptr()
+    out[9] = none ? 0 : x.ns;         // script entries, left in x.S
 }
 
 constexpr int kDcFrames = 24;     // recursion depth <= log2(band) + 2 (every child band is at most half its parent's)
 
-#ifdef __CUDACC__
-// warp-wide entry used by the fused realign kernel: lane 0 runs the sweeps sequentially (exact by
-// construction); the other lanes wait.  The throughput path for wide bands is band_tasks_kernel
-// (task_kernels.cuh): one alignment per THREAD on lane-interleaved scratch.
-__device__ inline void align_banded(const DevParams& P, const BandScratch& scr, int slot, const uint8_t* read, int M,
-                                    const uint8_t* __restrict__ win, int N, int low, int up,
-                                    uint32_t* cig, int ops_cap, int* s_out)
-{
-    (void)ops_cap;
-    if ((threadIdx.x & 31) == 0) {
-        DcFrame st[kDcFrames];
-        align_banded_serial<1>(P, IArr<1>{scr.base + (long long)slot * scr.stride}, scr.max_band, scr.max_rows, st,
-                               read, M, win, N, low, up, cig, s_out);
-    }
-    __syncwarp();
-}
-#endif
 
 }  // namespace indelgpu

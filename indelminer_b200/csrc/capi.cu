@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "band_dp.cuh"
 #include "realign_kernel.cuh"
+#include "realign_pipeline.cuh"
 #include "task_kernels.cuh"
 
 using namespace indelgpu;
@@ -88,6 +89,7 @@ struct indelgpu_ctx {
     DevBuf out_status, out_nseg, out_rstart, out_segoff, out_segs, out_detail, out_cig1, out_cig2;
     DevBuf counters;         // bytes: 0 work counter (int) | 8 seg count (u64) | 16 cells (3 x u64) | 40 error flag (int) | 48 algorithmic bytes (u64)
     DevBuf scratch;
+    DevBuf p_low, p_aln, p_cig, p_plan, p_flags;      // intermediates of the banded pipeline (realign_pipeline.cuh)
     // task API staging
     DevBuf t_reads, t_roff, t_refs, t_woff, t_packed, t_anchor, t_low, t_up, t_score, t_ends, t_ncig, t_cig, t_script;
     void* pinned_small = nullptr;   // 64 bytes for counter read-back
@@ -161,6 +163,7 @@ extern "C" void indelgpu_destroy(indelgpu_ctx* c)
     DevBuf* all[] = {&c->ref_raw, &c->ref_packed, &c->ref_off, &c->ref_len, &c->in_reads, &c->in_off, &c->in_tid,
                      &c->in_pos, &c->in_rng, &c->out_status, &c->out_nseg, &c->out_rstart, &c->out_segoff,
                      &c->out_segs, &c->out_detail, &c->out_cig1, &c->out_cig2, &c->counters, &c->scratch,
+                     &c->p_low, &c->p_aln, &c->p_cig, &c->p_plan, &c->p_flags,
                      &c->t_reads, &c->t_roff, &c->t_refs, &c->t_woff, &c->t_packed, &c->t_anchor, &c->t_low,
                      &c->t_up, &c->t_score, &c->t_ends, &c->t_ncig, &c->t_cig, &c->t_script};
     for (DevBuf* b : all) b->release();
@@ -254,14 +257,82 @@ static int plan_warps(indelgpu_ctx* c, Kern kern, int bytes_per_warp, int* warps
     return 0;
 }
 
-static int ensure_scratch(indelgpu_ctx* c, int blocks, int max_read, BandScratch* out)
+static void fill_realign_args(indelgpu_ctx* c, RealignArgs& a, const indelgpu_batch* d_in, indelgpu_result* d_out,
+                              unsigned long long* d_seg_count, int max_read, int max_numdiag, const WarpLayout& L)
 {
-    out->base = nullptr; out->stride = 0; out->max_band = 0; out->max_rows = 0;
-    if (c->P.g <= 0) return 0;
-    const int max_band = 2 * (c->P.g + 1);
-    const long long ints = band_scratch_ints(max_band, max_read);
-    if (c->scratch.ensure((size_t)ints * 4 * (size_t)blocks)) return INDELGPU_ENOMEM;
-    out->base = c->scratch.as<int>(); out->stride = ints; out->max_band = max_band; out->max_rows = max_read;
+    a.P = c->P;
+    a.ref.raw = c->ref_raw.as<uint8_t>(); a.ref.packed = c->ref_packed.as<uint32_t>();
+    a.ref.contig_off = c->ref_off.as<int64_t>(); a.ref.contig_len = c->ref_len.as<int64_t>(); a.ref.ncontigs = c->ncontigs;
+    a.n = d_in->n; a.reads = d_in->read_bases; a.read_off = d_in->read_off;
+    a.tid = d_in->tid; a.position = d_in->position; a.range1 = d_in->range1;
+    a.status = d_out->status; a.nseg = d_out->nseg; a.rstart = d_out->rstart; a.seg_off = d_out->seg_off;
+    a.segs = d_out->segs; a.seg_capacity = d_out->seg_capacity; a.seg_count = d_seg_count;
+    a.detail = d_out->detail; a.cigar1 = d_out->cigar1; a.cigar2 = d_out->cigar2; a.cigar_stride = d_out->cigar_stride;
+    a.work_counter = ctr_work(c); a.cell_totals = ctr_cells(c); a.error_flag = ctr_err(c);
+    a.max_read = max_read; a.max_numdiag = max_numdiag; a.L = L;
+    a.scratch.base = nullptr; a.scratch.stride = 0; a.scratch.max_band = 0; a.scratch.max_rows = 0;
+}
+
+// -g N > 0: vote / DP / vote / DP / combine (realign_pipeline.cuh)
+static int launch_pipeline(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_read, int max_numdiag, const WarpLayout& L,
+                           indelgpu_result* d_out, unsigned long long* d_seg_count, cudaStream_t st, bool keep_totals)
+{
+    const int n = d_in->n;
+    const int max_band = c->P.g + 1;
+    PipeBufs p;
+    p.cig_stride = 2 * max_read + max_band + 4;
+    if (c->p_low.ensure(8 * (size_t)n) || c->p_aln.ensure(2 * sizeof(Aln) * (size_t)n) || c->p_plan.ensure(sizeof(Plan) * (size_t)n) ||
+        c->p_flags.ensure(4 * (size_t)n) || c->p_cig.ensure(8 * (size_t)n * (size_t)p.cig_stride)) return INDELGPU_ENOMEM;
+    p.low = c->p_low.as<int32_t>(); p.aln = c->p_aln.as<Aln>(); p.cig = c->p_cig.as<uint32_t>();
+    p.plan = c->p_plan.as<Plan>(); p.flags = c->p_flags.as<int32_t>();
+
+    RealignArgs a;
+    fill_realign_args(c, a, d_in, d_out, d_seg_count, max_read, max_numdiag, L);
+
+    void (*vk)(RealignArgs, PipeBufs, int);
+    if (L.hist_bits == 8) vk = L.direct ? pipe_vote_kernel<true, 8> : pipe_vote_kernel<false, 8>;
+    else                  vk = L.direct ? pipe_vote_kernel<true, 16> : pipe_vote_kernel<false, 16>;
+    int wpc = 0, occ = 0;
+    if (int rc = plan_warps(c, vk, L.total, &wpc, &occ)) return rc;
+    const int vblocks = (int)std::min<long long>((long long)c->sms * occ, std::max(1, (n + wpc - 1) / wpc));
+
+    const int mb = 2 * max_band;
+    size_t dsmem = (size_t)128 * 4 * 4 * (size_t)(mb + 4);           // band work arrays of 128 threads
+    int bands_in_smem = 1;
+    if (dsmem > (size_t)72 * 1024) { dsmem = 0; bands_in_smem = 0; }
+    CU(cudaFuncSetAttribute(pipe_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+    int docc = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&docc, pipe_dp_kernel, 128, dsmem));
+    if (docc < 1) return fail(INDELGPU_ELIMIT, "banded DP kernel does not fit on an SM");
+    const int dblocks = (int)std::min<long long>((long long)c->sms * docc, (n + 127) / 128);
+    const long long ints = band_scratch_ints(mb, max_read);
+    if (c->scratch.ensure((size_t)ints * 4 * 128 * (size_t)dblocks)) return INDELGPU_ENOMEM;
+    a.scratch.base = c->scratch.as<int>(); a.scratch.stride = ints; a.scratch.max_band = mb; a.scratch.max_rows = max_read;
+
+    const int cper = (4 * p.cig_stride + 8) * 4 + 256;
+    int cw = 8;
+    while (cw > 1 && (size_t)cw * cper > (size_t)c->max_smem_optin) cw >>= 1;
+    if ((size_t)cw * cper > (size_t)c->max_smem_optin) return fail(INDELGPU_ELIMIT, "reads too long for the combine kernel's shared memory");
+    CU(cudaFuncSetAttribute(pipe_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cw * cper));
+    int cocc = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cocc, pipe_combine_kernel, cw * 32, (size_t)cw * cper));
+    if (cocc < 1) return fail(INDELGPU_ELIMIT, "combine kernel does not fit on an SM");
+    const int cblocks = (int)std::min<long long>((long long)c->sms * cocc, std::max(1, (n + cw - 1) / cw));
+
+    if (keep_totals) CU(cudaMemsetAsync(c->counters.p, 0, 4, st));
+    else {
+        CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
+        if (d_seg_count != ctr_segs(c)) CU(cudaMemsetAsync(d_seg_count, 0, 8, st));
+    }
+    for (int round = 0; round < 2; round++) {
+        vk<<<vblocks, wpc * 32, (size_t)wpc * L.total, st>>>(a, p, round);
+        CU(cudaGetLastError());
+        pipe_dp_kernel<<<dblocks, 128, dsmem, st>>>(a, p, round, bands_in_smem);
+        CU(cudaGetLastError());
+    }
+    pipe_combine_kernel<<<cblocks, cw * 32, (size_t)cw * cper, st>>>(a, p);
+    CU(cudaGetLastError());
+    c->launches += 5;
     return 0;
 }
 
@@ -278,30 +349,17 @@ static int launch_realign(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_r
     const int max_numdiag = (int)nd;
     const bool banded = c->P.g > 0;
     const WarpLayout L = make_warp_layout(c->P, max_read, max_numdiag, banded ? 1 : 0);
+    if (((uintptr_t)d_in->read_bases & 15) != 0) return fail(INDELGPU_EINVAL, "read_bases must be 16-byte aligned on the device (TMA bulk copies)");
+    if (banded) return launch_pipeline(c, d_in, max_read, max_numdiag, L, d_out, d_seg_count, st, keep_totals);
     void (*kern)(RealignArgs);
-    if (L.hist_bits == 8)
-        kern = banded ? (L.direct ? realign_kernel<true, true, 8> : realign_kernel<true, false, 8>)
-                      : (L.direct ? realign_kernel<false, true, 8> : realign_kernel<false, false, 8>);
-    else
-        kern = banded ? (L.direct ? realign_kernel<true, true, 16> : realign_kernel<true, false, 16>)
-                      : (L.direct ? realign_kernel<false, true, 16> : realign_kernel<false, false, 16>);
+    if (L.hist_bits == 8) kern = L.direct ? realign_kernel<true, 8> : realign_kernel<false, 8>;
+    else                  kern = L.direct ? realign_kernel<true, 16> : realign_kernel<false, 16>;
     int wpc = 0, occ = 0;
     if (int rc = plan_warps(c, kern, L.total, &wpc, &occ)) return rc;
     const int blocks = (int)std::min<long long>((long long)c->sms * occ, std::max(1, (d_in->n + wpc - 1) / wpc));
-    if (((uintptr_t)d_in->read_bases & 15) != 0) return fail(INDELGPU_EINVAL, "read_bases must be 16-byte aligned on the device (TMA bulk copies)");
 
     RealignArgs a;
-    a.P = c->P;
-    a.ref.raw = c->ref_raw.as<uint8_t>(); a.ref.packed = c->ref_packed.as<uint32_t>();
-    a.ref.contig_off = c->ref_off.as<int64_t>(); a.ref.contig_len = c->ref_len.as<int64_t>(); a.ref.ncontigs = c->ncontigs;
-    a.n = d_in->n; a.reads = d_in->read_bases; a.read_off = d_in->read_off;
-    a.tid = d_in->tid; a.position = d_in->position; a.range1 = d_in->range1;
-    a.status = d_out->status; a.nseg = d_out->nseg; a.rstart = d_out->rstart; a.seg_off = d_out->seg_off;
-    a.segs = d_out->segs; a.seg_capacity = d_out->seg_capacity; a.seg_count = d_seg_count;
-    a.detail = d_out->detail; a.cigar1 = d_out->cigar1; a.cigar2 = d_out->cigar2; a.cigar_stride = d_out->cigar_stride;
-    a.work_counter = ctr_work(c); a.cell_totals = ctr_cells(c); a.error_flag = ctr_err(c);
-    a.max_read = max_read; a.max_numdiag = max_numdiag; a.L = L;
-    if (ensure_scratch(c, blocks * wpc, max_read, &a.scratch)) return INDELGPU_ENOMEM;
+    fill_realign_args(c, a, d_in, d_out, d_seg_count, max_read, max_numdiag, L);
 
     if (keep_totals) CU(cudaMemsetAsync(c->counters.p, 0, 4, st));
     else {
@@ -635,17 +693,20 @@ extern "C" int indelgpu_band_align_batch(indelgpu_ctx* c, int32_t n, const uint8
             if (c->t_cig.ensure(4 * (size_t)n * (size_t)need + 4)) return INDELGPU_ENOMEM;
             a.cigar = c->t_cig.as<uint32_t>(); a.cigar_stride = need;
         }
-        CU(cudaFuncSetAttribute(band_tasks_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+        const int mb = 2 * max_band;
+        size_t smem = (size_t)128 * 4 * 4 * (size_t)(mb + 4);        // band work arrays of 128 threads
+        int bands_in_smem = 1;
+        if (smem > (size_t)72 * 1024) { smem = 0; bands_in_smem = 0; }
+        CU(cudaFuncSetAttribute(band_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, band_tasks_kernel, 128, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, band_tasks_kernel, 128, smem));
         if (occ < 1) return fail(INDELGPU_ELIMIT, "band kernel does not fit on an SM");
         const int blocks = (int)std::min<long long>((long long)c->sms * occ, (n + 127) / 128);
-        const int mb = 2 * max_band;
         const long long ints = band_scratch_ints(mb, max_read);
         if (c->scratch.ensure((size_t)ints * 4 * 128 * (size_t)blocks)) return INDELGPU_ENOMEM;
         a.scratch.base = c->scratch.as<int>(); a.scratch.stride = ints; a.scratch.max_band = mb; a.scratch.max_rows = max_read;
         CU(cudaEventRecord(c->ev_t0, st));
-        band_tasks_kernel<<<blocks, 128, 0, st>>>(a);
+        band_tasks_kernel<<<blocks, 128, smem, st>>>(a, bands_in_smem);
         CU(cudaEventRecord(c->ev_t1, st));
         c->timed = true;
     } else {

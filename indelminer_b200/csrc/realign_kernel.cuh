@@ -32,7 +32,7 @@ struct RealignArgs {
     int* error_flag;                   // set non-zero on a limit violation
     int max_read, max_numdiag;
     WarpLayout L;                      // per-warp shared-memory slice, computed by the host
-    BandScratch scratch;               // global scratch for bands wider than one diagonal (one slice per warp)
+    BandScratch scratch;               // lane-interleaved work arrays of the banded DP (pipe_dp_kernel)
 };
 
 // round-2 plan produced by lane 0 after round 1 (alignment.c:568-717)
@@ -100,19 +100,17 @@ __device__ __forceinline__ void make_plan(const DevParams& P, const Aln& A1, con
     pl->go = 1;
 }
 
-// attempt_band_alignment (alignment.c:343-391) by one warp: local_align + fetch_cigar + coordinate shift.
-// BANDED = false is the default-flag build (-g 0): every band is one diagonal, so the banded DP
-// (and its registers) is compiled out.
-template <bool BANDED>
-__device__ void band_alignment_warp(const RealignArgs& a, Cta& S, int slot, int64_t cbase,
+// attempt_band_alignment (alignment.c:343-391) by one warp for a band of ONE diagonal (-g 0):
+// local_align + fetch_cigar + coordinate shift.  Wider bands go through realign_pipeline.cuh.
+__device__ __forceinline__ void band_alignment_warp(const RealignArgs& a, Cta& S, int64_t cbase,
                                     uint32_t zs1, uint32_t e1, uint32_t zs2, uint32_t e2,
                                     int low, int up, uint32_t* cig, Aln* out, int* s_tmp)
 {
     const int N = (int)(e1 - zs1), M = (int)(e2 - zs2);
     const uint8_t* win = a.ref.raw + cbase + zs1;
     const int lo = max(-M, low), hi = min(N, up);                // localalign.c:70-71
-    if (!BANDED || hi - lo + 1 == 1) align_diag1(a.P, S, win, N, (int)zs2, M, lo, cig, s_tmp);
-    else align_banded(a.P, a.scratch, slot, S.read + zs2, M, win, N, lo, hi, cig, S.L.ops_cap, s_tmp);
+    (void)hi;
+    align_diag1(a.P, S, win, N, (int)zs2, M, lo, cig, s_tmp);
     if ((threadIdx.x & 31) == 0) {
         const int score = s_tmp[0];
         out->low = low; out->up = up; out->score = score;
@@ -125,6 +123,63 @@ __device__ void band_alignment_warp(const RealignArgs& a, Cta& S, int slot, int6
         out->cells_fwd = s_tmp[6]; out->cells_rev = s_tmp[7]; out->cells_glob = s_tmp[8];
     }
     __syncwarp();
+}
+
+// Second half of attempt_diagonal_alignments (alignment.c:719-758) plus the whole-read exit (:575-582),
+// by one warp: soft-clip bookkeeping of round 2, junction choice, segment stitching into S.segs.
+// s_final = {status, number of segment words, reference start, junction index}.
+__device__ __forceinline__ void combine_read(Cta& S, int readlen, Aln* s_aln, const Plan* s_plan, int* s_final, bool done2)
+{
+    const int lane = threadIdx.x & 31;
+    const Aln* s_a1 = s_aln; const Aln* s_a2 = s_aln + 1;
+    if (done2) {
+        const Plan pl = *s_plan;
+        const int q1 = s_a1->q1, q2 = s_a1->q2, r1 = s_a1->r1, r2 = s_a1->r2, n1 = s_a1->n;
+        const int q3 = s_a2->q1, q4 = s_a2->q2, r3 = s_a2->r1, r4 = s_a2->r2;
+        int n2 = s_a2->n;
+        const bool fail = pl.tail ? (q4 != readlen || q3 == q4) : (q3 != 0 || q3 == q4);
+        if (fail) { if (lane == 0) s_final[0] = INDELGPU_ST_R2FAIL; }
+        else {
+            if (lane == 0) {                 // add_prefix/suffix_soft_clip (:478-532)
+                if (pl.tail && pl.f_nonmatch) {
+                    if (cig_op(S.cig2[0]) == OP_SOFT) S.cig2[0] = ((uint32_t)(cig_len(S.cig2[0]) + (int)pl.f_nonmatch) << 4) | OP_SOFT;
+                    else { for (int t = n2; t > 0; t--) S.cig2[t] = S.cig2[t - 1]; S.cig2[0] = (pl.f_nonmatch << 4) | OP_SOFT; n2++; }
+                } else if (!pl.tail && pl.l_nonmatch) {
+                    if (cig_op(S.cig2[n2 - 1]) == OP_SOFT) S.cig2[n2 - 1] = ((uint32_t)(cig_len(S.cig2[n2 - 1]) + (int)pl.l_nonmatch) << 4) | OP_SOFT;
+                    else { S.cig2[n2] = (pl.l_nonmatch << 4) | OP_SOFT; n2++; }
+                }
+                s_aln[1].n = n2;
+            }
+            n2 = __shfl_sync(0xFFFFFFFFu, n2, 0);
+            __syncwarp();
+            // combine (:719-758).  "first" = the segment earlier on the read.
+            int mode = 0;
+            if (q1 > q3 && q1 <= q4)      mode = 1;
+            else if (q3 > q1 && q3 <= q2) mode = 2;
+            else if (q1 > q4 && r1 == r4) mode = 3;
+            else if (q3 > q2 && r2 == r3) mode = 4;
+            if (mode == 0) { if (lane == 0) s_final[0] = INDELGPU_ST_NOCOMBINE; }
+            else {
+                const bool second_first = (mode == 1 || mode == 3);      // round-2 segment precedes round-1's
+                const uint32_t* cA = second_first ? S.cig2 : S.cig1; const int nA = second_first ? n2 : n1;
+                const uint32_t* cB = second_first ? S.cig1 : S.cig2; const int nB = second_first ? n1 : n2;
+                const int qA1 = second_first ? q3 : q1, qA2 = second_first ? q4 : q2, rA1 = second_first ? r3 : r1;
+                const int qB1 = second_first ? q1 : q3, qB2 = second_first ? q2 : q4, rB1 = second_first ? r1 : r3;
+                int index = qA2;                                         // abutting on the reference (:740-749)
+                if (mode <= 2) index = best_junction_warp(qA1, qA2, cA, nA, qB1, qB2, cB, nB);
+                if (lane == 0) {
+                    s_final[1] = stitch_segments(S.segs, rA1, cA, nA, index, qB1, rB1, cB, nB);
+                    s_final[0] = INDELGPU_ST_SPLIT; s_final[2] = rA1; s_final[3] = index;
+                }
+            }
+        }
+    } else if (lane == 0 && s_final[0] != ST_ASSERT) {
+        s_final[0] = s_plan->status;
+        if (s_plan->status == INDELGPU_ST_WHOLE) {            // :575-582
+            s_final[1] = stitch_segments(S.segs, s_a1->r1, S.cig1, s_a1->n, readlen, 0, -1, nullptr, 0);
+            s_final[2] = s_a1->r1; s_final[3] = readlen;
+        }
+    }
 }
 
 // everything the kernel derives from one batch entry (alignment.c:764-783 + the forceasserts :548-553)
@@ -180,17 +235,16 @@ __device__ __forceinline__ void stage_read(const RealignArgs& a, WarpView& V, co
 
 constexpr int kWorkChunk = 8;
 
-// BANDED: numgaps > 0 (bands of g+1 diagonals); DIRECT: direct-address k-mer table (k <= 6);
-// HB: bits per histogram counter (8 when no diagonal can collect more than 255 votes).
+// The -g 0 kernel.  DIRECT: direct-address k-mer table (k <= 6); HB: bits per histogram counter and
+// table entry (8 when a slice has at most 255 k-mers).
 // The two rounds are ONE loop body so that the vote and the alignment exist once in the instruction
 // stream: warps of a CTA are in different phases and the kernel has to stay instruction-cache friendly.
-template <bool BANDED, bool DIRECT, int HB>
+template <bool DIRECT, int HB>
 __global__ void __launch_bounds__(256)
 realign_kernel(const __grid_constant__ RealignArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int warps_per_cta = blockDim.x >> 5;
     WarpView V;
     bind_warp(V, smem + (size_t)warp * a.L.total, a.L);
     Cta& S = V.S;
@@ -202,7 +256,6 @@ realign_kernel(const __grid_constant__ RealignArgs a)
     Plan* s_plan = reinterpret_cast<Plan*>(V.misc + 24);         // 10 ints
     int*  s_tmp  = V.misc + 36;                                  // 16 ints
     int*  s_final = V.misc + 52;                                 // status, nseg, rstart, index
-    const int slot = blockIdx.x * warps_per_cta + warp;
     unsigned long long cells_f = 0, cells_r = 0, cells_g = 0, alg_bytes = 0;
     uint32_t phase = 0;                                          // bit b = parity of buffer b's barrier
 
@@ -268,7 +321,7 @@ realign_kernel(const __grid_constant__ RealignArgs a)
                     const int low = vote_band_warp<DIRECT, HB>(a.P, V, swin, sw0, cbase + zs1, (int)(e1 - zs1), (int)zs2,
                                                                (int)(e2 - zs2), (int)(anc - zs1), &ok);
                     if (!ok) { if (lane == 0 && round == 1) s_final[0] = ST_ASSERT; break; }
-                    band_alignment_warp<BANDED>(a, S, slot, cbase, zs1, e1, zs2, e2, low, low + a.P.g,
+                    band_alignment_warp(a, S, cbase, zs1, e1, zs2, e2, low, low + a.P.g,
                                                 round ? S.cig2 : S.cig1, s_aln + round, s_tmp);
                     if (round == 1) { done2 = true; break; }
                     if (lane == 0) make_plan(a.P, s_aln[0], S.cig1, anchor, left2, right2, (unsigned)readlen, s_plan);
@@ -278,54 +331,7 @@ realign_kernel(const __grid_constant__ RealignArgs a)
                 }
                 const Aln* s_a1 = s_aln; const Aln* s_a2 = s_aln + 1;
 
-                if (done2) {
-                    const Plan pl = *s_plan;
-                    const int q1 = s_a1->q1, q2 = s_a1->q2, r1 = s_a1->r1, r2 = s_a1->r2, n1 = s_a1->n;
-                    const int q3 = s_a2->q1, q4 = s_a2->q2, r3 = s_a2->r1, r4 = s_a2->r2;
-                    int n2 = s_a2->n;
-                    const bool fail = pl.tail ? (q4 != readlen || q3 == q4) : (q3 != 0 || q3 == q4);
-                    if (fail) { if (lane == 0) s_final[0] = INDELGPU_ST_R2FAIL; }
-                    else {
-                        if (lane == 0) {                 // add_prefix/suffix_soft_clip (:478-532)
-                            if (pl.tail && pl.f_nonmatch) {
-                                if (cig_op(S.cig2[0]) == OP_SOFT) S.cig2[0] = ((uint32_t)(cig_len(S.cig2[0]) + (int)pl.f_nonmatch) << 4) | OP_SOFT;
-                                else { for (int t = n2; t > 0; t--) S.cig2[t] = S.cig2[t - 1]; S.cig2[0] = (pl.f_nonmatch << 4) | OP_SOFT; n2++; }
-                            } else if (!pl.tail && pl.l_nonmatch) {
-                                if (cig_op(S.cig2[n2 - 1]) == OP_SOFT) S.cig2[n2 - 1] = ((uint32_t)(cig_len(S.cig2[n2 - 1]) + (int)pl.l_nonmatch) << 4) | OP_SOFT;
-                                else { S.cig2[n2] = (pl.l_nonmatch << 4) | OP_SOFT; n2++; }
-                            }
-                            s_aln[1].n = n2;
-                        }
-                        n2 = __shfl_sync(0xFFFFFFFFu, n2, 0);
-                        __syncwarp();
-                        // combine (:719-758).  "first" = the segment earlier on the read.
-                        int mode = 0;
-                        if (q1 > q3 && q1 <= q4)      mode = 1;
-                        else if (q3 > q1 && q3 <= q2) mode = 2;
-                        else if (q1 > q4 && r1 == r4) mode = 3;
-                        else if (q3 > q2 && r2 == r3) mode = 4;
-                        if (mode == 0) { if (lane == 0) s_final[0] = INDELGPU_ST_NOCOMBINE; }
-                        else {
-                            const bool second_first = (mode == 1 || mode == 3);      // round-2 segment precedes round-1's
-                            const uint32_t* cA = second_first ? S.cig2 : S.cig1; const int nA = second_first ? n2 : n1;
-                            const uint32_t* cB = second_first ? S.cig1 : S.cig2; const int nB = second_first ? n1 : n2;
-                            const int qA1 = second_first ? q3 : q1, qA2 = second_first ? q4 : q2, rA1 = second_first ? r3 : r1;
-                            const int qB1 = second_first ? q1 : q3, qB2 = second_first ? q2 : q4, rB1 = second_first ? r1 : r3;
-                            int index = qA2;                                         // abutting on the reference (:740-749)
-                            if (mode <= 2) index = best_junction_warp(qA1, qA2, cA, nA, qB1, qB2, cB, nB);
-                            if (lane == 0) {
-                                s_final[1] = stitch_segments(S.segs, rA1, cA, nA, index, qB1, rB1, cB, nB);
-                                s_final[0] = INDELGPU_ST_SPLIT; s_final[2] = rA1; s_final[3] = index;
-                            }
-                        }
-                    }
-                } else if (lane == 0 && s_final[0] != ST_ASSERT) {
-                    s_final[0] = s_plan->status;
-                    if (s_plan->status == INDELGPU_ST_WHOLE) {            // :575-582
-                        s_final[1] = stitch_segments(S.segs, s_a1->r1, S.cig1, s_a1->n, readlen, 0, -1, nullptr, 0);
-                        s_final[2] = s_a1->r1; s_final[3] = readlen;
-                    }
-                }
+                combine_read(S, readlen, s_aln, s_plan, s_final, done2);
                 __syncwarp();
 
                 // ---------------- results

@@ -84,7 +84,7 @@ vote_tasks_kernel(const __grid_constant__ TaskArgs a)
     }
 }
 
-// local_align + ALIGN + fetch_cigar over n tasks, one warp per task
+// local_align + ALIGN + fetch_cigar over n tasks with bands of ONE diagonal, one warp per task
 __global__ void __launch_bounds__(32)
 align_tasks_kernel(const __grid_constant__ TaskArgs a)
 {
@@ -105,8 +105,7 @@ align_tasks_kernel(const __grid_constant__ TaskArgs a)
         const int M = (int)(a.read_off[idx + 1] - roff), N = (int)(a.ref_off[idx + 1] - woff);
         const int lo = max(-M, a.low[idx]), hi = min(N, a.up[idx]);       // localalign.c:70-71
         const int band = hi - lo + 1;
-        const bool bad = M <= 0 || N <= 0 || M > a.max_read || band < 1 ||
-                         (band > 1 && (2 * band > a.scratch.max_band || M > a.scratch.max_rows));
+        const bool bad = M <= 0 || N <= 0 || M > a.max_read || band != 1;   // wider bands: band_tasks_kernel
         if (bad) {
             if (lane == 0) { a.score[idx] = 0; a.ncigar[idx] = 0; for (int t = 0; t < 4; t++) a.ends[4 * idx + t] = 0; atomicExch(a.error_flag, 1); }
             continue;
@@ -114,8 +113,7 @@ align_tasks_kernel(const __grid_constant__ TaskArgs a)
         for (int t = lane; t < M; t += 32) S.read[t] = a.reads[roff + t];
         __syncwarp();
         const uint8_t* win = a.refs + woff;
-        if (band == 1) align_diag1(a.P, S, win, N, 0, M, lo, S.cig1, s_tmp);
-        else align_banded(a.P, a.scratch, blockIdx.x, S.read, M, win, N, lo, hi, S.cig1, S.L.ops_cap, s_tmp);
+        align_diag1(a.P, S, win, N, 0, M, lo, S.cig1, s_tmp);
         const int score = s_tmp[0], n = s_tmp[5];
         if (lane == 0) {
             a.score[idx] = score;
@@ -126,13 +124,9 @@ align_tasks_kernel(const __grid_constant__ TaskArgs a)
         if (score > 0 && a.cigar) for (int t = lane; t < min(n, a.cigar_stride); t += 32) a.cigar[(int64_t)idx * a.cigar_stride + t] = S.cig1[t];
         if (score > 0 && a.script) {
             int32_t* out = a.script + (int64_t)idx * a.script_stride;
-            if (band == 1) { const int len = s_tmp[3] - s_tmp[1] + 1; for (int t = lane; t < min(len, a.script_stride); t += 32) out[t] = 0; if (lane == 0 && len < a.script_stride) out[len] = 0x7FFFFFFF; }
-            else {
-                const int* Sg = band_script_ptr(a.scratch, blockIdx.x);
-                const int len = s_tmp[9];
-                for (int t = lane; t < min(len, a.script_stride); t += 32) out[t] = Sg[t];
-                if (lane == 0 && len < a.script_stride) out[len] = 0x7FFFFFFF;
-            }
+            const int len = s_tmp[3] - s_tmp[1] + 1;                     // all-REP script (globalalign.c:358-365)
+            for (int t = lane; t < min(len, a.script_stride); t += 32) out[t] = 0;
+            if (lane == 0 && len < a.script_stride) out[len] = 0x7FFFFFFF;
         }
     }
     if (lane == 0 && (cells[0] | cells[1] | cells[2])) {
@@ -149,22 +143,29 @@ align_tasks_kernel(const __grid_constant__ TaskArgs a)
 // lane-interleaved scratch (IArr<32>) turns the per-cell work-array traffic into full 128-byte lines
 // that stay in L1.  The exact divide-and-conquer of the reference runs unchanged per thread.
 __global__ void __launch_bounds__(128)
-band_tasks_kernel(const __grid_constant__ TaskArgs a)
+band_tasks_kernel(const __grid_constant__ TaskArgs a, const int bands_in_smem)
 {
-    const int lane = threadIdx.x & 31;
+    // dynamic shared memory (when it fits): the four band-wide work arrays of every thread, lane-interleaved
+    // ([element][thread of the CTA] -> bank = lane, conflict-free); they take ~8 accesses per DP cell
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    // scratch of warp w: [w * 32 * stride, (w + 1) * 32 * stride), lane l at element offset l
-    const IArr<32> base{a.scratch.base + (long long)gwarp * 32 * a.scratch.stride + lane};
+    const int wb4 = 4 * (a.scratch.max_band + 4);
+    // global scratch of warp w: [w * 32 * stride, (w + 1) * 32 * stride), lane l at element offset l
+    const IArr<32> gbase{a.scratch.base + (long long)gwarp * 32 * a.scratch.stride + lane};
+    const IArr<32> bands = bands_in_smem ? IArr<32>{reinterpret_cast<int*>(smem) + (size_t)warp * 32 * wb4 + lane} : gbase;
+    const IArr<32> rowsb = gbase + wb4;
     unsigned long long cf = 0, cr = 0, cg = 0;
     DcFrame st[kDcFrames];
+#pragma unroll 1
     for (int idx = gwarp * 32 + lane; idx < a.n; idx += nwarps * 32) {
         const int64_t roff = a.read_off[idx], woff = a.ref_off[idx];
         const int M = (int)(a.read_off[idx + 1] - roff), N = (int)(a.ref_off[idx + 1] - woff);
         const int lo = max(-M, a.low[idx]), hi = min(N, a.up[idx]);       // localalign.c:70-71
         const int band = hi - lo + 1;
         const bool bad = M <= 0 || N <= 0 || band < 1 || 2 * band > a.scratch.max_band || M > a.scratch.max_rows ||
-                         (a.cigar && 2 * M + band + 4 > a.cigar_stride);
+                         2 * M + band + 4 > a.cigar_stride;
         if (bad) {
             a.score[idx] = 0; a.ncigar[idx] = 0;
             for (int t = 0; t < 4; t++) a.ends[4 * idx + t] = 0;
@@ -172,8 +173,8 @@ band_tasks_kernel(const __grid_constant__ TaskArgs a)
             continue;
         }
         int out[10];
-        uint32_t* cig = a.cigar ? a.cigar + (int64_t)idx * a.cigar_stride : nullptr;
-        align_banded_serial<32>(a.P, base, a.scratch.max_band, a.scratch.max_rows, st,
+        uint32_t* cig = a.cigar + (int64_t)idx * a.cigar_stride;
+        align_banded_serial<32>(a.P, bands, rowsb, a.scratch.max_band, a.scratch.max_rows, st,
                                 a.reads + roff, M, a.refs + woff, N, lo, hi, cig, out);
         const int score = out[0];
         a.score[idx] = score;
@@ -182,12 +183,13 @@ band_tasks_kernel(const __grid_constant__ TaskArgs a)
         cf += (unsigned long long)out[6]; cr += (unsigned long long)out[7]; cg += (unsigned long long)out[8];
         if (score > 0 && a.script) {
             int32_t* so = a.script + (int64_t)idx * a.script_stride;
-            const IArr<32> S = base + 8 * (a.scratch.max_band + 4) + 8 * (a.scratch.max_rows + 2);
+            const IArr<32> S = rowsb + 8 * (a.scratch.max_rows + 2);
             const int len = out[9];
             for (int t = 0; t < min(len, a.script_stride); t++) so[t] = S[t];
             if (len < a.script_stride) so[len] = 0x7FFFFFFF;
         }
     }
+    __syncwarp();
     // one atomic per warp and counter
     cf = __reduce_add_sync(0xFFFFFFFFu, (unsigned)cf) + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(cf >> 32)) << 32);
     cr = __reduce_add_sync(0xFFFFFFFFu, (unsigned)cr) + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(cr >> 32)) << 32);
@@ -210,7 +212,7 @@ __global__ void global_align_one_kernel(DevParams P, BandScratch scr, const uint
     DcCtx<1> x;
     x.P = &P; x.A = A; x.B = B; x.cells = 0;
     x.cc = base; x.dd = base + wb; x.cp = base + 2 * wb; x.dp = base + 3 * wb;
-    const IArr<1> rows = base + 8 * wb;
+    const IArr<1> rows = base + 4 * wb;
     x.mp[0] = rows; x.mp[1] = rows + wr; x.mp[2] = rows + 2 * wr; x.fp = rows + 3 * wr;
     x.mt[0] = rows + 4 * wr; x.mt[1] = rows + 5 * wr; x.mt[2] = rows + 6 * wr; x.ft = rows + 7 * wr;
     x.S = IArr<1>{out_script};
