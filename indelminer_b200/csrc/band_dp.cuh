@@ -43,7 +43,7 @@ __host__ __device__ inline long long band_scratch_ints(int max_band, int max_row
 template <int STRIDE>
 struct IArr {
     int* p;
-    IG_HD int& operator[](int i) const { return p[(long long)i * STRIDE]; }
+    IG_HD int& operator[](int i) const { return p[i * STRIDE]; }           // |i * STRIDE| < 2^31 for every supported size
     IG_HD IArr operator+(long long k) const { return IArr{p + k * STRIDE}; }
 };
 

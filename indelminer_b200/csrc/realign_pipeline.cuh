@@ -81,7 +81,7 @@ pipe_vote_kernel(const __grid_constant__ RealignArgs a, const PipeBufs p, const 
 }
 
 // ---- thread per read: attempt_band_alignment (alignment.c:343-391) ----------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, BAND_MIN_BLOCKS)
 pipe_dp_kernel(const __grid_constant__ RealignArgs a, const PipeBufs p, const int round, const int bands_in_smem)
 {
     extern __shared__ __align__(128) unsigned char smem[];

@@ -6,6 +6,10 @@
 #include "band_dp.cuh"
 #include "warp_vote.cuh"
 
+#ifndef BAND_MIN_BLOCKS
+#define BAND_MIN_BLOCKS 4
+#endif
+
 namespace indelgpu {
 
 struct TaskArgs {
@@ -142,7 +146,7 @@ align_tasks_kernel(const __grid_constant__ TaskArgs a)
 // most of a warp idle; 32 independent alignments per warp keep every lane busy, and the
 // lane-interleaved scratch (IArr<32>) turns the per-cell work-array traffic into full 128-byte lines
 // that stay in L1.  The exact divide-and-conquer of the reference runs unchanged per thread.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, BAND_MIN_BLOCKS)
 band_tasks_kernel(const __grid_constant__ TaskArgs a, const int bands_in_smem)
 {
     // dynamic shared memory (when it fits): the four band-wide work arrays of every thread, lane-interleaved
