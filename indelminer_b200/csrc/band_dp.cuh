@@ -16,6 +16,11 @@
 // never calls them on the host).
 #define IG_HD __host__ __device__
 
+// resident CTAs per SM the thread-per-alignment kernels are compiled for (register cap 65536 / (128 * N))
+#ifndef BAND_MIN_BLOCKS
+#define BAND_MIN_BLOCKS 4
+#endif
+
 namespace indelgpu {
 
 IG_HD inline int ig_min(int a, int b) { return a < b ? a : b; }

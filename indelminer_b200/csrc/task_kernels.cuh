@@ -6,10 +6,6 @@
 #include "band_dp.cuh"
 #include "warp_vote.cuh"
 
-#ifndef BAND_MIN_BLOCKS
-#define BAND_MIN_BLOCKS 4
-#endif
-
 namespace indelgpu {
 
 struct TaskArgs {
