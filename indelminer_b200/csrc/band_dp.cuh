@@ -301,6 +301,119 @@ IG_HD inline int script_to_cigar(const uint8_t* A, const uint8_t* B, int M, int 
     return n;
 }
 
+// ---------------------------------------------------------------------------------------
+// local_align's two sweeps (localalign.c:82-176) for bands of at most W diagonals with ALL DP state in
+// registers: one (H, D) pair per diagonal, updated in place (ascending t forward, descending t in
+// reverse, so every cell still sees the previous row's neighbours), the band's W reference bytes in a
+// byte-shifted register window, every loop over the band fully unrolled.  Cells outside the band or
+// the window keep -infinity, which reproduces the reference's boundary cases (t == tlo, j == 0,
+// the column right of the end cell) without branches: with E, D or the diagonal at -infinity each
+// special case of the serial code is the general recurrence.
+// Same results and cell counts as the memory-resident sweeps below (tests/test_host_harness.py).
+// ---------------------------------------------------------------------------------------
+template <int W>
+IG_HD inline void local_sweeps_reg(const DevParams& P, const uint8_t* read, int M, const uint8_t* win, int N,
+                                   int low, int up, int& best_o, int& endi_o, int& endj_o,
+                                   int& starti_o, int& startj_o, bool& found_o, int& cf_o, int& cr_o)
+{
+    constexpr int NW = (W + 3) / 4;
+    const int G = P.G, Hh = P.H, m = G + Hh;
+    const int band = up - low + 1;
+    const int si = ig_max(0, -up), ei = ig_min(M, N - low);
+    int Hr[W], Dr[W];
+    uint32_t wr[NW];
+#pragma unroll
+    for (int t = 0; t < W; t++) {
+        const int j = si + low + t;
+        const bool v = t < band && j >= 0 && j <= N;
+        Hr[t] = v ? 0 : kNeg; Dr[t] = v ? -G : kNeg;
+    }
+#pragma unroll
+    for (int k = 0; k < NW; k++) wr[k] = 0;
+#pragma unroll
+    for (int t = 0; t < W; t++) {                                  // byte t = win[i + low + t - 1] for row i = si + 1
+        const int x = si + low + t;
+        if (x >= 0 && x < N) wr[t >> 2] |= (uint32_t)win[x] << (8 * (t & 3));
+    }
+    int best = 0, endi = si, endt = 0, cf = 0;
+    for (int i = si + 1; i <= ei; i++) {
+        const int tlo = ig_max(0, -i - low), thi = ig_min(band - 1, N - i - low);
+        const uint32_t ai = read[i - 1];
+        int e = kNeg, left = kNeg;
+#pragma unroll
+        for (int t = 0; t < W; t++) {
+            const int hup = (t + 1 < W) ? Hr[t + 1] : kNeg, dup = (t + 1 < W) ? Dr[t + 1] : kNeg;
+            const int d = ig_max(hup - m, dup - Hh);
+            const bool eq = ((wr[t >> 2] >> (8 * (t & 3))) & 0xFFu) == ai;
+            e = ig_max(left - m, e - Hh);
+            int c = ig_max(ig_max(Hr[t] + (eq ? P.match : P.mismatch), e), ig_max(d, 0));
+            const bool v = t >= tlo && t <= thi;
+            if (v) {
+                Hr[t] = c; Dr[t] = d; left = c;
+                if (c > best) { best = c; endi = i; endt = t; }
+            } else { left = kNeg; e = kNeg; }
+        }
+        cf += thi - tlo + 1;
+#pragma unroll
+        for (int k = 0; k < NW; k++) wr[k] = (wr[k] >> 8) | ((k + 1 < NW) ? (wr[k + 1] << 24) : 0u);
+        const int x = i + low + W - 1;                              // new top byte for row i + 1
+        if (x >= 0 && x < N) wr[(W - 1) >> 2] |= (uint32_t)win[x] << (8 * ((W - 1) & 3));
+    }
+    const int endj = endi + low + endt;
+    best_o = best; endi_o = endi; endj_o = (best > 0) ? endj : si + low; cf_o = cf;
+    starti_o = 0; startj_o = 0; found_o = false; cr_o = 0;
+    if (best <= 0) return;
+
+    // reverse (localalign.c:132-176)
+    const int tend = (endj - endi) - low;
+    {
+        const int tl = ig_max(0, -endi - low);
+#pragma unroll
+        for (int t = 0; t < W; t++) {
+            const bool v = t <= tend && t >= tl;
+            const int acc = -(G + Hh * (tend - t));
+            Hr[t] = (t == tend) ? 0 : (v ? acc : kNeg);
+            Dr[t] = (t == tend) ? -G : (v ? acc - G : kNeg);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NW; k++) wr[k] = 0;
+#pragma unroll
+    for (int t = 0; t < W; t++) {                                  // byte t = win[i + low + t - 1] for row i = endi
+        const int x = endi + low + t - 1;
+        if (x >= 0 && x < N) wr[t >> 2] |= (uint32_t)win[x] << (8 * (t & 3));
+    }
+    int starti = 0, startt = 0, cr = 0; bool found = false;
+    for (int i = endi; i >= 1 && !found; i--) {
+        const int thi = ig_min(band - 1, tend + (endi - i) + 1);
+        const int tlo = ig_max(0, 1 - i - low);
+        const uint32_t ai = read[i - 1];
+        int e = kNeg, right = kNeg;
+#pragma unroll
+        for (int t = W - 1; t >= 0; t--) {
+            const int hdn = (t > 0) ? Hr[t - 1] : kNeg, ddn = (t > 0) ? Dr[t - 1] : kNeg;
+            const int d = ig_max(hdn - m, ddn - Hh);
+            const bool eq = ((wr[t >> 2] >> (8 * (t & 3))) & 0xFFu) == ai;
+            e = ig_max(right - m, e - Hh);
+            const int c = ig_max(ig_max(Hr[t] + (eq ? P.match : P.mismatch), e), d);
+            const bool v = t >= tlo && t <= thi && !found;
+            if (v) {
+                Hr[t] = c; Dr[t] = d; right = c;
+                if (c == best) { found = true; starti = i; startt = t; cr += thi - t + 1; }
+            } else {
+                right = kNeg; e = kNeg;
+                if (t < tlo) { Hr[t] = kNeg; Dr[t] = kNeg; }          // left the window: stale values must not be read
+            }
+        }
+        if (!found) cr += ig_max(0, thi - tlo + 1);
+#pragma unroll
+        for (int k = NW - 1; k >= 0; k--) wr[k] = (wr[k] << 8) | ((k > 0) ? (wr[k - 1] >> 24) : 0u);
+        const int x = i + low - 2;                                  // new bottom byte for row i - 1
+        if (x >= 0 && x < N) wr[0] |= (uint32_t)win[x];
+    }
+    starti_o = starti; startj_o = starti + low + startt; found_o = found; cr_o = cr;
+}
+
 // local_align + ALIGN + fetch_cigar on a band of >= 2 diagonals, executed by ONE thread.
 // `low`/`up` are already clamped (localalign.c:70-71); `base` is this CTA's scratch slice.
 // out: score, q1, r1, q2, r2 (1-based inclusive, slice/window relative), ncigar, cells fwd, rev, glob, nscript
@@ -322,6 +435,12 @@ IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> bands, IA
     x.mp[0] = rows; x.mp[1] = rows + wr; x.mp[2] = rows + 2 * wr; x.fp = rows + 3 * wr;
     x.mt[0] = rows + 4 * wr; x.mt[1] = rows + 5 * wr; x.mt[2] = rows + 6 * wr; x.ft = rows + 7 * wr;
     x.S = rows + 8 * wr;
+    int best = 0, endi = 0, endj = 0, cf = 0, cr = 0, starti = 0, startj = 0; bool found = false;
+    if (band <= 8)       local_sweeps_reg<8>(P, read, M, win, N, low, up, best, endi, endj, starti, startj, found, cf, cr);
+    else if (band <= 16) local_sweeps_reg<16>(P, read, M, win, N, low, up, best, endi, endj, starti, startj, found, cf, cr);
+    else if (band <= 24) local_sweeps_reg<24>(P, read, M, win, N, low, up, best, endi, endj, starti, startj, found, cf, cr);
+    else if (band <= 40) local_sweeps_reg<40>(P, read, M, win, N, low, up, best, endi, endj, starti, startj, found, cf, cr);
+    else {
 #define AT(arr, t) ((arr)[(t) + 1])
     // forward (localalign.c:82-131)
     const int si = ig_max(0, -up), ei = ig_min(M, N - low);
@@ -333,7 +452,7 @@ IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> bands, IA
         const int j = si + low + t;
         if (j >= 0 && j <= N) { AT(Hp, t) = 0; AT(Dp, t) = -G; }
     }
-    int best = 0, endi = si, endj = si + low, cf = 0, cr = 0;
+    best = 0; endi = si; endj = si + low; cf = 0; cr = 0;
     for (int i = si + 1; i <= ei; i++) {
         const int tlo = ig_max(0, -i - low), thi = ig_min(band - 1, N - i - low);
         AT(Hn, tlo - 1) = kNeg; AT(Dn, tlo - 1) = kNeg; AT(Hn, thi + 1) = kNeg; AT(Dn, thi + 1) = kNeg;
@@ -359,7 +478,7 @@ IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> bands, IA
         IArr<STRIDE> tmp = Hp; Hp = Hn; Hn = tmp; tmp = Dp; Dp = Dn; Dn = tmp;
     }
     // reverse (localalign.c:132-176)
-    int starti = 0, startj = 0; bool found = false;
+    starti = 0; startj = 0; found = false;
     if (best > 0) {
         const int tend = (endj - endi) - low;
         for (int t = -1; t <= band; t++) { AT(Hp, t) = kNeg; AT(Dp, t) = kNeg; AT(Hn, t) = kNeg; AT(Dn, t) = kNeg; }
@@ -397,6 +516,7 @@ IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> bands, IA
             }
             IArr<STRIDE> tmp = Hp; Hp = Hn; Hn = tmp; tmp = Dp; Dp = Dn; Dn = tmp;
         }
+    }
     }
 #undef AT
     const bool none = best <= 0 || !found || starti > M || startj > N ||
