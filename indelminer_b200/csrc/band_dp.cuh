@@ -262,6 +262,30 @@ IG_HD inline void dc_align(DcCtx<STRIDE>& x, DcFrame* st, int a0, int b0, int M0
     }
 }
 
+// Cells the reference's align() sweeps (globalalign.c:147-234, all recursion levels) when the optimal
+// path of an M x M problem is the main diagonal and is unique: a level whose mid-diagonal is not
+// diagonal 0 finds no crossing and recurses on the half band that holds the path (:260-262); the level
+// whose mid-diagonal is diagonal 0 crosses on every row and emits its REPs without recursing.
+IG_HD inline int dc_cells_of_diagonal_path(int M, int low, int up)
+{
+    low = ig_min(ig_max(-M, low), 0);                                  // ALIGN's clamps with N == M (:347-348)
+    up  = ig_max(ig_min(M, up), 0);
+    int cells = 0;
+    while (up - low + 1 > 1) {
+        const int band = up - low + 1;
+        int leftd = 1 - low, rightd = band;
+        for (int i = 1; i <= M; i++) {
+            if (i > M - up) rightd--;
+            if (leftd > 1) leftd--;
+            cells += rightd - leftd + 1;
+        }
+        const int rmid = low + band / 2;                               // low + midd - 1, midd = band / 2 + 1
+        if (rmid == 0) break;
+        if (rmid < 0) low = rmid + 1; else up = rmid - 1;
+    }
+    return cells;
+}
+
 // ALIGN (globalalign.c:333-401): A, B 0-based first symbols.  Returns the number of script entries.
 template <int STRIDE>
 IG_HD inline int global_align_script(DcCtx<STRIDE>& x, DcFrame* st, int M, int N, int low, int up)
@@ -525,7 +549,26 @@ IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> bands, IA
     if (!none) {
         const int M2 = endi - starti + 1, N2 = endj - startj + 1;
         x.A = read + starti - 1; x.B = win + startj - 1;
-        global_align_script(x, st, M2, N2, low - (startj - starti), up - (startj - starti));
+        const int low2 = low - (startj - starti), up2 = up - (startj - starti);
+        // Shortcut that needs no sweep: when the end points lie on one diagonal, the ungapped path reaches
+        // the local optimum and it has so few mismatches that every gapped path (which pays at least two gap
+        // opens and two extensions and aligns at least one pair fewer) scores strictly less, the all-REP
+        // script is the UNIQUE optimum, so ALIGN's divide and conquer (globalalign.c:66-307) returns it
+        // whatever its tie rules.  Its cell count is still reported: it depends on the geometry only.
+        bool unique_diag = false;
+        if (M2 == N2 && P.match > 0 && P.mismatch < P.match && G >= 0 && H >= 0) {
+            int mm = 0;
+            for (int i = 0; i < M2; i++) mm += (x.A[i] != x.B[i]) ? 1 : 0;
+            const long long sd = (long long)(M2 - mm) * P.match + (long long)mm * P.mismatch;
+            unique_diag = sd == (long long)best && (long long)mm * (P.match - P.mismatch) < (long long)P.match + 2LL * m;
+        }
+        if (unique_diag) {
+            for (int i = 0; i < M2; i++) x.S[i] = 0;
+            x.ns = M2; x.last = 0;
+            x.cells = dc_cells_of_diagonal_path(M2, low2, up2);
+        } else {
+            global_align_script(x, st, M2, N2, low2, up2);
+        }
         n = script_to_cigar(x.A, x.B, M2, N2, x.S, starti, M, cig);
     }
     out[0] = none ? 0 : best;         // ALIGN's score equals the local optimum
