@@ -363,7 +363,9 @@ def run_ours(a, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "realign_kernel<%s>" % ("true" if a.numgaps else "false"),
+                     "traffic": None,
+                     "kernel": "realign_kernel<DIRECT, HB=8> (fused, warp per read)" if a.numgaps == 0
+                               else "pipe_vote / pipe_dp / pipe_combine (5 launches per step; time = whole step)",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_s * 1e3, "peak_source": peak_src},
     }
     prof = os.path.join(ROOT, "profiles", "traffic.json")

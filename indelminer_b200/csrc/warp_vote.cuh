@@ -22,7 +22,7 @@ struct WarpLayout {
     int pk_words;        // packed read words
     int ops_cap;         // words per CIGAR buffer
     int off_tab, off_hist, off_win0, off_win1, off_read0, off_read1, off_pk, off_psum, off_bits,
-        off_cig1, off_cig2, off_segs, off_bar, off_misc;
+        off_cig1, off_cig2, off_segs, off_bar, off_misc, off_list;
     int total;           // bytes per warp (multiple of 128)
 };
 
@@ -46,7 +46,7 @@ __host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int m
     #pragma unroll 1
     while (hs < 4 * max_read) hs <<= 1;
     L.hash_slots = L.direct ? 0 : hs;
-    L.hist_bits = (max_read - P.k + 1 <= 255) ? 8 : 16;
+    L.hist_bits = (max_read - P.k + 1 <= 255 && max_numdiag <= 65535) ? 8 : 16;
     const int tab_bytes = L.direct ? ((L.hist_bits / 8) << (2 * P.k)) : hs * 8;
     L.hist_words = round_up((max_numdiag + 4) * (L.hist_bits / 8), 16) / 4;
     L.win_bytes = round_up(max_numdiag / 4 + 64, 16);             // window <= max_numdiag bases, 64-base aligned start, hi word
@@ -68,6 +68,7 @@ __host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int m
     L.off_segs = o;  o += round_up((2 * L.ops_cap + 4) * 4, 16);
     L.off_bar = o;   o += 16;                                      // two mbarriers
     L.off_misc = o;  o += 256;                                     // Aln x 2, Plan, scalars
+    L.off_list = o;  o += round_up((32 + 512 + 32) * (L.hist_bits == 8 ? 2 : 4), 16);   // hit list (kHitListCap entries)
     L.total = round_up(o, 128);
     return L;
 }
@@ -128,6 +129,7 @@ struct WarpView {
     uint32_t* pk;
     uint64_t* bar;        // [2]
     int* misc;
+    void* list;           // hit list of the vote (HitIdx<HB>::type[kHitListCap])
     Cta S;                // psum / bits / cig1 / cig2 / segs views used by the scalar pieces (kernels.cuh)
 };
 
@@ -146,6 +148,7 @@ __device__ __forceinline__ void bind_warp(WarpView& V, unsigned char* base, cons
     V.pk = reinterpret_cast<uint32_t*>(base + L.off_pk);
     V.bar = reinterpret_cast<uint64_t*>(base + L.off_bar);
     V.misc = reinterpret_cast<int*>(base + L.off_misc);
+    V.list = base + L.off_list;
     V.S.keys = nullptr; V.S.vals = nullptr; V.S.hist = nullptr;
     V.S.read = nullptr;
     V.S.bits = reinterpret_cast<uint32_t*>(base + L.off_bits);
@@ -193,6 +196,11 @@ __device__ __forceinline__ uint32_t kmer_at(const uint32_t* pk, int i, uint32_t 
     const int w = i >> 4;
     return __funnelshift_r(pk[w], pk[w + 1], 2 * (i & 15)) & kmask;
 }
+
+// element type of the per-warp hit list: diagonal indices fit 16 bits whenever HB == 8 (make_warp_layout)
+template <int HB> struct HitIdx { typedef uint32_t type; };
+template <> struct HitIdx<8> { typedef uint16_t type; };
+constexpr int kHitListCap = 32 + 512 + 32;     // carried remainder + one step of 32 lanes x 16 positions
 
 // table entry: offset + 1 of the read k-mer if it occurs exactly once in the slice, else 0.
 // Direct tables hold one entry per possible k-mer, HB/8 bytes wide (HB == 8 iff the slice has at most
@@ -273,8 +281,11 @@ __device__ __forceinline__ int vote_band_warp(const DevParams& P, WarpView& V, c
     __syncwarp();
 
     // 2. scan the window: one packed word (16 k-mer starts) per lane per step.
-    //    Pass A is branch-free: which of the 16 positions hit a unique read k-mer.  Pass B visits only the
-    //    hits and merges consecutive votes for one diagonal (the true alignment) into a single atomic.
+    //    Pass A is branch-free: which of the 16 positions hit a unique read k-mer.  Pass B appends the
+    //    diagonal index of every hit to a per-warp list (a lane's hits go to consecutive slots, lanes in
+    //    window order, so the votes of one diagonal -- the true alignment -- are neighbours).  Pass C
+    //    drains the list 32 entries at a time with all lanes busy: equal neighbours are merged by ballot
+    //    and their leader issues one shared-memory atomic for the run.
     //    For one-diagonal bands (g == 0) select_band (alignment.c:142-181) rides along: an atomic that
     //    returns the largest count ever seen is the LAST vote of its diagonal, so every lane keeps the
     //    largest count its own atomics produced and, among those, the smallest tie key
@@ -283,45 +294,76 @@ __device__ __forceinline__ int vote_band_warp(const DevParams& P, WarpView& V, c
     a = a < -1 ? -1 : (a > numdiag ? numdiag : a);                // clamping keeps every comparison
     uint32_t lbest = 0, lkey = 0xFFFFFFFFu;
     if (N >= k) {
+        typedef typename HitIdx<HB>::type hit_t;
+        hit_t* list = reinterpret_cast<hit_t*>(V.list);
         const int fr = (int)(wabs - (sw0 << 4));                  // first k-mer start, relative to the staged buffer
         const int lr = fr + N - k;                                // last k-mer start, inclusive
         const int w0 = fr >> 4, w1 = lr >> 4;
         const int shiftM = M - k + 1;
-        #pragma unroll 1
-        for (int wi = w0 + lane; wi <= w1; wi += 32) {
-            const uint32_t lo = swin[wi], hi = swin[wi + 1];
-            const int rel0 = (wi << 4) - fr;                      // window offset of position 0 of this word
-            uint32_t hits = 0;
-#pragma unroll
-            for (int p = 0; p < 16; p++) {
-                const uint32_t code = __funnelshift_r(lo, hi, 2 * p) & kmask;
-                if (kmer_lookup<DIRECT, HB>(V, code) != 0u) hits |= 1u << p;
-            }
-            const int plo = rel0 < 0 ? -rel0 : 0;
-            const int phi = (wi == w1) ? (lr - (wi << 4)) : 15;
-            hits &= (0xFFFFu << plo) & (0xFFFFu >> (15 - phi));
-            int cur = -1; uint32_t cnt = 0;
+        int fill = 0;                                             // entries waiting in the list (warp-uniform)
 #pragma unroll 1
-            while (true) {
-                int idx = -1;
-                if (hits) {
+        for (int wb = w0; wb <= w1 || fill > 0; wb += 32) {
+            const int wi = wb + lane;
+            if (wb <= w1) {
+                uint32_t hits = 0, lo = 0, hi = 0;
+                const int rel0 = (wi << 4) - fr;                  // window offset of position 0 of this word
+                if (wi <= w1) {
+                    lo = swin[wi]; hi = swin[wi + 1];
+#pragma unroll
+                    for (int p = 0; p < 16; p++) {
+                        const uint32_t code = __funnelshift_r(lo, hi, 2 * p) & kmask;
+                        if (kmer_lookup<DIRECT, HB>(V, code) != 0u) hits |= 1u << p;
+                    }
+                    const int plo = rel0 < 0 ? -rel0 : 0;
+                    const int phi = (wi == w1) ? (lr - (wi << 4)) : 15;
+                    hits &= (0xFFFFu << plo) & (0xFFFFu >> (15 - phi));
+                }
+                const int mine = __popc(hits);
+                int pre = mine;                                   // inclusive scan of the lanes' hit counts
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, pre, o); if (lane >= o) pre += t; }
+                const int total = __shfl_sync(0xFFFFFFFFu, pre, 31);
+                int slot = fill + pre - mine;
+#pragma unroll 1
+                while (hits) {
                     const int p = __ffs(hits) - 1;
                     hits &= hits - 1;
                     const uint32_t off = kmer_lookup<DIRECT, HB>(V, __funnelshift_r(lo, hi, 2 * p) & kmask);
-                    idx = rel0 + p - (int)(off - 1u) + shiftM;
+                    list[slot++] = (hit_t)(rel0 + p - (int)(off - 1u) + shiftM);
                 }
-                if (idx != cur && cnt) {                          // the run ended: one atomic for all of it
+                fill += total;
+                __syncwarp();
+            }
+            // pass C: full chunks of 32; the last, partial chunk once the window is exhausted
+            int done = 0;
+#pragma unroll 1
+            while (fill - done >= 32 || (wb + 32 > w1 && fill - done > 0)) {
+                const int n = min(32, fill - done);
+                const bool valid = lane < n;
+                const int idx = valid ? (int)list[done + lane] : -1;
+                const int prev = __shfl_up_sync(0xFFFFFFFFu, idx, 1);
+                const bool leader = valid && (lane == 0 || idx != prev);
+                const uint32_t leaders = __ballot_sync(0xFFFFFFFFu, leader);
+                if (leader) {
+                    const uint32_t rest = (lane == 31) ? 0u : (leaders >> (lane + 1));
+                    const uint32_t cnt = (uint32_t)(rest ? __ffs(rest) : n - lane);
                     constexpr int LG = (HB == 8) ? 2 : 1;
-                    const int sh = (cur & ((1 << LG) - 1)) * HB;
-                    const uint32_t old = atomicAdd(&V.hist[cur >> LG], cnt << sh);
+                    const int sh = (idx & ((1 << LG) - 1)) * HB;
+                    const uint32_t old = atomicAdd(&V.hist[idx >> LG], cnt << sh);
                     const uint32_t now = ((old >> sh) & ((1u << HB) - 1u)) + cnt;
-                    const uint32_t key = 2u * (uint32_t)(a > cur ? a - cur : cur - a) + (cur > a ? 1u : 0u);
+                    const uint32_t key = 2u * (uint32_t)(a > idx ? a - idx : idx - a) + (idx > a ? 1u : 0u);
                     if (now > lbest) { lbest = now; lkey = key; }
                     else if (now == lbest) lkey = min(lkey, key);
-                    cnt = 0;
                 }
-                if (idx < 0) break;
-                cur = idx; cnt++;
+                done += n;
+            }
+            if (done) {                                           // carry the remainder (< 32 entries) to the front
+                const int rem = fill - done;
+                const hit_t v = (lane < rem) ? list[done + lane] : (hit_t)0;
+                __syncwarp();
+                if (lane < rem) list[lane] = v;
+                fill = rem;
+                __syncwarp();
             }
         }
     }

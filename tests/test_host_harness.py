@@ -119,3 +119,42 @@ def test_interleaved_view_matches_oracle_incl_band_1(harness, oracle):
             assert cig == exp_cig, ctx
             assert (out[6], out[7], out[8]) == (cells.fwd, cells.rev, cells.glob), ctx
     assert npos > 500
+
+
+@pytest.mark.parametrize("scoring", [(1, -10, 10, 10), (1, -3, 2, 1), (2, -1, 4, 1), (1, -1, 0, 1), (3, -2, 1, 0)])
+def test_unique_diagonal_shortcut_is_exact_under_other_scorings(harness, oracle, scoring):
+    """align_banded_serial skips ALIGN's sweeps when the ungapped path is provably the unique optimum.
+    With cheap gaps the proof condition is tight (few mismatches allowed), so near-ungapped reads over
+    two- and four-letter alphabets probe both sides of it; the oracle always runs the full divide and
+    conquer.  Scripts, CIGARs and the three cell counters must agree."""
+    match, mismatch, G, H = scoring
+    rng = make_rng(9000 + 7 * match - mismatch + 3 * G + H)
+    p = oracle.default_params()
+    p.match, p.mismatch, p.gapopen, p.gapextend = match, mismatch, G, H
+    prm = (6, 0, 1000, 10, match, mismatch, G, H)
+    n = 0
+    for it in range(1200):
+        alpha = rng.choice(["AC", "ACGT"])
+        N = rng.randrange(20, 200)
+        ref = rseq(rng, N, alpha)
+        M = rng.randrange(4, min(100, N - 2))
+        off = rng.randrange(0, N - M)
+        read = mutate(rng, ref[off:off + M], alpha, sub=rng.choice([0, 0.01, 0.03, 0.06]),
+                      nindel=rng.choice([0, 0, 0, 1]), maxindel=3)
+        M = len(read)
+        w = rng.choice([2, 3, 5, 9, 17])
+        low = off - rng.randrange(0, w)
+        up = low + w - 1
+        if min(N, up) - max(-M, low) + 1 < 1:
+            continue
+        cells = oracle.Cells()
+        score, ends, script = oracle.local_align(p, read, ref, low, up, cells=cells)
+        out, cig, scr = run(harness, read, ref, low, up, prm=prm, lane=it % 32)
+        ctx = (scoring, read, ref, low, up)
+        assert out[0] == score, ctx
+        if score > 0:
+            n += 1
+            assert tuple(out[1:5]) == ends, ctx
+            assert scr == script, ctx
+            assert (out[6], out[7], out[8]) == (cells.fwd, cells.rev, cells.glob), ctx
+    assert n > 600
