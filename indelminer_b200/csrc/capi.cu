@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "../../include/indelgpu.h"
@@ -898,27 +899,40 @@ extern "C" int ALIGN(char* A, char* B, int M, int N, int low, int up, int W[][12
     return score;
 }
 
+// Debug pretty-printer with the output format of globalalign.c:408-457: blocks of at most 50 alignment
+// columns, a ruler, the read row, a marker row ('|' match, ' ' mismatch, '-' gap) and the reference row.
+// Pure formatting of a script the GPU produced; host only.
+namespace {
+struct DisplayBlock {
+    std::string top, mid, bot;
+    void put(char a, char m, char b) { top.push_back(a); mid.push_back(m); bot.push_back(b); }
+    void emit(FILE* F, int block_no, int ap, int bp)
+    {
+        const int w = (int)top.size();
+        fprintf(F, "\n%5d ", 50 * block_no);
+        for (int t = 10; t <= w; t += 10) fputs("    .    :", F);
+        if (w % 10 >= 5) fputs("    .", F);
+        fprintf(F, "\n%5d %s\n      %s\n%5d %s\n", ap, top.c_str(), mid.c_str(), bp, bot.c_str());
+        top.clear(); mid.clear(); bot.clear();
+    }
+};
+}  // namespace
+
 extern "C" int DISPLAY(FILE* F, char* A, char* B, int M, int N, int* S, int AP, int BP)
 {
-    // debug pretty-printer of globalalign.c:408-457: 50 columns per block, '|' under matches,
-    // '-' under gaps.  Pure formatting, host only.
-    char al[51], bl[51], cl[51];
-    int i = 0, j = 0, op = 0, lines = 0, ap = AP, bp = BP, w = 0;
+    DisplayBlock blk;
+    int i = 0, j = 0, blocks = 0, ap = AP, bp = BP, k = 0;
+    int gap = 0;                                  // remaining symbols of the gap being printed (sign = kind)
     while (i < M || j < N) {
-        if (op == 0 && *S == 0) { op = *S++; al[w] = A[++i]; bl[w] = B[++j]; cl[w] = (al[w] == bl[w]) ? '|' : ' '; w++; }
+        if (gap == 0 && S[k] == 0) { k++; const char a = A[++i], b = B[++j]; blk.put(a, a == b ? '|' : ' ', b); }
         else {
-            if (op == 0) op = *S++;
-            if (op > 0) { al[w] = ' '; bl[w] = B[++j]; op--; }
-            else        { al[w] = A[++i]; bl[w] = ' '; op++; }
-            cl[w++] = '-';
+            if (gap == 0) gap = S[k++];
+            if (gap > 0) { blk.put(' ', '-', B[++j]); gap--; }
+            else         { blk.put(A[++i], '-', ' '); gap++; }
         }
-        if (w >= 50 || (i >= M && j >= N)) {
-            al[w] = bl[w] = cl[w] = '\0';
-            fprintf(F, "\n%5d ", 50 * lines++);
-            for (int t = 10; t <= w; t += 10) fprintf(F, "    .    :");
-            if (w % 10 >= 5) fprintf(F, "    .");
-            fprintf(F, "\n%5d %s\n      %s\n%5d %s\n", ap, al, cl, bp, bl);
-            ap = AP + i; bp = BP + j; w = 0;
+        if (blk.top.size() >= 50 || (i >= M && j >= N)) {
+            blk.emit(F, blocks++, ap, bp);
+            ap = AP + i; bp = BP + j;
         }
     }
     return -1;

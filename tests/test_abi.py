@@ -60,3 +60,44 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".c")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower().replace("no cpu", ""), os.path.join(dirpath, f)
+
+
+def test_display_matches_reference_byte_for_byte(tmp_path):
+    """DISPLAY (globalalign.h:30-37) is pure host formatting, so it can be checked without a GPU:
+    same script through libindelgpu.so and through the reference object (oracle/_ref/libref_dp.so)."""
+    import ctypes as C
+    import random
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_dp.so")
+    if not os.path.exists(ref_so):
+        import pytest
+        pytest.skip("oracle/_ref not built")
+    from indelminer_b200 import lib as _lib
+    ours, ref = _lib.load(), C.CDLL(ref_so)
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    rng = random.Random(5)
+    for case in range(40):
+        # a random script over random sequences: 0 = pair, +k = k reference symbols, -k = k read symbols
+        S, M, N = [], 0, 0
+        for _ in range(rng.randrange(1, 40)):
+            r = rng.random()
+            if r < 0.7:
+                n = rng.randrange(1, 30); S += [0] * n; M += n; N += n
+            elif r < 0.85:
+                n = rng.randrange(1, 70); S.append(n); N += n
+            else:
+                n = rng.randrange(1, 70); S.append(-n); M += n
+        A = b"\0" + bytes(rng.choice(b"ACGT") for _ in range(M))
+        B = b"\0" + bytes(rng.choice(b"ACGT") for _ in range(N))
+        outs = []
+        for tag, L in (("ours", ours), ("ref", ref)):
+            path = str(tmp_path / f"{tag}{case}.txt").encode()
+            fp = libc.fopen(path, b"w")
+            Sa = (C.c_int * (len(S) + 1))(*S)
+            L.DISPLAY.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+            L.DISPLAY(fp, A, B, M, N, Sa, 7, 1001)
+            libc.fclose(fp)
+            outs.append(open(path, "rb").read())
+        assert outs[0] == outs[1], case
