@@ -70,6 +70,8 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+struct WarpPlanFwd { const void* kern; int bytes_per_warp, warps_per_cta, ctas_per_sm; };
+
 struct indelgpu_ctx {
     int device = 0;
     int sms = 0;
@@ -79,6 +81,7 @@ struct indelgpu_ctx {
     std::vector<cudaEvent_t> ev_in, ev_k;             // per chunk: inputs landed, kernel done
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;     // around the kernel(s) of the last batch call
     bool timed = false;
+    std::vector<WarpPlanFwd> plans;                   // cached launch shapes of the warp-per-read kernels
     indelgpu_params params;
     DevParams P;
     // reference
@@ -238,9 +241,19 @@ extern "C" int64_t indelgpu_seg_bound(int32_t n, int64_t total_read_bases)
 
 // Persistent warp-per-read kernels: pick the CTA size that puts the most warps on an SM given the
 // per-warp shared-memory slice.
+typedef WarpPlanFwd WarpPlan;
+
 template <class Kern>
 static int plan_warps(indelgpu_ctx* c, Kern kern, int bytes_per_warp, int* warps_per_cta, int* ctas_per_sm)
 {
+    // the answer only depends on (kernel, slice size): remember it, the runtime queries are not free
+    for (const WarpPlan& w : c->plans)
+        if (w.kern == (const void*)kern && w.bytes_per_warp == bytes_per_warp) {
+            *warps_per_cta = w.warps_per_cta; *ctas_per_sm = w.ctas_per_sm;
+            // the limit is per function, not per context: another configuration may have lowered it
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, w.warps_per_cta * bytes_per_warp));
+            return 0;
+        }
     static const int cand[] = {8, 7, 6, 5, 4, 3, 2, 1};       // __launch_bounds__(256)
     int best = 0;
     *warps_per_cta = 0; *ctas_per_sm = 0;
@@ -255,6 +268,7 @@ static int plan_warps(indelgpu_ctx* c, Kern kern, int bytes_per_warp, int* warps
     if (best == 0) return fail(INDELGPU_ELIMIT, "window/read sizes need %d bytes of shared memory per warp (limit %d): range1 + maxdelsize or the read length is too large",
                                bytes_per_warp, c->max_smem_optin);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, *warps_per_cta * bytes_per_warp));
+    c->plans.push_back(WarpPlan{(const void*)kern, bytes_per_warp, *warps_per_cta, *ctas_per_sm});
     return 0;
 }
 

@@ -360,3 +360,46 @@ def test_chunked_host_path_equals_single_launch(gpu, monkeypatch):
     for i in range(6000):
         assert list(a.words(i)) == list(b.words(i)), i
     R.close()
+
+
+@pytest.mark.parametrize("k,g", [(6, 0), (9, 0), (6, 2)])
+def test_long_reads_use_the_wide_counter_path(gpu, oracle, k, g):
+    """reads longer than 255 + k bases switch the vote to 16-bit table entries / histogram counters and
+    32-bit hit-list entries (HB = 16); large range1 values widen the windows beyond 65535 diagonals"""
+    rng = make_rng(4000 + k + g)
+    p = oracle.default_params(k, g)
+    contigs = [rseq(rng, 90000, "ACGT"), rseq(rng, 60000, "ACGTN")]
+    cases = []
+    for i in range(120):
+        t = rng.randrange(2)
+        ref = contigs[t]
+        M = rng.randrange(300, 1200)
+        start = rng.randrange(2000, len(ref) - M - 3000)
+        mode = rng.random()
+        if mode < 0.5:
+            dl, cut = rng.randrange(1, 600), rng.randrange(20, M - 20)
+            read = ref[start:start + cut] + ref[start + cut + dl:start + dl + M]
+        elif mode < 0.8:
+            il, cut = rng.randrange(1, 80), rng.randrange(20, M - 20)
+            read = (ref[start:start + cut] + rseq(rng, il) + ref[start + cut:start + M])[:M]
+        else:
+            read = ref[start:start + M]
+        read = "".join(rng.choice("ACGT") if rng.random() < 0.01 else ch for ch in read)
+        position = max(0, min(len(ref) - 1, start + rng.randrange(-800, 800)))
+        range1 = rng.choice([700, 1500, 40000 if i % 7 == 0 else 900])
+        cases.append((t, position, range1, read))
+    R = gpu.Realigner(klength=k, numgaps=g)
+    R.set_reference(contigs)
+    res = R.attempt_pe_alignment_batch([c[3] for c in cases], [c[0] for c in cases],
+                                       [c[1] for c in cases], [c[2] for c in cases], detail=True)
+    seen = set()
+    for i, (t, position, range1, read) in enumerate(cases):
+        o = oracle.realign_read(p, contigs[t], position, range1, read)
+        d = res.detail[i]
+        ctx = (k, g, i, t, position, range1, len(read))
+        assert res.status[i] == o.status, ctx
+        assert (d["low1"], d["r1"], d["r2"], d["q1"], d["q2"], d["score1"]) == (o.low1, o.r1, o.r2, o.q1, o.q2, o.score1), ctx
+        assert res.segments(i) == o.segments(), ctx
+        seen.add(int(o.status))
+    assert 6 in seen
+    R.close()
