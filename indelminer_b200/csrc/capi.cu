@@ -363,7 +363,8 @@ static int launch_realign(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_r
     if (nd > (1 << 20)) return fail(INDELGPU_ELIMIT, "window of %lld diagonals exceeds the kernel limit", nd);
     const int max_numdiag = (int)nd;
     const bool banded = c->P.g > 0;
-    const WarpLayout L = make_warp_layout(c->P, max_read, max_numdiag, banded ? 1 : 0);
+    // the banded pipeline only votes with this layout (its CIGARs live in HBM), so it takes the compact form too
+    const WarpLayout L = make_warp_layout(c->P, max_read, max_numdiag, 0);
     if (((uintptr_t)d_in->read_bases & 15) != 0) return fail(INDELGPU_EINVAL, "read_bases must be 16-byte aligned on the device (TMA bulk copies)");
     if (banded) return launch_pipeline(c, d_in, max_read, max_numdiag, L, d_out, d_seg_count, st, keep_totals);
     void (*kern)(RealignArgs);

@@ -386,7 +386,7 @@ def test_long_reads_use_the_wide_counter_path(gpu, oracle, k, g):
             read = ref[start:start + M]
         read = "".join(rng.choice("ACGT") if rng.random() < 0.01 else ch for ch in read)
         position = max(0, min(len(ref) - 1, start + rng.randrange(-800, 800)))
-        range1 = rng.choice([700, 1500, 40000 if i % 7 == 0 else 900])
+        range1 = rng.choice([700, 1500, (40000 if k == 6 else 12000) if i % 7 == 0 else 900])   # hash tables (k > 6) leave less room
         cases.append((t, position, range1, read))
     R = gpu.Realigner(klength=k, numgaps=g)
     R.set_reference(contigs)
