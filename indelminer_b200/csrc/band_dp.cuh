@@ -438,27 +438,35 @@ IG_HD inline void local_sweeps_reg(const DevParams& P, const uint8_t* read, int 
     starti_o = starti; startj_o = starti + low + startt; found_o = found; cr_o = cr;
 }
 
-// local_align + ALIGN + fetch_cigar on a band of >= 2 diagonals, executed by ONE thread.
-// `low`/`up` are already clamped (localalign.c:70-71); `base` is this CTA's scratch slice.
-// out: score, q1, r1, q2, r2 (1-based inclusive, slice/window relative), ncigar, cells fwd, rev, glob, nscript
-// `bands`: 4 * (max_band + 4) ints (shared memory when it fits, else the head of the global slice);
-// `rowsb`: 8 * (max_rows + 2) ints + the script.
+// ---------------------------------------------------------------------------------------
+// One banded alignment = local_align (two sweeps) + ALIGN (divide and conquer) + fetch_cigar, executed
+// by ONE thread.  It is split in two phases so that kernels can run the second phase only for the
+// alignments that need it, 32 at a time per warp (banded_two_phase_loop): inside a warp the
+// few gapped alignments would otherwise serialise against the many that finish after phase 1.
+// `low`/`up` are already clamped (localalign.c:70-71).
+//   bands : 4 * (max_band + 4) ints (shared memory when it fits, else the head of the global slice)
+//   rowsb : 8 * (max_rows + 2) ints + the script
+// ---------------------------------------------------------------------------------------
+// an alignment waiting for its ALIGN phase (banded_two_phase_loop)
+struct DcTask { int idx, best, endi, endj, starti, startj; };
+
+struct BandLocal {
+    int best, endi, endj, starti, startj, cf, cr;
+    bool none;                 // no alignment (localalign.c:180-193)
+};
+
+// a script of zeros that needs no memory (all-REP alignments)
+struct ZeroScript { IG_HD int operator[](int) const { return 0; } };
+
+// phase 1a: the two sweeps of local_align
 template <int STRIDE>
-IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> bands, IArr<STRIDE> rowsb, int max_band, int max_rows, DcFrame* st,
-                                      const uint8_t* read, int M, const uint8_t* win, int N,
-                                      int low, int up, uint32_t* cig, int* out)
+IG_HD inline BandLocal band_local(const DevParams& P, IArr<STRIDE> bands, int max_band,
+                                  const uint8_t* read, int M, const uint8_t* win, int N, int low, int up)
 {
     const int G = P.G, H = P.H, m = G + H;
     const int band = up - low + 1;
-    const int wb = max_band + 4, wr = max_rows + 2;
-    DcCtx<STRIDE> x;
-    x.P = &P; x.A = read; x.B = win; x.cells = 0; x.ns = 0; x.last = 0;
-    x.cc = bands; x.dd = bands + wb; x.cp = bands + 2 * wb; x.dp = bands + 3 * wb;
-    IArr<STRIDE> Hp = bands, Dp = bands + wb, Hn = bands + 2 * wb, Dn = bands + 3 * wb;    // done before ALIGN starts
-    const IArr<STRIDE> rows = rowsb;
-    x.mp[0] = rows; x.mp[1] = rows + wr; x.mp[2] = rows + 2 * wr; x.fp = rows + 3 * wr;
-    x.mt[0] = rows + 4 * wr; x.mt[1] = rows + 5 * wr; x.mt[2] = rows + 6 * wr; x.ft = rows + 7 * wr;
-    x.S = rows + 8 * wr;
+    const int wb = max_band + 4;
+    IArr<STRIDE> Hp = bands, Dp = bands + wb, Hn = bands + 2 * wb, Dn = bands + 3 * wb;
     int best = 0, endi = 0, endj = 0, cf = 0, cr = 0, starti = 0, startj = 0; bool found = false;
     if (band <= 8)       local_sweeps_reg<8>(P, read, M, win, N, low, up, best, endi, endj, starti, startj, found, cf, cr);
     else if (band <= 16) local_sweeps_reg<16>(P, read, M, win, N, low, up, best, endi, endj, starti, startj, found, cf, cr);
@@ -543,39 +551,114 @@ IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> bands, IA
     }
     }
 #undef AT
-    const bool none = best <= 0 || !found || starti > M || startj > N ||
-                      endi - starti == 0 || endj - startj == 0;            // localalign.c:180-193
-    int n = 0;
-    if (!none) {
-        const int M2 = endi - starti + 1, N2 = endj - startj + 1;
-        x.A = read + starti - 1; x.B = win + startj - 1;
-        const int low2 = low - (startj - starti), up2 = up - (startj - starti);
-        // Shortcut that needs no sweep: when the end points lie on one diagonal, the ungapped path reaches
-        // the local optimum and it has so few mismatches that every gapped path (which pays at least two gap
-        // opens and two extensions and aligns at least one pair fewer) scores strictly less, the all-REP
-        // script is the UNIQUE optimum, so ALIGN's divide and conquer (globalalign.c:66-307) returns it
-        // whatever its tie rules.  Its cell count is still reported: it depends on the geometry only.
-        bool unique_diag = false;
-        if (M2 == N2 && P.match > 0 && P.mismatch < P.match && G >= 0 && H >= 0) {
-            int mm = 0;
-            for (int i = 0; i < M2; i++) mm += (x.A[i] != x.B[i]) ? 1 : 0;
-            const long long sd = (long long)(M2 - mm) * P.match + (long long)mm * P.mismatch;
-            unique_diag = sd == (long long)best && (long long)mm * (P.match - P.mismatch) < (long long)P.match + 2LL * m;
-        }
-        if (unique_diag) {
-            for (int i = 0; i < M2; i++) x.S[i] = 0;
-            x.ns = M2; x.last = 0;
-            x.cells = dc_cells_of_diagonal_path(M2, low2, up2);
-        } else {
-            global_align_script(x, st, M2, N2, low2, up2);
-        }
-        n = script_to_cigar(x.A, x.B, M2, N2, x.S, starti, M, cig);
-    }
-    out[0] = none ? 0 : best;         // ALIGN's score equals the local optimum
-    out[1] = starti; out[2] = startj; out[3] = endi; out[4] = endj;
-    out[5] = n; out[6] = cf; out[7] = cr; out[8] = none ? 0 : x.cells;
-    out[9] = none ? 0 : x.ns;         // script entries, left in x.S
+    BandLocal L;
+    L.best = best; L.endi = endi; L.endj = endj; L.starti = starti; L.startj = startj; L.cf = cf; L.cr = cr;
+    L.none = best <= 0 || !found || starti > M || startj > N ||
+             endi - starti == 0 || endj - startj == 0;            // localalign.c:180-193
+    return L;
 }
+
+// phase 1b, exact shortcut: when the end points lie on one diagonal, the ungapped path reaches the local
+// optimum and it has so few mismatches that every gapped path (which pays at least two gap opens and two
+// extensions and aligns at least one pair fewer) scores strictly less, the all-REP script is the UNIQUE
+// optimum, so ALIGN's divide and conquer (globalalign.c:66-307) returns it whatever its tie rules.
+// Writes the CIGAR and returns true; the cell count ALIGN would have swept depends on the geometry only.
+IG_HD inline bool band_unique_diagonal(const DevParams& P, const uint8_t* read, int M, const uint8_t* win,
+                                       int low, int up, const BandLocal& L, uint32_t* cig, int* ncig, int* cells_glob)
+{
+    const int M2 = L.endi - L.starti + 1, N2 = L.endj - L.startj + 1;
+    if (M2 != N2 || !(P.match > 0 && P.mismatch < P.match && P.G >= 0 && P.H >= 0)) return false;
+    const uint8_t* A = read + L.starti - 1;
+    const uint8_t* B = win + L.startj - 1;
+    int mm = 0;
+    for (int i = 0; i < M2; i++) mm += (A[i] != B[i]) ? 1 : 0;
+    const long long sd = (long long)(M2 - mm) * P.match + (long long)mm * P.mismatch;
+    if (sd != (long long)L.best || (long long)mm * (P.match - P.mismatch) >= (long long)P.match + 2LL * (P.G + P.H)) return false;
+    *ncig = script_to_cigar(A, B, M2, N2, ZeroScript(), L.starti, M, cig);
+    *cells_glob = dc_cells_of_diagonal_path(M2, low - (L.startj - L.starti), up - (L.startj - L.starti));
+    return true;
+}
+
+// phase 2: ALIGN (divide and conquer) on the sub-rectangle + fetch_cigar.  Leaves the script in rowsb.
+template <int STRIDE>
+IG_HD inline void band_global(const DevParams& P, IArr<STRIDE> bands, IArr<STRIDE> rowsb, int max_band, int max_rows, DcFrame* st,
+                              const uint8_t* read, int M, const uint8_t* win, int low, int up, const BandLocal& L,
+                              uint32_t* cig, int* ncig, int* cells_glob, int* nscript)
+{
+    const int wb = max_band + 4, wr = max_rows + 2;
+    DcCtx<STRIDE> x;
+    x.P = &P; x.cells = 0; x.ns = 0; x.last = 0;
+    x.cc = bands; x.dd = bands + wb; x.cp = bands + 2 * wb; x.dp = bands + 3 * wb;
+    x.mp[0] = rowsb; x.mp[1] = rowsb + wr; x.mp[2] = rowsb + 2 * wr; x.fp = rowsb + 3 * wr;
+    x.mt[0] = rowsb + 4 * wr; x.mt[1] = rowsb + 5 * wr; x.mt[2] = rowsb + 6 * wr; x.ft = rowsb + 7 * wr;
+    x.S = rowsb + 8 * wr;
+    const int M2 = L.endi - L.starti + 1, N2 = L.endj - L.startj + 1;
+    x.A = read + L.starti - 1; x.B = win + L.startj - 1;
+    global_align_script(x, st, M2, N2, low - (L.startj - L.starti), up - (L.startj - L.starti));
+    *ncig = script_to_cigar(x.A, x.B, M2, N2, x.S, L.starti, M, cig);
+    *cells_glob = x.cells; *nscript = x.ns;
+}
+
+// both phases back to back (host harness, single-task kernels)
+// out: score, q1, r1, q2, r2 (1-based inclusive, slice/window relative), ncigar, cells fwd, rev, glob, nscript
+template <int STRIDE>
+IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> bands, IArr<STRIDE> rowsb, int max_band, int max_rows, DcFrame* st,
+                                      const uint8_t* read, int M, const uint8_t* win, int N,
+                                      int low, int up, uint32_t* cig, int* out)
+{
+    const BandLocal L = band_local<STRIDE>(P, bands, max_band, read, M, win, N, low, up);
+    int n = 0, cg = 0, ns = 0;
+    if (!L.none) {
+        if (band_unique_diagonal(P, read, M, win, low, up, L, cig, &n, &cg)) {
+            ns = L.endi - L.starti + 1;
+            const IArr<STRIDE> S = rowsb + 8 * (max_rows + 2);
+            for (int i = 0; i < ns; i++) S[i] = 0;
+        } else {
+            band_global<STRIDE>(P, bands, rowsb, max_band, max_rows, st, read, M, win, low, up, L, cig, &n, &cg, &ns);
+        }
+    }
+    out[0] = L.none ? 0 : L.best;     // ALIGN's score equals the local optimum
+    out[1] = L.starti; out[2] = L.startj; out[3] = L.endi; out[4] = L.endj;
+    out[5] = n; out[6] = L.cf; out[7] = L.cr; out[8] = L.none ? 0 : cg;
+    out[9] = L.none ? 0 : ns;         // script entries, left in rowsb
+}
+
+#ifdef __CUDACC__
+// Warp-level scheduling of the two phases (used by band_tasks_kernel and pipe_dp_kernel).  Every lane
+// runs phase 1 (sweeps + shortcut) on its own task; tasks that need ALIGN are collected in a per-warp
+// buffer and phase 2 runs whenever 32 are waiting (and once more for the tail), so that the divide and
+// conquer always executes with a full warp while other warps of the SM hide its latency.
+// phase1(idx, DcTask&) -> bool "needs phase 2"; phase2(const DcTask&).  `pend` holds 64 DcTask per warp.
+template <class P1, class P2>
+__device__ __forceinline__ void banded_two_phase_loop(int n, DcTask* pend, P1 phase1, P2 phase2)
+{
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    int waiting = 0;                                             // warp-uniform
+#pragma unroll 1
+    for (int idx0 = gwarp * 32; idx0 < n || waiting > 0; idx0 += nwarps * 32) {
+        if (idx0 < n) {
+            const int idx = idx0 + lane;
+            DcTask t;
+            t.idx = idx;
+            const bool q = (idx < n) ? phase1(idx, t) : false;
+            const uint32_t qm = __ballot_sync(0xFFFFFFFFu, q);
+            if (q) pend[waiting + __popc(qm & ((1u << lane) - 1u))] = t;
+            waiting += __popc(qm);
+            __syncwarp();
+        }
+        const bool last = idx0 + nwarps * 32 >= n;
+#pragma unroll 1
+        while (waiting >= 32 || (last && waiting > 0)) {
+            const int take = min(32, waiting);
+            if (lane < take) phase2(pend[waiting - take + lane]);
+            waiting -= take;
+            __syncwarp();
+        }
+    }
+}
+#endif
 
 constexpr int kDcFrames = 24;     // recursion depth <= log2(band) + 2 (every child band is at most half its parent's)
 

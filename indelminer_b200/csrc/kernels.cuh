@@ -133,6 +133,13 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
     return v;
 }
 
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
 struct Cta {
     // dynamic shared memory views
     uint32_t* keys; uint32_t* vals; uint32_t* hist; uint8_t* read; uint32_t* bits; int* psum;

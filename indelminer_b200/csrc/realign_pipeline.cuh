@@ -81,35 +81,38 @@ pipe_vote_kernel(const __grid_constant__ RealignArgs a, const PipeBufs p, const 
 }
 
 // ---- thread per read: attempt_band_alignment (alignment.c:343-391) ----------------------------
+// which window / read slice an alignment of `round` uses; false when the read takes no part in it
+__device__ __forceinline__ bool pipe_task(const RealignArgs& a, const PipeBufs& p, int round, int idx, ReadCtx* c,
+                                          uint32_t* zs1, uint32_t* e1, uint32_t* zs2, uint32_t* e2, int* low)
+{
+    *c = load_read_ctx(a, idx);
+    if (c->bad) return false;
+    const int flags = p.flags[idx];
+    if (!(round == 0 ? (flags & PF_VOTE1_OK) : (flags & PF_VOTE2_OK))) return false;
+    *low = p.low[(int64_t)round * a.n + idx];
+    if (round == 0) { *zs1 = (uint32_t)c->left1; *e1 = (uint32_t)c->right1; *zs2 = 0; *e2 = (uint32_t)c->readlen; }
+    else { const Plan pl = p.plan[idx]; *zs1 = pl.zs1; *e1 = pl.e1; *zs2 = pl.zs2; *e2 = pl.e2; }
+    return true;
+}
+
+// sweeps of local_align + the unique-diagonal shortcut for every read; the alignments that need ALIGN's
+// divide and conquer run it 32 at a time (banded_two_phase_loop; see band_tasks_kernel for why)
 __global__ void __launch_bounds__(128, BAND_MIN_BLOCKS)
 pipe_dp_kernel(const __grid_constant__ RealignArgs a, const PipeBufs p, const int round, const int bands_in_smem)
 {
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ DcTask s_pend[4][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int wb4 = 4 * (a.scratch.max_band + 4);
     const IArr<32> gbase{a.scratch.base + (long long)gwarp * 32 * a.scratch.stride + lane};
     const IArr<32> bands = bands_in_smem ? IArr<32>{reinterpret_cast<int*>(smem) + (size_t)warp * 32 * wb4 + lane} : gbase;
     const IArr<32> rowsb = gbase + wb4;
     DcFrame st[kDcFrames];
-#pragma unroll 1
-    for (int idx0 = gwarp * 32; idx0 < a.n; idx0 += nwarps * 32) {
-        const int idx = idx0 + lane;
-        bool active = false;
-        ReadCtx c; c.bad = true; c.roff = 0; c.cbase = 0; c.readlen = 0;
-        uint32_t zs1 = 0, e1 = 0, zs2 = 0, e2 = 0;
-        int low = 0;
-        if (idx < a.n) {
-            c = load_read_ctx(a, idx);
-            const int flags = c.bad ? 0 : p.flags[idx];
-            active = !c.bad && (round == 0 ? (flags & PF_VOTE1_OK) != 0 : (flags & PF_VOTE2_OK) != 0);
-            if (active) {
-                low = p.low[(int64_t)round * a.n + idx];
-                if (round == 0) { zs1 = (uint32_t)c.left1; e1 = (uint32_t)c.right1; zs2 = 0; e2 = (uint32_t)c.readlen; }
-                else { const Plan pl = p.plan[idx]; zs1 = pl.zs1; e1 = pl.e1; zs2 = pl.zs2; e2 = pl.e2; }
-            }
-        }
+
+    auto phase1 = [&](int idx, DcTask& t) -> bool {
+        ReadCtx c; uint32_t zs1 = 0, e1 = 0, zs2 = 0, e2 = 0; int low = 0;
+        bool active = pipe_task(a, p, round, idx, &c, &zs1, &e1, &zs2, &e2, &low);
         const int N = (int)(e1 - zs1), M = (int)(e2 - zs2);
         const int lo = max(-M, low), hi = min(N, low + a.P.g);            // localalign.c:70-71
         const int band = hi - lo + 1;
@@ -117,27 +120,47 @@ pipe_dp_kernel(const __grid_constant__ RealignArgs a, const PipeBufs p, const in
             atomicExch(a.error_flag, 1);                                  // cannot happen for N, M >= 1; kept as a guard
             active = false;
         }
-        const uint8_t* rptr = a.reads + c.roff + zs2;
-        const uint8_t* wptr = a.ref.raw + c.cbase + zs1;
-        if (!active) {
-            if (idx < a.n && round == 0) { Aln z; memset(&z, 0, sizeof(z)); p.aln[idx] = z; p.aln[(int64_t)a.n + idx] = z; }
-            continue;
-        }
-        int out[10];
-        uint32_t* cig = p.cig + ((int64_t)round * a.n + idx) * p.cig_stride;
-        align_banded_serial<32>(a.P, bands, rowsb, a.scratch.max_band, a.scratch.max_rows, st, rptr, M, wptr, N, lo, hi, cig, out);
         Aln r;
-        r.low = low; r.up = low + a.P.g; r.score = out[0];
-        if (out[0] <= 0) { r.r1 = r.r2 = r.q1 = r.q2 = 0; r.n = 0; }      // alignment.c:365-372
-        else {
-            r.q1 = out[1] + (int)zs2 - 1; r.r1 = out[2] + (int)zs1 - 1;   // :385-388
-            r.q2 = out[3] + (int)zs2;     r.r2 = out[4] + (int)zs1;
-            r.n = out[5];
+        memset(&r, 0, sizeof(r));
+        bool need = false;
+        if (active) {
+            const uint8_t* read = a.reads + c.roff + zs2;
+            const uint8_t* win = a.ref.raw + c.cbase + zs1;
+            const BandLocal L = band_local<32>(a.P, bands, a.scratch.max_band, read, M, win, N, lo, hi);
+            r.low = low; r.up = low + a.P.g;
+            r.cells_fwd = L.cf; r.cells_rev = L.cr;
+            if (!L.none) {                                                // :385-388
+                r.score = L.best;
+                r.q1 = L.starti + (int)zs2 - 1; r.r1 = L.startj + (int)zs1 - 1;
+                r.q2 = L.endi + (int)zs2;       r.r2 = L.endj + (int)zs1;
+                uint32_t* cig = p.cig + ((int64_t)round * a.n + idx) * p.cig_stride;
+                int n = 0, cells = 0;
+                if (band_unique_diagonal(a.P, read, M, win, lo, hi, L, cig, &n, &cells)) { r.n = n; r.cells_glob = cells; }
+                else {
+                    need = true;
+                    t.best = L.best; t.endi = L.endi; t.endj = L.endj; t.starti = L.starti; t.startj = L.startj;
+                }
+            }
         }
-        r.cells_fwd = out[6]; r.cells_rev = out[7]; r.cells_glob = out[8];
-        p.aln[(int64_t)round * a.n + idx] = r;
+        if (active || round == 0) p.aln[(int64_t)round * a.n + idx] = r;
         if (round == 0) { Aln z; memset(&z, 0, sizeof(z)); p.aln[(int64_t)a.n + idx] = z; }
-    }
+        return need;
+    };
+    auto phase2 = [&](const DcTask& t) {
+        const int idx = t.idx;
+        ReadCtx c; uint32_t zs1 = 0, e1 = 0, zs2 = 0, e2 = 0; int low = 0;
+        pipe_task(a, p, round, idx, &c, &zs1, &e1, &zs2, &e2, &low);
+        const int N = (int)(e1 - zs1), M = (int)(e2 - zs2);
+        const int lo = max(-M, low), hi = min(N, low + a.P.g);
+        BandLocal L;
+        L.best = t.best; L.endi = t.endi; L.endj = t.endj; L.starti = t.starti; L.startj = t.startj; L.cf = 0; L.cr = 0; L.none = false;
+        int n = 0, cells = 0, ns = 0;
+        band_global<32>(a.P, bands, rowsb, a.scratch.max_band, a.scratch.max_rows, st, a.reads + c.roff + zs2, M,
+                        a.ref.raw + c.cbase + zs1, lo, hi, L, p.cig + ((int64_t)round * a.n + idx) * p.cig_stride, &n, &cells, &ns);
+        Aln* r = p.aln + (int64_t)round * a.n + idx;
+        r->n = n; r->cells_glob = cells;
+    };
+    banded_two_phase_loop(a.n, s_pend[warp], phase1, phase2);
 }
 
 // ---- warp per read: combine + results ----------------------------------------------------------

@@ -139,27 +139,28 @@ align_tasks_kernel(const __grid_constant__ TaskArgs a)
 // local_align + ALIGN + fetch_cigar over n tasks, ONE THREAD PER TASK (inter-task parallelism).
 // At the band widths the caller produces (numgaps + 1 diagonals, typically <= 17) one anti-diagonal
 // of a band holds at most band/2 independent cells, so a wavefront inside one alignment would leave
-// most of a warp idle; 32 independent alignments per warp keep every lane busy, and the
-// lane-interleaved scratch (IArr<32>) turns the per-cell work-array traffic into full 128-byte lines
-// that stay in L1.  The exact divide-and-conquer of the reference runs unchanged per thread.
+// most of a warp idle; 32 independent alignments per warp keep every lane busy.
+//
+// Every lane first runs the two sweeps of local_align (registers for bands <= 40) and the
+// unique-diagonal shortcut; the few tasks that really need ALIGN's divide and conquer wait in a per-warp
+// buffer until 32 of them can run it together (banded_two_phase_loop) on lane-interleaved scratch
+// (IArr<32>: one 128-byte line per access).  Doing both in one pass per task would make every warp wait
+// for its two or three gapped alignments at 10 % lane utilisation.
 __global__ void __launch_bounds__(128, BAND_MIN_BLOCKS)
 band_tasks_kernel(const __grid_constant__ TaskArgs a, const int bands_in_smem)
 {
-    // dynamic shared memory (when it fits): the four band-wide work arrays of every thread, lane-interleaved
-    // ([element][thread of the CTA] -> bank = lane, conflict-free); they take ~8 accesses per DP cell
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ DcTask s_pend[4][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int wb4 = 4 * (a.scratch.max_band + 4);
-    // global scratch of warp w: [w * 32 * stride, (w + 1) * 32 * stride), lane l at element offset l
     const IArr<32> gbase{a.scratch.base + (long long)gwarp * 32 * a.scratch.stride + lane};
     const IArr<32> bands = bands_in_smem ? IArr<32>{reinterpret_cast<int*>(smem) + (size_t)warp * 32 * wb4 + lane} : gbase;
     const IArr<32> rowsb = gbase + wb4;
     unsigned long long cf = 0, cr = 0, cg = 0;
     DcFrame st[kDcFrames];
-#pragma unroll 1
-    for (int idx = gwarp * 32 + lane; idx < a.n; idx += nwarps * 32) {
+
+    auto phase1 = [&](int idx, DcTask& t) -> bool {
         const int64_t roff = a.read_off[idx], woff = a.ref_off[idx];
         const int M = (int)(a.read_off[idx + 1] - roff), N = (int)(a.ref_off[idx + 1] - woff);
         const int lo = max(-M, a.low[idx]), hi = min(N, a.up[idx]);       // localalign.c:70-71
@@ -168,32 +169,62 @@ band_tasks_kernel(const __grid_constant__ TaskArgs a, const int bands_in_smem)
                          2 * M + band + 4 > a.cigar_stride;
         if (bad) {
             a.score[idx] = 0; a.ncigar[idx] = 0;
-            for (int t = 0; t < 4; t++) a.ends[4 * idx + t] = 0;
+            for (int u = 0; u < 4; u++) a.ends[4 * idx + u] = 0;
             atomicExch(a.error_flag, 1);
-            continue;
+            return false;
         }
-        int out[10];
-        uint32_t* cig = a.cigar + (int64_t)idx * a.cigar_stride;
-        align_banded_serial<32>(a.P, bands, rowsb, a.scratch.max_band, a.scratch.max_rows, st,
-                                a.reads + roff, M, a.refs + woff, N, lo, hi, cig, out);
-        const int score = out[0];
+        const uint8_t* read = a.reads + roff;
+        const uint8_t* win = a.refs + woff;
+        const BandLocal L = band_local<32>(a.P, bands, a.scratch.max_band, read, M, win, N, lo, hi);
+        const int score = L.none ? 0 : L.best;
         a.score[idx] = score;
-        for (int t = 0; t < 4; t++) a.ends[4 * idx + t] = score > 0 ? out[1 + t] : 0;      // q1 r1 q2 r2
-        a.ncigar[idx] = score > 0 ? out[5] : 0;
-        cf += (unsigned long long)out[6]; cr += (unsigned long long)out[7]; cg += (unsigned long long)out[8];
-        if (score > 0 && a.script) {
+        a.ends[4 * idx + 0] = score > 0 ? L.starti : 0; a.ends[4 * idx + 1] = score > 0 ? L.startj : 0;
+        a.ends[4 * idx + 2] = score > 0 ? L.endi : 0;   a.ends[4 * idx + 3] = score > 0 ? L.endj : 0;
+        cf += (unsigned long long)L.cf; cr += (unsigned long long)L.cr;
+        int n = 0, cells = 0;
+        bool need = false;
+        if (!L.none) {
+            if (band_unique_diagonal(a.P, read, M, win, lo, hi, L, a.cigar + (int64_t)idx * a.cigar_stride, &n, &cells)) {
+                cg += (unsigned long long)cells;
+                if (a.script) {
+                    int32_t* so = a.script + (int64_t)idx * a.script_stride;
+                    const int len = L.endi - L.starti + 1;
+                    for (int u = 0; u < min(len, a.script_stride); u++) so[u] = 0;
+                    if (len < a.script_stride) so[len] = 0x7FFFFFFF;
+                }
+            } else {
+                need = true;
+                t.best = L.best; t.endi = L.endi; t.endj = L.endj; t.starti = L.starti; t.startj = L.startj;
+            }
+        }
+        a.ncigar[idx] = n;
+        return need;
+    };
+    auto phase2 = [&](const DcTask& t) {
+        const int idx = t.idx;
+        const int64_t roff = a.read_off[idx], woff = a.ref_off[idx];
+        const int M = (int)(a.read_off[idx + 1] - roff), N = (int)(a.ref_off[idx + 1] - woff);
+        const int lo = max(-M, a.low[idx]), hi = min(N, a.up[idx]);
+        BandLocal L;
+        L.best = t.best; L.endi = t.endi; L.endj = t.endj; L.starti = t.starti; L.startj = t.startj; L.cf = 0; L.cr = 0; L.none = false;
+        int n = 0, cells = 0, ns = 0;
+        band_global<32>(a.P, bands, rowsb, a.scratch.max_band, a.scratch.max_rows, st, a.reads + roff, M, a.refs + woff, lo, hi, L,
+                        a.cigar + (int64_t)idx * a.cigar_stride, &n, &cells, &ns);
+        a.ncigar[idx] = n;
+        cg += (unsigned long long)cells;
+        if (a.script) {
             int32_t* so = a.script + (int64_t)idx * a.script_stride;
             const IArr<32> S = rowsb + 8 * (a.scratch.max_rows + 2);
-            const int len = out[9];
-            for (int t = 0; t < min(len, a.script_stride); t++) so[t] = S[t];
-            if (len < a.script_stride) so[len] = 0x7FFFFFFF;
+            for (int u = 0; u < min(ns, a.script_stride); u++) so[u] = S[u];
+            if (ns < a.script_stride) so[ns] = 0x7FFFFFFF;
         }
-    }
+    };
+    banded_two_phase_loop(a.n, s_pend[warp], phase1, phase2);
+
     __syncwarp();
-    // one atomic per warp and counter
-    cf = __reduce_add_sync(0xFFFFFFFFu, (unsigned)cf) + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(cf >> 32)) << 32);
-    cr = __reduce_add_sync(0xFFFFFFFFu, (unsigned)cr) + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(cr >> 32)) << 32);
-    cg = __reduce_add_sync(0xFFFFFFFFu, (unsigned)cg) + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(cg >> 32)) << 32);
+    cf = warp_sum_u64(cf);
+    cr = warp_sum_u64(cr);
+    cg = warp_sum_u64(cg);
     if (lane == 0 && (cf | cr | cg)) {
         atomicAdd(a.cell_totals + 0, cf);
         atomicAdd(a.cell_totals + 1, cr);
