@@ -268,6 +268,13 @@ static int plan_warps(indelgpu_ctx* c, Kern kern, int bytes_per_warp, int* warps
     if (best == 0) return fail(INDELGPU_ELIMIT, "window/read sizes need %d bytes of shared memory per warp (limit %d): range1 + maxdelsize or the read length is too large",
                                bytes_per_warp, c->max_smem_optin);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, *warps_per_cta * bytes_per_warp));
+    if (const char* e = getenv("INDELGPU_MAX_WARPS_PER_SM")) {   // occupancy experiments only
+        const int cap = atoi(e);
+        if (cap > 0) {
+            *warps_per_cta = std::min(*warps_per_cta, cap);
+            *ctas_per_sm = std::max(1, std::min(*ctas_per_sm, cap / *warps_per_cta));
+        }
+    }
     c->plans.push_back(WarpPlan{(const void*)kern, bytes_per_warp, *warps_per_cta, *ctas_per_sm});
     return 0;
 }
