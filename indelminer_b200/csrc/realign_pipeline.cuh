@@ -28,6 +28,14 @@ struct PipeBufs {
 };
 
 // ---- warp per read: (plan +) vote ------------------------------------------------------------
+// what one read needs from the vote of `round`; staged one read ahead like in the fused kernel
+struct VoteJob {
+    ReadCtx c;
+    uint32_t zs1, e1, zs2, e2, anc;
+    int flags;
+    bool go;                  // false: nothing to stage or vote for this read in this round
+};
+
 template <bool DIRECT, int HB>
 __global__ void __launch_bounds__(256)
 pipe_vote_kernel(const __grid_constant__ RealignArgs a, const PipeBufs p, const int round)
@@ -37,46 +45,66 @@ pipe_vote_kernel(const __grid_constant__ RealignArgs a, const PipeBufs p, const 
     WarpView V;
     bind_warp(V, smem + (size_t)warp * a.L.total, a.L);
     init_warp_tables(V);
-    if (lane == 0) { mbar_init(V.bar, 1); mbar_fence_init(); }
+    if (lane == 0) { mbar_init(V.bar + 0, 1); mbar_init(V.bar + 1, 1); mbar_fence_init(); }
     __syncwarp();
-    uint32_t phase = 0;
+    uint32_t phase = 0;                                           // bit b = parity of buffer b's barrier
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-#pragma unroll 1
-    for (int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < a.n; idx += nwarps) {
-        const ReadCtx c = load_read_ctx(a, idx);
-        if (c.bad) { if (round == 0 && lane == 0) p.flags[idx] = 0; continue; }
-        const int flags = round ? p.flags[idx] : 0;
-        if (round == 1 && !(flags & PF_VOTE1_OK)) continue;
-        uint32_t zs1 = (uint32_t)c.left1, e1 = (uint32_t)c.right1, zs2 = 0, e2 = (uint32_t)c.readlen, anc = (uint32_t)c.position;
-        if (round == 1) {                                         // plan: alignment.c:568-717
-            Plan* s_plan = reinterpret_cast<Plan*>(V.misc);
+    Plan* s_plan = reinterpret_cast<Plan*>(V.misc);
+
+    // derive the job of read idx (round 1: plan first, alignment.c:568-717) and start its copies
+    auto prepare = [&](int idx, int buf) -> VoteJob {
+        VoteJob j;
+        j.go = false; j.flags = 0;
+        j.zs1 = j.e1 = j.zs2 = j.e2 = j.anc = 0;
+        if (idx >= a.n) { j.c.bad = true; return j; }
+        j.c = load_read_ctx(a, idx);
+        if (j.c.bad) { if (round == 0 && lane == 0) p.flags[idx] = 0; return j; }
+        j.zs1 = (uint32_t)j.c.left1; j.e1 = (uint32_t)j.c.right1; j.zs2 = 0; j.e2 = (uint32_t)j.c.readlen; j.anc = (uint32_t)j.c.position;
+        j.go = true;
+        if (round == 1) {
+            j.flags = p.flags[idx];
+            if (!(j.flags & PF_VOTE1_OK)) { j.go = false; return j; }
+            __syncwarp();
             if (lane == 0) {
                 const Aln a1 = p.aln[idx];
-                make_plan(a.P, a1, p.cig + (int64_t)idx * p.cig_stride, c.position, c.left2, c.right2, (unsigned)c.readlen, s_plan);
+                make_plan(a.P, a1, p.cig + (int64_t)idx * p.cig_stride, j.c.position, j.c.left2, j.c.right2, (unsigned)j.c.readlen, s_plan);
                 p.plan[idx] = *s_plan;
             }
             __syncwarp();
-            const bool go = s_plan->go != 0;
-            zs1 = s_plan->zs1; e1 = s_plan->e1; zs2 = s_plan->zs2; e2 = s_plan->e2; anc = s_plan->anc;
+            j.go = s_plan->go != 0;
+            j.zs1 = s_plan->zs1; j.e1 = s_plan->e1; j.zs2 = s_plan->zs2; j.e2 = s_plan->e2; j.anc = s_plan->anc;
             __syncwarp();
-            if (!go) continue;
         }
-        if (lane == 0) stage_read(a, V, c, 0);
-        const bool landed = mbar_wait(V.bar, phase);
-        phase ^= 1u;
-        if (!landed) { if (lane == 0) atomicExch(a.error_flag, 3); break; }
-        const uint8_t* read = read_buf(V, 0) + (int)(c.roff & 15);
-        pack_read_warp(V, read, c.readlen);
-        const int64_t sw0 = ((c.cbase + c.left2) & ~(int64_t)63) >> 4;
-        bool ok;
-        const int low = vote_band_warp<DIRECT, HB>(a.P, V, win_buf(V, 0), sw0, c.cbase + zs1, (int)(e1 - zs1), (int)zs2,
-                                                   (int)(e2 - zs2), (int)(anc - zs1), &ok);
-        if (lane == 0) {
-            p.low[(int64_t)round * a.n + idx] = low;
-            if (round == 0) p.flags[idx] = ok ? PF_VOTE1_OK : 0;
-            else p.flags[idx] = flags | PF_GO | (ok ? PF_VOTE2_OK : 0);
+        if (j.go && lane == 0) stage_read(a, V, j.c, buf);
+        return j;
+    };
+
+    int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int it = 0;
+    VoteJob cur = prepare(idx, 0);
+#pragma unroll 1
+    for (; idx < a.n; idx += nwarps, it++) {
+        const int buf = it & 1;
+        const VoteJob nxt = prepare(idx + nwarps, buf ^ 1);
+        if (cur.go) {
+            const bool landed = mbar_wait(V.bar + buf, (phase >> buf) & 1u);
+            phase ^= 1u << buf;
+            if (!landed) { if (lane == 0) atomicExch(a.error_flag, 3); break; }
+            const ReadCtx& c = cur.c;
+            const uint8_t* read = read_buf(V, buf) + (int)(c.roff & 15);
+            pack_read_warp(V, read, c.readlen);
+            const int64_t sw0 = ((c.cbase + c.left2) & ~(int64_t)63) >> 4;
+            bool ok;
+            const int low = vote_band_warp<DIRECT, HB>(a.P, V, win_buf(V, buf), sw0, c.cbase + cur.zs1, (int)(cur.e1 - cur.zs1),
+                                                       (int)cur.zs2, (int)(cur.e2 - cur.zs2), (int)(cur.anc - cur.zs1), &ok);
+            if (lane == 0) {
+                p.low[(int64_t)round * a.n + idx] = low;
+                if (round == 0) p.flags[idx] = ok ? PF_VOTE1_OK : 0;
+                else p.flags[idx] = cur.flags | PF_GO | (ok ? PF_VOTE2_OK : 0);
+            }
+            __syncwarp();
         }
-        __syncwarp();
+        cur = nxt;
     }
 }
 
