@@ -78,7 +78,8 @@ struct indelgpu_ctx {
     int max_smem_optin = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t st_in = nullptr, st_out = nullptr;   // H2D / D2H streams of the chunked host path
-    std::vector<cudaEvent_t> ev_in, ev_k;             // per chunk: inputs landed, kernel done
+    std::vector<cudaEvent_t> ev_in, ev_k, ev_out;     // per chunk: inputs landed, kernel done, segment count on the host
+    void* pinned_counts = nullptr; int pinned_counts_cap = 0;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;     // around the kernel(s) of the last batch call
     bool timed = false;
     std::vector<WarpPlanFwd> plans;                   // cached launch shapes of the warp-per-read kernels
@@ -164,6 +165,8 @@ extern "C" void indelgpu_destroy(indelgpu_ctx* c)
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_out) cudaEventDestroy(e);
+    if (c->pinned_counts) cudaFreeHost(c->pinned_counts);
     DevBuf* all[] = {&c->ref_raw, &c->ref_packed, &c->ref_off, &c->ref_len, &c->in_reads, &c->in_off, &c->in_tid,
                      &c->in_pos, &c->in_rng, &c->out_status, &c->out_nseg, &c->out_rstart, &c->out_segoff,
                      &c->out_segs, &c->out_detail, &c->out_cig1, &c->out_cig2, &c->counters, &c->scratch,
@@ -480,14 +483,20 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
         !o->status || !o->nseg || !o->rstart || !o->seg_off || !o->segs)
         return fail(INDELGPU_EINVAL, "realign_batch: NULL buffer");
     CU(cudaSetDevice(c->device));
-    int max_read = 0, max_range = 0;
-    for (int i = 0; i < n; i++) {
-        const int64_t len = h->read_off[i + 1] - h->read_off[i];
-        if (len <= 0 || len > 65000) return fail(INDELGPU_ELIMIT, "read %d has length %lld (must be 1..65000)", i, (long long)len);
-        max_read = std::max(max_read, (int)len);
-        if (h->range1[i] < 0) return fail(INDELGPU_EINVAL, "read %d: negative range", i);
-        max_range = std::max(max_range, h->range1[i]);
-    }
+    // sizes are validated (and the kernel limits derived) chunk by chunk, right before a chunk is enqueued,
+    // so that the first copies do not wait for a pass over the whole batch
+    auto scan_range = [&](int lo, int hi, int* mr, int* mg) -> int {
+        int max_read = 0, max_range = 0;
+        for (int i = lo; i < hi; i++) {
+            const int64_t len = h->read_off[i + 1] - h->read_off[i];
+            if (len <= 0 || len > 65000) return fail(INDELGPU_ELIMIT, "read %d has length %lld (must be 1..65000)", i, (long long)len);
+            max_read = std::max(max_read, (int)len);
+            if (h->range1[i] < 0) return fail(INDELGPU_EINVAL, "read %d: negative range", i);
+            max_range = std::max(max_range, h->range1[i]);
+        }
+        *mr = max_read; *mg = max_range;
+        return 0;
+    };
     const int64_t nbases = h->read_off[n] - h->read_off[0];
     if (h->read_off[0] != 0) return fail(INDELGPU_EINVAL, "read_off[0] must be 0");
     const int64_t segcap = std::min<int64_t>(o->seg_capacity, indelgpu_seg_bound(n, nbases));
@@ -515,6 +524,7 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
     // Large batches without debug outputs are cut into chunks so that the H2D copy of chunk i+1 and
     // the D2H copy of chunk i-1 overlap the kernel of chunk i (three streams, two events per chunk).
     // Chunks share the reference, the segment allocator and the counters; read offsets stay absolute.
+    int64_t segs_copied = 0;                         // segment words the chunked path has already brought back
     const bool debug_out = o->detail || o->cigar1 || o->cigar2;
     int kChunkReads = 1 << 17;
     if (const char* e = getenv("INDELGPU_CHUNK_READS")) { const int v = atoi(e); if (v >= 64) kChunkReads = v; }
@@ -526,10 +536,24 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
             CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
             c->ev_in.push_back(e1); c->ev_k.push_back(e2);
         }
-        CU(cudaMemcpyAsync(c->in_off.p, h->read_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->st_in));
+        if (!c->pinned_counts || c->pinned_counts_cap < nchunks) {
+            if (c->pinned_counts) cudaFreeHost(c->pinned_counts);
+            c->pinned_counts = nullptr; c->pinned_counts_cap = 0;
+            CU(cudaMallocHost(&c->pinned_counts, 8 * (size_t)(nchunks + 8)));
+            c->pinned_counts_cap = nchunks + 8;
+        }
+        while ((int)c->ev_out.size() < nchunks) {
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->ev_out.push_back(e);
+        }
+        unsigned long long* counts = reinterpret_cast<unsigned long long*>(c->pinned_counts);
         for (int ch = 0; ch < nchunks; ch++) {
             const int c0 = ch * kChunkReads, c1 = std::min(n, c0 + kChunkReads), m = c1 - c0;
+            int max_read = 0, max_range = 0;
+            if (int rcs = scan_range(c0, c1, &max_read, &max_range)) { cudaDeviceSynchronize(); return rcs; }
             const int64_t b0 = h->read_off[c0], b1 = h->read_off[c1];
+            CU(cudaMemcpyAsync(c->in_off.as<int64_t>() + c0, h->read_off + c0, 8 * (size_t)(m + 1), cudaMemcpyHostToDevice, c->st_in));
             CU(cudaMemcpyAsync(c->in_reads.as<uint8_t>() + b0, h->read_bases + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->st_in));
             CU(cudaMemcpyAsync(c->in_tid.as<int32_t>() + c0, h->tid + c0, 4 * (size_t)m, cudaMemcpyHostToDevice, c->st_in));
             CU(cudaMemcpyAsync(c->in_pos.as<int32_t>() + c0, h->position + c0, 4 * (size_t)m, cudaMemcpyHostToDevice, c->st_in));
@@ -541,16 +565,31 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
             indelgpu_result rc2 = dout;
             rc2.status = dout.status + c0; rc2.nseg = dout.nseg + c0; rc2.rstart = dout.rstart + c0; rc2.seg_off = dout.seg_off + c0;
             int rcl = launch_realign(c, &dc, max_read, max_range, &rc2, ctr_segs(c), st, ch > 0);
-            if (rcl) return rcl;
+            if (rcl) { cudaDeviceSynchronize(); return rcl; }
             CU(cudaEventRecord(c->ev_k[ch], st));
             CU(cudaStreamWaitEvent(c->st_out, c->ev_k[ch], 0));
+            CU(cudaMemcpyAsync(counts + ch, ctr_segs(c), 8, cudaMemcpyDeviceToHost, c->st_out));
+            CU(cudaEventRecord(c->ev_out[ch], c->st_out));
             CU(cudaMemcpyAsync(o->status + c0, dout.status + c0, 4 * (size_t)m, cudaMemcpyDeviceToHost, c->st_out));
             CU(cudaMemcpyAsync(o->nseg + c0, dout.nseg + c0, 4 * (size_t)m, cudaMemcpyDeviceToHost, c->st_out));
             CU(cudaMemcpyAsync(o->rstart + c0, dout.rstart + c0, 4 * (size_t)m, cudaMemcpyDeviceToHost, c->st_out));
             CU(cudaMemcpyAsync(o->seg_off + c0, dout.seg_off + c0, 8 * (size_t)m, cudaMemcpyDeviceToHost, c->st_out));
         }
+        // segment words: the allocator is monotonic and the chunks' kernels run in order, so the words of
+        // chunk ch are [count after ch-1, count after ch); copy each range as soon as its count is known,
+        // while the later chunks are still being realigned
+        unsigned long long prev = 0;
+        for (int ch = 0; ch < nchunks; ch++) {
+            CU(cudaEventSynchronize(c->ev_out[ch]));
+            const unsigned long long cur = std::min<unsigned long long>(counts[ch], (unsigned long long)segcap);
+            if (cur > prev) CU(cudaMemcpyAsync(o->segs + prev, dout.segs + prev, 4 * (size_t)(cur - prev), cudaMemcpyDeviceToHost, c->st_out));
+            prev = std::max(prev, cur);
+        }
+        segs_copied = (int64_t)prev;
         CU(cudaStreamSynchronize(c->st_out));
     } else {
+        int max_read = 0, max_range = 0;
+        if (int rcs = scan_range(0, n, &max_read, &max_range)) return rcs;
         CU(cudaMemcpyAsync(c->in_reads.p, h->read_bases, (size_t)nbases, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(c->in_off.p, h->read_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(c->in_tid.p, h->tid, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
@@ -576,7 +615,8 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
     if (err == 3) return fail(INDELGPU_ECUDA, "a TMA bulk copy never completed (mbarrier wait timed out)");
     if (err == 2 || (int64_t)segcount > segcap) return fail(INDELGPU_ELIMIT, "segment buffer too small: need %llu words, have %lld", segcount, (long long)segcap);
     o->seg_count = (int64_t)segcount;
-    if (segcount) CU(cudaMemcpyAsync(o->segs, dout.segs, 4 * (size_t)segcount, cudaMemcpyDeviceToHost, st));
+    if ((int64_t)segcount > segs_copied)
+        CU(cudaMemcpyAsync(o->segs + segs_copied, dout.segs + segs_copied, 4 * (size_t)((int64_t)segcount - segs_copied), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (err == 1) return fail(INDELGPU_ELIMIT, "at least one read was rejected (status %d): bad contig/position, window assert of alignment.c:548-553 or a size limit", ST_ASSERT);
     return 0;
