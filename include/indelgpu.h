@@ -138,11 +138,17 @@ typedef struct indelgpu_result {
 /* worst-case number of segment words a batch can produce */
 int64_t indelgpu_seg_bound(int32_t n, int64_t total_read_bases);
 
-/* Host buffers in, host buffers out: H2D copies, kernels, D2H copies, synchronised on return. */
+/* Host buffers in, host buffers out: H2D copies, kernels, D2H copies, synchronised on return.
+ * Batches of >= 2^18 reads are processed in chunks of 2^17 reads whose copies overlap the kernels of
+ * the neighbouring chunks (pinned buffers from indelgpu_host_alloc make the copies asynchronous);
+ * results do not depend on the chunking.  Contexts are independent and may be driven from different
+ * host threads, one thread per context at a time. */
 int indelgpu_realign_batch(indelgpu_ctx* ctx, const indelgpu_batch* h_in, indelgpu_result* h_out);
 
 /* Device buffers in and out (all pointers in *d_in / *d_out are device pointers, the structs
- * themselves live on the host).  d_out->seg_count is not filled; the count is left in the
+ * themselves live on the host).  d_in->read_bases must be 16-byte aligned and readable up to the next
+ * 16-byte boundary past its last base (the kernels stage reads with TMA bulk copies; any cudaMalloc'ed
+ * buffer qualifies).  d_out->seg_count is not filled; the count is left in the
  * int64 device word *d_seg_count.  Asynchronous on `stream`. */
 int indelgpu_realign_batch_device(indelgpu_ctx* ctx, const indelgpu_batch* d_in,
                                   int32_t max_read_len, int32_t max_range1,
