@@ -468,10 +468,17 @@ IG_HD inline BandLocal band_local(const DevParams& P, IArr<STRIDE> bands, int ma
     const int wb = max_band + 4;
     IArr<STRIDE> Hp = bands, Dp = bands + wb, Hn = bands + 2 * wb, Dn = bands + 3 * wb;
     int best = 0, endi = 0, endj = 0, cf = 0, cr = 0, starti = 0, startj = 0; bool found = false;
-    if (band <= 8)       local_sweeps_reg<8>(P, read, M, win, N, low, up, best, endi, endj, starti, startj, found, cf, cr);
-    else if (band <= 16) local_sweeps_reg<16>(P, read, M, win, N, low, up, best, endi, endj, starti, startj, found, cf, cr);
-    else if (band <= 24) local_sweeps_reg<24>(P, read, M, win, N, low, up, best, endi, endj, starti, startj, found, cf, cr);
-    else if (band <= 40) local_sweeps_reg<40>(P, read, M, win, N, low, up, best, endi, endj, starti, startj, found, cf, cr);
+    // the unrolled sweeps compute W diagonals whatever the band: pick the tightest instantiation
+#define IG_SWEEP(W) local_sweeps_reg<W>(P, read, M, win, N, low, up, best, endi, endj, starti, startj, found, cf, cr)
+    if (band <= 6)       IG_SWEEP(6);
+    else if (band <= 8)  IG_SWEEP(8);
+    else if (band <= 12) IG_SWEEP(12);
+    else if (band <= 16) IG_SWEEP(16);
+    else if (band <= 20) IG_SWEEP(20);
+    else if (band <= 24) IG_SWEEP(24);
+    else if (band <= 32) IG_SWEEP(32);
+    else if (band <= 40) IG_SWEEP(40);
+#undef IG_SWEEP
     else {
 #define AT(arr, t) ((arr)[(t) + 1])
     // forward (localalign.c:82-131)
