@@ -322,12 +322,10 @@ static int launch_pipeline(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_
     const int vblocks = (int)std::min<long long>((long long)c->sms * occ, std::max(1, (n + wpc - 1) / wpc));
 
     const int mb = 2 * max_band;
-    size_t dsmem = (size_t)128 * 4 * 4 * (size_t)(mb + 4);           // band work arrays of 128 threads
-    int bands_in_smem = 1;
-    if (dsmem > (size_t)72 * 1024) { dsmem = 0; bands_in_smem = 0; }
-    CU(cudaFuncSetAttribute(pipe_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+    // (no shared-memory carve-out preference: asking for the largest L1 made the driver pick a carve-out too
+    //  small for four resident CTAs and cost 30 %; the default leaves the L1-resident work arrays enough room)
     int docc = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&docc, pipe_dp_kernel, 128, dsmem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&docc, pipe_dp_kernel, 128, 0));
     if (docc < 1) return fail(INDELGPU_ELIMIT, "banded DP kernel does not fit on an SM");
     const int dblocks = (int)std::min<long long>((long long)c->sms * docc, (n + 127) / 128);
     const long long ints = band_scratch_ints(mb, max_read);
@@ -352,7 +350,7 @@ static int launch_pipeline(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_
     for (int round = 0; round < 2; round++) {
         vk<<<vblocks, wpc * 32, (size_t)wpc * L.total, st>>>(a, p, round);
         CU(cudaGetLastError());
-        pipe_dp_kernel<<<dblocks, 128, dsmem, st>>>(a, p, round, bands_in_smem);
+        pipe_dp_kernel<<<dblocks, 128, 0, st>>>(a, p, round);
         CU(cudaGetLastError());
     }
     pipe_combine_kernel<<<cblocks, cw * 32, (size_t)cw * cper, st>>>(a, p);
@@ -757,19 +755,15 @@ extern "C" int indelgpu_band_align_batch(indelgpu_ctx* c, int32_t n, const uint8
             a.cigar = c->t_cig.as<uint32_t>(); a.cigar_stride = need;
         }
         const int mb = 2 * max_band;
-        size_t smem = (size_t)128 * 4 * 4 * (size_t)(mb + 4);        // band work arrays of 128 threads
-        int bands_in_smem = 1;
-        if (smem > (size_t)72 * 1024) { smem = 0; bands_in_smem = 0; }
-        CU(cudaFuncSetAttribute(band_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, band_tasks_kernel, 128, smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, band_tasks_kernel, 128, 0));
         if (occ < 1) return fail(INDELGPU_ELIMIT, "band kernel does not fit on an SM");
         const int blocks = (int)std::min<long long>((long long)c->sms * occ, (n + 127) / 128);
         const long long ints = band_scratch_ints(mb, max_read);
         if (c->scratch.ensure((size_t)ints * 4 * 128 * (size_t)blocks)) return INDELGPU_ENOMEM;
         a.scratch.base = c->scratch.as<int>(); a.scratch.stride = ints; a.scratch.max_band = mb; a.scratch.max_rows = max_read;
         CU(cudaEventRecord(c->ev_t0, st));
-        band_tasks_kernel<<<blocks, 128, smem, st>>>(a, bands_in_smem);
+        band_tasks_kernel<<<blocks, 128, 0, st>>>(a);
         CU(cudaEventRecord(c->ev_t1, st));
         c->timed = true;
     } else {

@@ -126,15 +126,14 @@ __device__ __forceinline__ bool pipe_task(const RealignArgs& a, const PipeBufs& 
 // sweeps of local_align + the unique-diagonal shortcut for every read; the alignments that need ALIGN's
 // divide and conquer run it 32 at a time (banded_two_phase_loop; see band_tasks_kernel for why)
 __global__ void __launch_bounds__(128, BAND_MIN_BLOCKS)
-pipe_dp_kernel(const __grid_constant__ RealignArgs a, const PipeBufs p, const int round, const int bands_in_smem)
+pipe_dp_kernel(const __grid_constant__ RealignArgs a, const PipeBufs p, const int round)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
     __shared__ DcTask s_pend[4][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int wb4 = 4 * (a.scratch.max_band + 4);
     const IArr<32> gbase{a.scratch.base + (long long)gwarp * 32 * a.scratch.stride + lane};
-    const IArr<32> bands = bands_in_smem ? IArr<32>{reinterpret_cast<int*>(smem) + (size_t)warp * 32 * wb4 + lane} : gbase;
+    const IArr<32> bands = gbase;
     const IArr<32> rowsb = gbase + wb4;
     DcFrame st[kDcFrames];
 

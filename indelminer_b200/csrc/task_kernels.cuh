@@ -144,18 +144,17 @@ align_tasks_kernel(const __grid_constant__ TaskArgs a)
 // Every lane first runs the two sweeps of local_align (registers for bands <= 40) and the
 // unique-diagonal shortcut; the few tasks that really need ALIGN's divide and conquer wait in a per-warp
 // buffer until 32 of them can run it together (banded_two_phase_loop) on lane-interleaved scratch
-// (IArr<32>: one 128-byte line per access).  Doing both in one pass per task would make every warp wait
+// (IArr<32>: one 128-byte line per access, L1-resident).  Doing both in one pass per task would make every warp wait
 // for its two or three gapped alignments at 10 % lane utilisation.
 __global__ void __launch_bounds__(128, BAND_MIN_BLOCKS)
-band_tasks_kernel(const __grid_constant__ TaskArgs a, const int bands_in_smem)
+band_tasks_kernel(const __grid_constant__ TaskArgs a)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
     __shared__ DcTask s_pend[4][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int wb4 = 4 * (a.scratch.max_band + 4);
     const IArr<32> gbase{a.scratch.base + (long long)gwarp * 32 * a.scratch.stride + lane};
-    const IArr<32> bands = bands_in_smem ? IArr<32>{reinterpret_cast<int*>(smem) + (size_t)warp * 32 * wb4 + lane} : gbase;
+    const IArr<32> bands = gbase;            // L1-resident; shared memory measured slower (it costs resident warps)
     const IArr<32> rowsb = gbase + wb4;
     unsigned long long cf = 0, cr = 0, cg = 0;
     DcFrame st[kDcFrames];
