@@ -195,6 +195,114 @@ IG_HD inline void dc_sweep(DcCtx<STRIDE>& x, DcFrame& f)
     f.t2 = up - rmid - 1; f.t3 = low - rmid + 1;
 }
 
+// dc_sweep for bands of at most W2 diagonals with the four band-wide arrays (CC, DD, CP, DP) in
+// registers and the loop over the band unrolled.  One cell body serves every diagonal: the first cell
+// of a row (globalalign.c:150-166) is the general cell with the horizontal inputs at -infinity (then
+// e and IP come out of the next cell's "open" branch with exactly the values the reference's separate
+// first-cell code assigns), and the mid-diagonal cell (:189-232) is the general cell plus its
+// crossing records.  Cells outside [leftd, rightd] leave every register untouched.
+template <int W2, int STRIDE>
+IG_HD inline void dc_sweep_reg(DcCtx<STRIDE>& x, DcFrame& f)
+{
+    const int g = x.P->G, h = x.P->H, m = g + h;
+    const uint8_t* a1 = x.A + f.a - 1;
+    const uint8_t* b1 = x.B + f.b - 1;
+    const int M = f.M, N = f.N, low = f.low, up = f.up, tb = f.tb, te = f.te;
+    const int band = up - low + 1;
+    const int midd = band / 2 + 1;
+    const int rmid = low + midd - 1;
+    int leftd = 1 - low, rightd = band;
+    int CC[W2 + 2], DD[W2 + 2], CP[W2 + 2], DP[W2 + 2];
+    int IP = 0;
+    {
+        const int fr = leftd - midd;
+        const int t0 = (tb == 2) ? 0 : -g;
+#pragma unroll
+        for (int j = 0; j <= W2 + 1; j++) {
+            int p;
+            if (leftd < midd)      p = (j < midd) ? -1 : 0;
+            else if (leftd > midd) p = (j <= midd) ? fr : -1;
+            else                   p = 0;
+            CP[j] = DP[j] = p;
+            int cc = kNeg, dd = kNeg;
+            if (j == leftd) { cc = 0; dd = (tb == 1) ? 0 : -g; }
+            else if (j > leftd && j <= rightd) { cc = t0 - h * (j - leftd); dd = cc - g; }
+            CC[j] = cc; DD[j] = dd;
+        }
+        if (leftd < midd || leftd == midd) x.mp[0][0] = x.mp[1][0] = x.mp[2][0] = -1;
+        else x.mp[0][fr] = x.mp[1][fr] = x.mp[2][fr] = -1;
+    }
+    int c = 0, d = 0, e = 0;                                     // values of the last cell of the last row
+    for (int i = 1; i <= M; i++) {
+        if (i > N - up) rightd--;
+        if (leftd > 1) leftd--;
+        const uint8_t ai = a1[i];
+        x.cells += rightd - leftd + 1;
+        int cl = kNeg, el = kNeg;                                // horizontal inputs of the row's first cell
+#pragma unroll
+        for (int q = 1; q <= W2; q++) {
+            if (q >= leftd && q <= rightd) {
+                const bool first = q == leftd;
+                const int ib = q + low - 1 + i;
+                // horizontal
+                int openh = cl - m, en = el - h;
+                const bool eopen = openh > en;
+                if (eopen) en = openh;
+                const int ipn = eopen ? CP[q - 1] : IP;          // pointer of the best path ending in an insert here
+                // vertical
+                const int openv = CC[q + 1] - m;
+                int dn = DD[q + 1] - h;
+                const bool dopen = openv > dn;
+                if (dopen) dn = openv;
+                const int dpn = dopen ? CP[q + 1] : DP[q + 1];
+                // diagonal (column 0 and below has none: CC[q] is -infinity there)
+                int cn = CC[q] + ((ib > 0 && ai == b1[ib > 0 ? ib : 1]) ? x.P->match : x.P->mismatch);
+                if (ib <= 0) cn = kNeg;
+                int cpn = CP[q], kind = 0;                       // 0 diagonal, 1 came from d, 2 came from e
+                if (cn < dn || cn < en) {
+                    if (en > dn) { cn = en; cpn = ipn; kind = 2; }
+                    else         { cn = dn; cpn = dpn; kind = 1; }
+                }
+                if (!first && q == midd) {                       // crossing records (:189-232)
+                    int mp1 = ipn, mt1 = 2, mp2 = dpn, mt2 = 1, mp0, mt0;
+                    if (kind == 2)      { mp0 = mp1; mt0 = 2; }
+                    else if (kind == 1) { mp0 = mp2; mt0 = 1; }
+                    else                { mp0 = i - 1; mt0 = 0; }
+                    if (cn - g > en) { mp1 = mp0; mt1 = mt0; }
+                    if (cn - g > dn) { mp2 = mp0; mt2 = mt0; }
+                    x.mp[0][i] = mp0; x.mt[0][i] = mt0;
+                    x.mp[1][i] = mp1; x.mt[1][i] = mt1;
+                    x.mp[2][i] = mp2; x.mt[2][i] = mt2;
+                }
+                IP = first ? cpn : ipn;                          // :164 IP = CP[leftd] ; else the carried insert pointer
+                if (q == midd) { cpn = i; IP = i; DP[q] = i; } else DP[q] = dpn;
+                CP[q] = cpn; CC[q] = cn; DD[q] = dn;
+                cl = cn; el = first ? cn - g : en;               // :162 e = c - g after the first cell
+                c = cn; d = dn; e = el;
+            }
+        }
+    }
+    int k, l;
+    int dpr = DP[1], cpr = CP[1];
+#pragma unroll
+    for (int q = 2; q <= W2; q++) if (q == rightd) { dpr = DP[q]; cpr = CP[q]; }
+    if (te == 1 && d + g > c)      { k = dpr; l = 2; }
+    else if (te == 2 && e + g > c) { k = IP;  l = 1; }
+    else                           { k = cpr; l = 0; }
+    if (rmid > N - M) l = 2; else if (rmid < N - M) l = 1;
+    int r = -1;
+    while (k > -1) {
+        x.fp[k] = r; x.ft[k] = l;
+        r = k;
+        const int nk = x.mp[l][r], nl = x.mt[l][r];
+        k = nk; l = nl;
+    }
+    f.rmid = rmid;
+    f.k = r;
+    if (r != -1) { f.l = x.fp[r]; f.kt = x.ft[r]; }
+    f.t2 = up - rmid - 1; f.t3 = low - rmid + 1;
+}
+
 IG_HD inline void dc_push(DcFrame* st, int& sp, int a, int b, int M, int N,
                                         int low, int up, int tb, int te)
 {
@@ -215,7 +323,12 @@ IG_HD inline void dc_align(DcCtx<STRIDE>& x, DcFrame* st, int a0, int b0, int M0
             if (f.N <= 0) { if (f.M > 0) put_del(x, f.M); sp--; break; }
             if (f.M <= 0) { put_ins(x, f.N); sp--; break; }
             if (f.up - f.low + 1 <= 1) { for (int i = 0; i < f.M; i++) put_rep(x); sp--; break; }
-            dc_sweep(x, f);
+            {
+                const int bw = f.up - f.low + 1;
+                if (bw <= 12)      dc_sweep_reg<12>(x, f);
+                else if (bw <= 20) dc_sweep_reg<20>(x, f);
+                else               dc_sweep(x, f);
+            }
             const int r = f.k, rmid = f.rmid;
             if (r == -1) {                                   // :260-262
                 f.stage = 6;
