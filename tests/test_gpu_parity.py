@@ -403,3 +403,27 @@ def test_long_reads_use_the_wide_counter_path(gpu, oracle, k, g):
         seen.add(int(o.status))
     assert 6 in seen
     R.close()
+
+
+def test_synthetic_cfg3_batch_exact_vs_oracle(gpu, oracle):
+    """20 000 candidates of the benchmark's own generator (deletions, insertions, clean, chimeric, all
+    anchored by a mate position), every read compared with the oracle: status, start, segment words"""
+    from indelminer_b200 import synth
+    ref = synth.make_reference(3_000_000, seed=1, n_frac=0.0005)
+    w = synth.make_candidates(ref, 20000, seed=99)
+    R = gpu.Realigner()
+    R.set_reference([ref.tobytes()])
+    res = R.attempt_pe_alignment_batch(None, w["tid"], w["position"], w["range1"],
+                                       packed=(w["read_bases"], w["read_off"]))
+    p = oracle.default_params()
+    cs = ref.tobytes()
+    M = w["read_len"]
+    hist = {}
+    for i in range(20000):
+        o = oracle.realign_read(p, cs, int(w["position"][i]), int(w["range1"][i]),
+                                w["read_bases"][i * M:(i + 1) * M].tobytes())
+        assert int(res.status[i]) == o.status, i
+        assert res.segments(i) == o.segments(), i
+        hist[o.status] = hist.get(o.status, 0) + 1
+    assert hist.get(6, 0) > 5000 and hist.get(1, 0) > 200
+    R.close()
