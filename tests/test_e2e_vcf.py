@@ -51,3 +51,27 @@ def test_vcf_vs_upstream_expected_differs_only_in_the_known_token():
     assert len(diff) <= 1
     for a, b in diff:
         assert a.replace("BF=52,48", "BF=48,52") == b
+
+
+@pytest.mark.parametrize("flags,golden", [([], "testdata_refrun.vcf"), (["-g", "4"], "testdata_refrun_g4.vcf")])
+def test_record_replay_batched_mode_prints_the_same_vcf(tmp_path, flags, golden):
+    """the batched integration with an UNCHANGED caller (host/indelgpu_attempt.c): run 1 records every
+    attempt_pe_alignment call and realigns them with one indelgpu_realign_batch per contig at exit,
+    run 2 replays the results in call order and prints the VCF"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if not os.path.exists(PROG):
+        pytest.skip("oracle/_ref/indelminer_gpu not built")
+    from indelminer_b200 import build
+    build.build()
+    env = dict(os.environ, INDELGPU_REPLAY_FILE=str(tmp_path / "replay.bin"))
+    cmd = [PROG] + flags + ["-i", "indelminer.config", "testdata_reference.fa", "sample=alignments.bam"]
+    r1 = subprocess.run(cmd, cwd=GOLD, capture_output=True, text=True, timeout=600, env=dict(env, INDELGPU_MODE="record"))
+    assert r1.returncode == 0, r1.stderr[-2000:]
+    assert "697 candidate reads realigned in batches" in r1.stderr
+    r2 = subprocess.run(cmd, cwd=GOLD, capture_output=True, text=True, timeout=600, env=dict(env, INDELGPU_MODE="replay"))
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    with open(os.path.join(GOLD, golden)) as f:
+        assert r2.stdout == f.read()
+    assert r1.stdout != r2.stdout          # the recording run answered NULL everywhere: its VCF is not the result
