@@ -67,81 +67,90 @@ def make_dataset(path_prefix, length=1_000_000, depth=20, read_len=150, insert_m
     npairs = int(depth * length / (2 * M))
     fstart = rng.integers(0, S - 1000, size=npairs)
     isz = np.clip(rng.normal(insert_mean, insert_sd, size=npairs), 2 * M + 10, insert_mean + 4 * insert_sd).astype(np.int64)
-    records = []          # (sortpos, line)
+    keep = fstart + isz < S
+    fstart, isz = fstart[keep], isz[keep]
+    npairs = len(fstart)
+    first_left = rng.random(npairs) < 0.5
+    records = []          # (sortpos, serial, line)
     nrec = 0
-    for k in range(npairs):
-        f, ins = int(fstart[k]), int(isz[k])
-        if f + ins >= S:
-            continue
-        name = f"p{k}"
-        ends = []
-        for which, s in ((0, f), (1, f + ins - M)):
-            bases = samp[s:s + M].copy()
-            sub = rng.random(M) < sub_rate
-            if sub.any():
-                bases[sub] = acgt[rng.integers(0, 4, size=int(sub.sum()))]
-            rc = rcmap[s:s + M]
-            pos0, ops = _cigar_from_refcoords(rc)
-            ends.append(dict(which=which, bases=bases.tobytes(), pos0=pos0, ops=ops, rev=(which == 1)))
-        first_is_left = rng.random() < 0.5
-        # representation of reads that touch an indel
-        for e in ends:
-            e["unmapped"] = e["ops"] is None
-            if e["unmapped"]:
+    qual = "I" * M
+    cols = np.arange(M, dtype=np.int64)[None, :]
+    for c0 in range(0, npairs, 50000):                      # chunks keep the [pairs, M] arrays small
+        c1 = min(npairs, c0 + 50000)
+        starts = np.stack([fstart[c0:c1], fstart[c0:c1] + isz[c0:c1] - M], axis=1)        # [m, 2] sample offsets
+        idx = starts[:, :, None] + cols[None, :, :]                                          # [m, 2, M]
+        bases = samp[idx]
+        sub = rng.random(bases.shape) < sub_rate
+        bases = np.where(sub, acgt[rng.integers(0, 4, size=bases.shape)], bases)
+        rc_first, rc_last = rcmap[starts], rcmap[starts + M - 1]
+        clean = (rc_first >= 0) & (rc_last - rc_first == M - 1)                              # no indel inside the read
+        for r in range(c1 - c0):
+            k = c0 + r
+            name = f"p{k}"
+            ends = []
+            for which in (0, 1):
+                if clean[r, which]:
+                    ends.append(dict(which=which, bases=bases[r, which].tobytes(), pos0=int(rc_first[r, which]),
+                                     ops=[(M, "M")], rev=(which == 1), unmapped=False))
+                    continue
+                s0 = int(starts[r, which])
+                pos0, ops = _cigar_from_refcoords(rcmap[s0:s0 + M])
+                e = dict(which=which, bases=bases[r, which].tobytes(), pos0=pos0, ops=ops, rev=(which == 1),
+                         unmapped=ops is None)
+                if not e["unmapped"]:
+                    # inserted bases at a read end are what an aligner soft-clips
+                    if ops[0][1] == "I":
+                        ops[0] = (ops[0][0], "S")
+                    if ops[-1][1] == "I":
+                        ops[-1] = (ops[-1][0], "S")
+                    if any(o in "ID" for _n, o in ops):
+                        u = rng.random()
+                        if u < 0.4:
+                            pass                                   # the aligner found the indel
+                        elif u < 0.8:                              # soft clip at the (first) indel, keeping the longer side
+                            i0 = next(i for i, (_n, o) in enumerate(ops) if o in "ID")
+                            left = sum(n for n, o in ops[:i0] if o in "MIS")
+                            right = sum(n for n, o in ops[i0 + 1:] if o in "MIS") + (ops[i0][0] if ops[i0][1] == "I" else 0)
+                            if left >= right:
+                                e["ops"] = ops[:i0] + [(M - left, "S")]
+                            else:
+                                consumed_ref = sum(n for n, o in ops[:i0 + 1] if o in "MD")
+                                kept = ops[i0 + 1:]
+                                e["pos0"] = e["pos0"] + consumed_ref
+                                e["ops"] = [(M - sum(n for n, o in kept if o in "MIS"), "S")] + kept
+                        else:
+                            e["unmapped"] = True
+                ends.append(e)
+            a, b = ends
+            if a["unmapped"] and b["unmapped"]:
                 continue
-            ops = e["ops"]
-            # inserted bases at a read end are what an aligner soft-clips
-            if ops[0][1] == "I":
-                ops[0] = (ops[0][0], "S")
-            if ops[-1][1] == "I":
-                ops[-1] = (ops[-1][0], "S")
-            if any(o in "ID" for _n, o in ops):
-                u = rng.random()
-                if u < 0.4:
-                    pass                                   # the aligner found the indel
-                elif u < 0.8:                              # soft clip at the (first) indel, keeping the longer side
-                    idx = next(i for i, (_n, o) in enumerate(ops) if o in "ID")
-                    left = sum(n for n, o in ops[:idx] if o in "MIS")
-                    right = sum(n for n, o in ops[idx + 1:] if o in "MIS") + (ops[idx][0] if ops[idx][1] == "I" else 0)
-                    if left >= right:
-                        e["ops"] = ops[:idx] + [(M - left, "S")]
-                    else:
-                        consumed_ref = sum(n for n, o in ops[:idx + 1] if o in "MD")
-                        keep = ops[idx + 1:]
-                        e["pos0"] = e["pos0"] + consumed_ref
-                        e["ops"] = [(M - sum(n for n, o in keep if o in "MIS"), "S")] + keep
+            for e, mate in ((a, b), (b, a)):
+                flag = 0x1 | (0x40 if (e["which"] == 0) == bool(first_left[k]) else 0x80)
+                if e["rev"]:
+                    flag |= 0x10
+                if mate["rev"]:
+                    flag |= 0x20
+                if e["unmapped"]:
+                    flag |= 0x4
+                if mate["unmapped"]:
+                    flag |= 0x8
+                if not e["unmapped"] and not mate["unmapped"]:
+                    flag |= 0x2
+                if e["unmapped"]:
+                    pos, cigar, mapq = mate["pos0"], "*", 0
                 else:
-                    e["unmapped"] = True
-        a, b = ends
-        if a["unmapped"] and b["unmapped"]:
-            continue
-        for e, mate in ((a, b), (b, a)):
-            flag = 0x1 | (0x40 if (e["which"] == 0) == first_is_left else 0x80)
-            if e["rev"]:
-                flag |= 0x10
-            if mate["rev"]:
-                flag |= 0x20
-            if e["unmapped"]:
-                flag |= 0x4
-            if mate["unmapped"]:
-                flag |= 0x8
-            if not e["unmapped"] and not mate["unmapped"]:
-                flag |= 0x2
-            if e["unmapped"]:
-                pos, cigar, mapq = mate["pos0"], "*", 0
-            else:
-                pos, cigar, mapq = e["pos0"], "".join(f"{n}{o}" for n, o in e["ops"]), 60
-            pnext = mate["pos0"] if not mate["unmapped"] else pos
-            tlen = 0
-            if not e["unmapped"] and not mate["unmapped"]:
-                def ref_end(x):
-                    return x["pos0"] + sum(n for n, o in x["ops"] if o in "MD")
-                lo = min(e["pos0"], mate["pos0"]); hi = max(ref_end(e), ref_end(mate))
-                tlen = (hi - lo) if e["pos0"] <= mate["pos0"] else -(hi - lo)
-            seq = e["bases"].decode()
-            line = (f"{name}\t{flag}\t{contig}\t{pos + 1}\t{mapq}\t{cigar}\t=\t{pnext + 1}\t{tlen}\t{seq}\t{'I' * M}\tMQ:i:60")
-            records.append((pos, nrec, line))
-            nrec += 1
+                    pos, cigar, mapq = e["pos0"], "".join(f"{n}{o}" for n, o in e["ops"]), 60
+                pnext = mate["pos0"] if not mate["unmapped"] else pos
+                tlen = 0
+                if not e["unmapped"] and not mate["unmapped"]:
+                    e_end = e["pos0"] + sum(n for n, o in e["ops"] if o in "MD")
+                    m_end = mate["pos0"] + sum(n for n, o in mate["ops"] if o in "MD")
+                    lo = min(e["pos0"], mate["pos0"]); hi = max(e_end, m_end)
+                    tlen = (hi - lo) if e["pos0"] <= mate["pos0"] else -(hi - lo)
+                line = (f"{name}\t{flag}\t{contig}\t{pos + 1}\t{mapq}\t{cigar}\t=\t{pnext + 1}\t{tlen}\t"
+                        f"{e['bases'].decode()}\t{qual}\tMQ:i:60")
+                records.append((pos, nrec, line))
+                nrec += 1
     records.sort()
     with open(path_prefix + ".fa", "w") as f:
         f.write(f">{contig}\n")

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--length", type=int, default=4_000_000)
     ap.add_argument("--depth", type=int, default=20)
     ap.add_argument("--per-read", action="store_true", help="also time the per-read glue mode")
+    ap.add_argument("--only-default", action="store_true", help="default flags only (skip -g 4)")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     from tests.synth_bam import make_dataset
@@ -41,7 +42,7 @@ def main():
         subprocess.check_call([os.path.join(REFDIR, "sam2bam"), "d.sam", "d.bam"], cwd=d, stderr=subprocess.DEVNULL)
         t_gen = time.perf_counter() - t0
         res = dict(dataset=dict(length=a.length, depth=a.depth, **info), generate_s=t_gen, runs=[])
-        for flags in ([], ["-g", "4"]):
+        for flags in ([[]] if a.only_default else [[], ["-g", "4"]]):
             ref_vcf, t_ref, _ = run("indelminer_ref", d, flags)
             env = dict(INDELGPU_REPLAY_FILE=os.path.join(d, "replay.bin"))
             _v, t_rec, err = run("indelminer_gpu", d, flags, dict(env, INDELGPU_MODE="record"))
