@@ -27,9 +27,16 @@
  * Both process one read per call (a 1-element batch) unless INDELGPU_MODE selects the batched
  * record / replay operation described further down (and in INTEGRATION.md).
  */
+#define _GNU_SOURCE
+#include <dirent.h>
+#include <fcntl.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 #include "alignment.h"      /* the reference's header: evidence, readaln, constants */
 #include "slinklist.h"
@@ -143,7 +150,11 @@ static evidence* consume_segments(readaln* const rln, const char* read, const in
  *                         exit the queue is realigned contig by contig with ONE indelgpu_realign_batch
  *                         each and the results are written to $INDELGPU_REPLAY_FILE;
  *   INDELGPU_MODE=replay  every call is answered from that file, in order.
- * The second run prints the VCF; the GPU sees whole-contig batches instead of one read at a time. */
+ * The second run prints the VCF; the GPU sees whole-contig batches instead of one read at a time.
+ *   INDELGPU_MODE=auto    both in ONE run: at the first call the process forks; the child is the recording
+ *                         run (stdout discarded), the parent waits for it and continues as the replay run.
+ *                         Parent and child share the offsets of the open files (the BAM), so the parent
+ *                         puts every regular file's offset back where it was before it goes on. */
 enum { MODE_DIRECT = 0, MODE_RECORD = 1, MODE_REPLAY = 2 };
 static int g_mode = -1;
 
@@ -221,6 +232,7 @@ static void flush_recorded(void)
     fprintf(stderr, "libindelgpu: %lld candidate reads realigned in batches, results in %s\n", (long long)g_ncands, replay_path());
 }
 
+static char g_auto_path[64] = "";    /* temporary replay file of INDELGPU_MODE=auto */
 static int32_t* g_replay = NULL;     /* the whole replay file after its header, as 32-bit words */
 static int64_t g_replay_words = 0, g_replay_pos = 0, g_replay_left = 0;
 
@@ -238,6 +250,44 @@ static void load_replay(void)
     g_replay_words = bytes / 4;
     if (bytes > 0 && fread(g_replay, 1, (size_t)bytes, f) != (size_t)bytes) fatalf("libindelgpu: short read on %s", replay_path());
     fclose(f);
+    if (g_auto_path[0] != '\0') unlink(g_auto_path);     /* the temporary file of INDELGPU_MODE=auto */
+}
+
+/* INDELGPU_MODE=auto: fork the recording run; returns the mode this process continues in */
+
+static int fork_recording_run(void)
+{
+    /* offsets of every open regular file: the child will move them */
+    enum { MAXFD = 256 };
+    int fds[MAXFD]; off_t offs[MAXFD]; int nfd = 0;
+    DIR* d = opendir("/proc/self/fd");
+    if (d != NULL) {
+        for (struct dirent* e; (e = readdir(d)) != NULL && nfd < MAXFD;) {
+            const int fd = atoi(e->d_name);
+            struct stat st;
+            if (e->d_name[0] < '0' || e->d_name[0] > '9' || fd == dirfd(d)) continue;
+            if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) continue;
+            fds[nfd] = fd; offs[nfd] = lseek(fd, 0, SEEK_CUR); nfd++;
+        }
+        closedir(d);
+    }
+    if (getenv("INDELGPU_REPLAY_FILE") == NULL) {
+        snprintf(g_auto_path, sizeof(g_auto_path), "/tmp/indelgpu_replay_%d.bin", (int)getpid());
+        setenv("INDELGPU_REPLAY_FILE", g_auto_path, 1);
+    }
+    fflush(stdout); fflush(stderr);
+    const pid_t pid = fork();
+    if (pid < 0) fatalf("libindelgpu: fork failed");
+    if (pid == 0) {                                      /* child: the recording run, its VCF goes nowhere */
+        const int nul = open("/dev/null", O_WRONLY);
+        if (nul >= 0) { dup2(nul, STDOUT_FILENO); close(nul); }
+        return MODE_RECORD;
+    }
+    int status = 0;
+    if (waitpid(pid, &status, 0) != pid || !WIFEXITED(status) || WEXITSTATUS(status) != 0)
+        fatalf("libindelgpu: the recording run failed (status %d)", status);
+    for (int i = 0; i < nfd; i++) if (offs[i] != (off_t)-1) lseek(fds[i], offs[i], SEEK_SET);
+    return MODE_REPLAY;
 }
 
 evidence* attempt_pe_alignment(char** const sequences,
@@ -253,6 +303,7 @@ evidence* attempt_pe_alignment(char** const sequences,
     if (g_mode < 0) {
         const char* m = getenv("INDELGPU_MODE");
         g_mode = (m && strcmp(m, "record") == 0) ? MODE_RECORD : (m && strcmp(m, "replay") == 0) ? MODE_REPLAY : MODE_DIRECT;
+        if (m && strcmp(m, "auto") == 0) g_mode = fork_recording_run();
         if (g_mode == MODE_REPLAY) load_replay();
     }
 

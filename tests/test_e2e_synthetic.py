@@ -56,8 +56,10 @@ def test_synthetic_vcf_identical(dataset, flags):
     assert batched_vcf == ref_vcf
     direct_vcf, t_dir = run("indelminer_gpu", dataset, flags)
     assert direct_vcf == ref_vcf
+    auto_vcf, t_auto = run("indelminer_gpu", dataset, flags, dict(INDELGPU_MODE="auto"))
+    assert auto_vcf == ref_vcf
     out = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out):
         with open(os.path.join(out, "e2e_synthetic.json"), "a") as f:
             f.write(json.dumps(dict(flags=flags, dataset=dataset["info"], variants=len(body),
-                                    wall_s=dict(reference=t_ref, gpu_record=t_rec, gpu_replay=t_rep, gpu_per_read=t_dir))) + "\n")
+                                    wall_s=dict(reference=t_ref, gpu_record=t_rec, gpu_replay=t_rep, gpu_per_read=t_dir, gpu_auto=t_auto))) + "\n")

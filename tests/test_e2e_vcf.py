@@ -75,3 +75,22 @@ def test_record_replay_batched_mode_prints_the_same_vcf(tmp_path, flags, golden)
     with open(os.path.join(GOLD, golden)) as f:
         assert r2.stdout == f.read()
     assert r1.stdout != r2.stdout          # the recording run answered NULL everywhere: its VCF is not the result
+
+
+@pytest.mark.parametrize("flags,golden", [([], "testdata_refrun.vcf"), (["-g", "16"], "testdata_refrun_g16.vcf")])
+def test_auto_mode_single_run_batched(flags, golden):
+    """INDELGPU_MODE=auto: one command; the process forks its own recording run at the first call and
+    continues as the replay run (file offsets of the open BAM restored)"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if not os.path.exists(PROG):
+        pytest.skip("oracle/_ref/indelminer_gpu not built")
+    from indelminer_b200 import build
+    build.build()
+    cmd = [PROG] + flags + ["-i", "indelminer.config", "testdata_reference.fa", "sample=alignments.bam"]
+    r = subprocess.run(cmd, cwd=GOLD, capture_output=True, text=True, timeout=600, env=dict(os.environ, INDELGPU_MODE="auto"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "697 candidate reads realigned in batches" in r.stderr
+    with open(os.path.join(GOLD, golden)) as f:
+        assert r.stdout == f.read()
