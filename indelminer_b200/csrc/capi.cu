@@ -372,7 +372,8 @@ static int launch_realign(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_r
     const int max_numdiag = (int)nd;
     const bool banded = c->P.g > 0;
     // the banded pipeline only votes with this layout (its CIGARs live in HBM), so it takes the compact form too
-    const WarpLayout L = make_warp_layout(c->P, max_read, max_numdiag, 0);
+    const long long vd = std::max(2LL * max_range1, (long long)max_range1 + c->P.maxdel) + max_read + 2;
+    const WarpLayout L = make_warp_layout(c->P, max_read, max_numdiag, (int)vd, 0);
     if (((uintptr_t)d_in->read_bases & 15) != 0) return fail(INDELGPU_EINVAL, "read_bases must be 16-byte aligned on the device (TMA bulk copies)");
     if (banded) return launch_pipeline(c, d_in, max_read, max_numdiag, L, d_out, d_seg_count, st, keep_totals);
     void (*kern)(RealignArgs);
@@ -669,7 +670,7 @@ extern "C" int indelgpu_find_best_band_batch(indelgpu_ctx* c, int32_t n, const u
     if (pack_device(c, c->t_refs.as<uint8_t>(), c->t_packed.as<uint32_t>(), words)) return INDELGPU_ECUDA;
 
     const int max_numdiag = max_win + max_read + 4;
-    const WarpLayout L = make_warp_layout(c->P, max_read, max_numdiag, 0);
+    const WarpLayout L = make_warp_layout(c->P, max_read, max_numdiag, max_numdiag, 0);
     void (*vkern)(TaskArgs);
     if (L.hist_bits == 8) vkern = L.direct ? vote_tasks_kernel<true, 8> : vote_tasks_kernel<false, 8>;
     else                  vkern = L.direct ? vote_tasks_kernel<true, 16> : vote_tasks_kernel<false, 16>;

@@ -17,6 +17,7 @@ struct WarpLayout {
     int hash_slots;      // power of two (hash only)
     int hist_bits;       // 8 or 16 bits per diagonal counter
     int hist_words;      // uint32 words of the histogram (multiple of 4)
+    int hist_cap;        // diagonals the histogram can hold
     int win_bytes;       // bytes of one staged packed window (multiple of 16)
     int read_bytes;      // bytes of one staged read (multiple of 16, includes 16 bytes of misalignment)
     int pk_words;        // packed read words
@@ -38,7 +39,10 @@ __host__ __device__ inline int cigar_cap(const DevParams& P, int max_read, int b
     return max_read + 4;
 }
 
-__host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int max_read, int max_numdiag, int banded)
+// max_numdiag bounds the STAGED window (window 2, alignment.c:780-783) plus the read; max_votediag bounds
+// the diagonals one vote can address.  The two differ: round 1 votes on window 1 (2 * range1 bases) and
+// every round-2 window lies on one side of the anchor (alignment.c:606-706: at most range1 + maxdelsize).
+__host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int max_read, int max_numdiag, int max_votediag, int banded)
 {
     WarpLayout L;
     L.direct = P.k <= 6;
@@ -46,9 +50,10 @@ __host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int m
     #pragma unroll 1
     while (hs < 4 * max_read) hs <<= 1;
     L.hash_slots = L.direct ? 0 : hs;
-    L.hist_bits = (max_read - P.k + 1 <= 255 && max_numdiag <= 65535) ? 8 : 16;
+    L.hist_bits = (max_read - P.k + 1 <= 255 && max_votediag <= 65535) ? 8 : 16;
+    L.hist_cap = max_votediag;
     const int tab_bytes = L.direct ? ((L.hist_bits / 8) << (2 * P.k)) : hs * 8;
-    L.hist_words = round_up((max_numdiag + 4) * (L.hist_bits / 8), 16) / 4;
+    L.hist_words = round_up((max_votediag + 4) * (L.hist_bits / 8), 16) / 4;
     L.win_bytes = round_up(max_numdiag / 4 + 64, 16);             // window <= max_numdiag bases, 64-base aligned start, hi word
     L.read_bytes = round_up(max_read + 32, 16);
     L.pk_words = max_read / 16 + 3;
@@ -61,14 +66,19 @@ __host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int m
     L.off_read0 = o; o += L.read_bytes;
     L.off_read1 = o; o += L.read_bytes;
     L.off_pk = o;    o += round_up(L.pk_words * 4, 16);
-    L.off_psum = o;  o += round_up((max_read + 2) * 4, 16);
-    L.off_bits = o;  o += round_up(((max_read + 127) / 128 * 4 + 4) * 4, 16);
     L.off_cig1 = o;  o += round_up(L.ops_cap * 4, 16);
     L.off_cig2 = o;  o += round_up(L.ops_cap * 4, 16);
     L.off_segs = o;  o += round_up((2 * L.ops_cap + 4) * 4, 16);
     L.off_bar = o;   o += 16;                                      // two mbarriers
     L.off_misc = o;  o += 256;                                     // Aln x 2, Plan, scalars
-    L.off_list = o;  o += round_up((32 + 512 + 32) * (L.hist_bits == 8 ? 2 : 4), 16);   // hit list (kHitListCap entries)
+    // the vote's hit list and the alignment's prefix sums / match bits are never live together: one region
+    {
+        const int list_bytes = round_up((32 + 512 + 32) * (L.hist_bits == 8 ? 2 : 4), 16);       // kHitListCap entries
+        const int psum_bytes = round_up((max_read + 2) * 4, 16);
+        const int bits_bytes = round_up(((max_read + 127) / 128 * 4 + 4) * 4, 16);
+        L.off_list = o; L.off_psum = o; L.off_bits = o + psum_bytes;
+        o += list_bytes > psum_bytes + bits_bytes ? list_bytes : psum_bytes + bits_bytes;
+    }
     L.total = round_up(o, 128);
     return L;
 }
@@ -247,8 +257,8 @@ __device__ __forceinline__ int vote_band_warp(const DevParams& P, WarpView& V, c
     const int lane = threadIdx.x & 31;
     const int k = P.k, g = P.g;
     const int numdiag = (N - (k - 1)) + (M - (k - 1));            // alignment.c:403-404
-    *ok = numdiag > g;
-    if (!*ok) return 0;
+    *ok = numdiag > g && numdiag <= V.L.hist_cap;                 // the second clause is this kernel's limit (never hit for
+    if (!*ok) return 0;                                           // windows derived from a batch entry; see make_warp_layout)
     if (M < k) return numdiag - 1;                                // alignment.c:408-412
     const uint32_t kmask = P.kmask;
     const int nk = M - k + 1;
