@@ -235,12 +235,16 @@ __device__ __forceinline__ void stage_read(const RealignArgs& a, WarpView& V, co
 
 constexpr int kWorkChunk = 8;
 
+#ifndef REALIGN_MIN_BLOCKS
+#define REALIGN_MIN_BLOCKS 3      // caps the kernel at 85 registers so that three CTAs of 7 warps fit an SM
+#endif
+
 // The -g 0 kernel.  DIRECT: direct-address k-mer table (k <= 6); HB: bits per histogram counter and
 // table entry (8 when a slice has at most 255 k-mers).
 // The two rounds are ONE loop body so that the vote and the alignment exist once in the instruction
 // stream: warps of a CTA are in different phases and the kernel has to stay instruction-cache friendly.
 template <bool DIRECT, int HB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, REALIGN_MIN_BLOCKS)
 realign_kernel(const __grid_constant__ RealignArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
