@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "band"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "band", "support"])
     ap.add_argument("--reads", type=int, default=1 << 20, help="candidate reads per GPU per step")
     ap.add_argument("--ref-mb", type=int, default=64, help="contig size in Mb")
     ap.add_argument("--band", type=int, default=33)
@@ -239,6 +239,8 @@ def run_ours(a, rank, world, local_rank):
 
     if a.workload == "band":
         return run_band(a, R, L, torch, dev, peak, peak_src)
+    if a.workload == "support":
+        return run_support(a, R, L, torch)
 
     # region sharding: rank r owns the r-th slice of the contig (weak scaling: same count per GPU)
     Lr = len(ref)
@@ -426,6 +428,60 @@ def run_band(a, R, L, torch, dev, peak, peak_src):
                          "frac": gcups * INT_OPS_PER_CELL / gops.value if gops.value else None,
                          "int_ops_per_cell": INT_OPS_PER_CELL,
                          "peak_source": "measured here: indelgpu_int32_peak (independent add + max chains)"}}
+    print(json.dumps(line), flush=True)
+
+
+SUPPORT_OPS_PER_CELL = 26      # integer instructions per DP cell of the wavefront kernel (SASS count)
+
+
+def run_support(a, R, L, torch):
+    """Row f1: the known-indel support check, realign_with_indel (variant.c:1246-1424), on
+    --tasks (target, query) pairs; GCUPS of the kernel (CUDA events inside the library) against the INT32
+    issue rate measured here, and the oracle's C port timed on a sample of the same pairs."""
+    from indelminer_b200 import synth
+    t = synth.make_support_tasks(a.tasks)
+    packed = (t["targets"], t["target_off"], t["queries"], t["query_off"])
+    gops = C.c_double(0)
+    if L.indelgpu_int32_peak(R._ctx, C.byref(gops)) != 0:
+        raise RuntimeError(_liberr())
+    for _ in range(a.warmup):
+        out = R.indel_support_batch(None, None, packed=packed)
+    torch.cuda.synchronize()
+    kms, wall = [], []
+    for _ in range(a.steps):
+        t0 = time.perf_counter()
+        out = R.indel_support_batch(None, None, packed=packed)
+        wall.append(time.perf_counter() - t0)
+        kms.append(L.indelgpu_last_kernel_ms(R._ctx))
+    cells = int(out["cells"])
+    k_s = float(np.mean(kms)) / 1e3
+    gcups = cells / k_s / 1e9
+    cpu = None
+    if not a.no_cpu:
+        from oracle import oracle as O          # the checker, timed as the CPU baseline (one core)
+        ns = min(a.tasks, 4096)
+        t0 = time.perf_counter()
+        cc = [0]
+        for k in range(ns):
+            tt = t["targets"][t["target_off"][k]:t["target_off"][k + 1]].tobytes()
+            q = t["queries"][t["query_off"][k]:t["query_off"][k + 1]].tobytes()
+            r = O.indel_support_dp(tt, q, cells=cc)
+            assert r == (int(out["subs"][k]), int(out["indels"][k]), int(out["aligned"][k])), k
+        dt = time.perf_counter() - t0
+        cpu = {"value": cc[0] / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port",
+               "sample": f"first {ns} pairs through oracle/indel_oracle.c orc_indel_support_dp (results compared)"}
+    line = {"metric": "indel_support_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": 1, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": k_s * 1e3, "higher_is_better": True, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"f1 known-indel support: {a.tasks} pairs, 150 bp reads, 1-50 bp indels, target ~{int(t['target_off'][-1] / a.tasks)} bp",
+                       "timing": "CUDA events around the kernel on the library's stream"},
+            "pairs_per_s": a.tasks / k_s, "gpu_launches": int(L.indelgpu_last_launch_count(R._ctx)),
+            "e2e": {"value": cells / float(np.mean(wall)) / 1e9, "unit": "GCUPS", "pairs_per_s": a.tasks / float(np.mean(wall)),
+                    "note": "host buffers in and out, copies included"},
+            "roofline": {"bound": "int32", "achieved": gcups * SUPPORT_OPS_PER_CELL, "peak": gops.value, "unit": "Gop/s",
+                         "frac": gcups * SUPPORT_OPS_PER_CELL / gops.value if gops.value else None,
+                         "int_ops_per_cell": SUPPORT_OPS_PER_CELL,
+                         "peak_source": "measured here: indelgpu_int32_peak (independent add + max chains)"},
+            "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
 
 

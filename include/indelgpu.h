@@ -193,6 +193,20 @@ int indelgpu_band_align_batch(indelgpu_ctx* ctx, int32_t n,
                               int32_t script_stride,
                               int64_t* h_cells);           /* 3: fwd, rev, glob totals, or NULL   */
 
+/* ---- known-indel support check ------------------------------
+ * Batched realign_with_indel (src/variant.c:1246-1424), the DP behind is_indel_supported
+ * (variant.h:91, annotate mode): task j aligns query j = h_queries[query_off[j]..query_off[j+1])
+ * -- the read slice [qstart, qstop) of variant.c:1278-1283 -- against target j, the reference
+ * interval with the variant spliced in that variant.c:1259-1275 builds (the host keeps building it
+ * with the reference's own string code).  Outputs per task are the three counters check_for_indel
+ * compares (variant.c:1549-1553): substitutions, gap columns, aligned columns (+1, as the reference
+ * counts).  Lengths up to 8000 (scores are kept in 16 bits). */
+int indelgpu_indel_support_batch(indelgpu_ctx* ctx, int32_t n,
+                                 const uint8_t* h_targets, const int64_t* h_target_off,
+                                 const uint8_t* h_queries, const int64_t* h_query_off,
+                                 int32_t* h_subs, int32_t* h_indels, int32_t* h_aligned,
+                                 int64_t* h_cells /* 1: sum of len1 * len2, or NULL */);
+
 /* ---- reference-prototype entry points (1-element batches on the default context) --------
  * Same names, arguments and results as the reference so the rest of the C caller links
  * unchanged.  The default context is created on first use on device $INDELGPU_DEVICE (0). */

@@ -226,6 +226,28 @@ class Realigner:
             cells.ctypes.data))
         return dict(score=score, ends=ends, ncigar=ncig, cigar=cig, script=script, cells=cells)
 
+    def indel_support_batch(self, targets, queries, packed=None):
+        """Batched realign_with_indel (variant.c:1246-1424) on already built targets (the reference interval
+        with the variant spliced in, variant.c:1259-1275) and query slices (read[qstart:qstop], :1278-1283).
+        `packed` = (target bytes, target_off, query bytes, query_off) skips the packing.
+        Returns dict(subs, indels, aligned: int32[n]; cells: sum of len1 * len2)."""
+        if packed is not None:
+            tb, toff, qb, qoff = packed
+            n = len(toff) - 1
+        else:
+            n = len(targets)
+            assert len(queries) == n
+            tb, toff = pack_sequences(targets)
+            qb, qoff = pack_sequences(queries)
+        tb = tb if tb.size else np.zeros(1, dtype=np.uint8)
+        qb = qb if qb.size else np.zeros(1, dtype=np.uint8)
+        subs, indels, aligned = (np.zeros(n, dtype=np.int32) for _ in range(3))
+        cells = C.c_int64(0)
+        _check(self._L.indelgpu_indel_support_batch(
+            self._ctx, n, tb.ctypes.data, toff.ctypes.data, qb.ctypes.data, qoff.ctypes.data,
+            subs.ctypes.data, indels.ctypes.data, aligned.ctypes.data, C.addressof(cells)))
+        return dict(subs=subs, indels=indels, aligned=aligned, cells=cells.value)
+
     def attempt_band_alignment(self, refseq, zstart1, end1, readseq, zstart2, end2, low, up):
         """alignment.c:343-391, same arguments; returns ((r1, r2, q1, q2), cigar words)."""
         r = self.band_align_batch([_as_bytes(readseq)[zstart2:end2]], [_as_bytes(refseq)[zstart1:end1]],

@@ -18,6 +18,7 @@
 #include "realign_kernel.cuh"
 #include "realign_pipeline.cuh"
 #include "task_kernels.cuh"
+#include "indel_support.cuh"
 
 using namespace indelgpu;
 
@@ -94,6 +95,7 @@ struct indelgpu_ctx {
     DevBuf out_status, out_nseg, out_rstart, out_segoff, out_segs, out_detail, out_cig1, out_cig2;
     DevBuf counters;         // bytes: 0 work counter (int) | 8 seg count (u64) | 16 cells (3 x u64) | 40 error flag (int) | 48 algorithmic bytes (u64)
     DevBuf scratch;
+    DevBuf s_tgt, s_toff, s_qry, s_qoff, s_out, s_idx, s_V, s_I, s_F;   // known-indel support check (indel_support.cuh)
     DevBuf p_low, p_aln, p_cig, p_plan, p_flags;      // intermediates of the banded pipeline (realign_pipeline.cuh)
     // task API staging
     DevBuf t_reads, t_roff, t_refs, t_woff, t_packed, t_anchor, t_low, t_up, t_score, t_ends, t_ncig, t_cig, t_script;
@@ -171,6 +173,7 @@ extern "C" void indelgpu_destroy(indelgpu_ctx* c)
                      &c->in_pos, &c->in_rng, &c->out_status, &c->out_nseg, &c->out_rstart, &c->out_segoff,
                      &c->out_segs, &c->out_detail, &c->out_cig1, &c->out_cig2, &c->counters, &c->scratch,
                      &c->p_low, &c->p_aln, &c->p_cig, &c->p_plan, &c->p_flags,
+                     &c->s_tgt, &c->s_toff, &c->s_qry, &c->s_qoff, &c->s_out, &c->s_idx, &c->s_V, &c->s_I, &c->s_F,
                      &c->t_reads, &c->t_roff, &c->t_refs, &c->t_woff, &c->t_packed, &c->t_anchor, &c->t_low,
                      &c->t_up, &c->t_score, &c->t_ends, &c->t_ncig, &c->t_cig, &c->t_script};
     for (DevBuf* b : all) b->release();
@@ -792,6 +795,101 @@ extern "C" int indelgpu_band_align_batch(indelgpu_ctx* c, int32_t n, const uint8
     int err; memcpy(&err, (char*)c->pinned_small + 40, 4);
     if (h_cells) memcpy(h_cells, (char*)c->pinned_small + 16, 24);
     if (err) return fail(INDELGPU_ELIMIT, "band_align_batch: a task exceeds a size limit");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// known-indel support check (row f1)
+// ---------------------------------------------------------------------------------------
+extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const uint8_t* h_targets,
+                                            const int64_t* h_target_off, const uint8_t* h_queries,
+                                            const int64_t* h_query_off, int32_t* h_subs, int32_t* h_indels,
+                                            int32_t* h_aligned, int64_t* h_cells)
+{
+    if (!c || n < 0 || !h_targets || !h_target_off || !h_queries || !h_query_off || !h_subs || !h_indels || !h_aligned)
+        return fail(INDELGPU_EINVAL, "indel_support_batch: bad argument");
+    c->launches = 0;
+    if (h_cells) *h_cells = 0;
+    if (n == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    if (h_target_off[0] != 0 || h_query_off[0] != 0) return fail(INDELGPU_EINVAL, "offset arrays must start at 0");
+    // pairs the wavefront kernel's packing holds go there (all real reads); the rest, one pair per thread
+    std::vector<int32_t> slow;
+    int max1 = 0, max2 = 0, fast1 = 0;
+    long long cells = 0;
+    for (int i = 0; i < n; i++) {
+        const int64_t l1 = h_target_off[i + 1] - h_target_off[i], l2 = h_query_off[i + 1] - h_query_off[i];
+        if (l1 < 0 || l2 < 0 || l1 > 8000 || l2 > 8000) return fail(INDELGPU_ELIMIT, "task %d: lengths %lld x %lld outside 0..8000", i, (long long)l1, (long long)l2);
+        cells += l1 * l2;
+        if (l1 > kWaveMaxTarget || l2 > kWaveMaxQuery) { slow.push_back(i); max1 = std::max(max1, (int)l1); max2 = std::max(max2, (int)l2); }
+        else fast1 = std::max(fast1, (int)l1);
+    }
+    const int nslow = (int)slow.size();
+    const int64_t nt = h_target_off[n], nq = h_query_off[n];
+    cudaStream_t st = c->stream;
+    if (c->s_tgt.ensure((size_t)nt + 16) || c->s_toff.ensure(8 * (size_t)(n + 1)) || c->s_qry.ensure((size_t)nq + 16) ||
+        c->s_qoff.ensure(8 * (size_t)(n + 1)) || c->s_out.ensure(12 * (size_t)n)) return INDELGPU_ENOMEM;
+    if (nt > 0) CU(cudaMemcpyAsync(c->s_tgt.p, h_targets, (size_t)nt, cudaMemcpyHostToDevice, st));
+    if (nq > 0) CU(cudaMemcpyAsync(c->s_qry.p, h_queries, (size_t)nq, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->s_toff.p, h_target_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->s_qoff.p, h_query_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
+    int32_t* d_subs = c->s_out.as<int32_t>();
+    int32_t* d_indels = d_subs + n;
+    int32_t* d_aligned = d_indels + n;
+    CU(cudaEventRecord(c->ev_t0, st));
+    if (nslow < n) {
+        WaveArgs w;
+        w.n = n;
+        w.targets = c->s_tgt.as<uint8_t>(); w.target_off = c->s_toff.as<int64_t>();
+        w.queries = c->s_qry.as<uint8_t>(); w.query_off = c->s_qoff.as<int64_t>();
+        w.subs = d_subs; w.indels = d_indels; w.aligned = d_aligned;
+        int occ = 0;
+        if (fast1 <= 256) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, indel_support_wave_kernel<8>, 128, 0));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, indel_support_wave_kernel<16>, 128, 0));
+        if (occ < 1) return fail(INDELGPU_ELIMIT, "support kernel does not fit on an SM");
+        const int blocks = (int)std::min<long long>((long long)c->sms * occ, ((long long)n + 3) / 4);
+        if (fast1 <= 256) indel_support_wave_kernel<8><<<blocks, 128, 0, st>>>(w);
+        else indel_support_wave_kernel<16><<<blocks, 128, 0, st>>>(w);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    if (nslow > 0) {
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, indel_support_kernel, 128, 0));
+        if (occ < 1) return fail(INDELGPU_ELIMIT, "support kernel does not fit on an SM");
+        const long long cells_cap = (long long)(max1 + 1) * (max2 + 1);
+        // resident threads are bounded by the scratch they need (3 bytes per DP cell per thread): at most ~8 GB
+        long long blocks = std::min<long long>((long long)c->sms * std::min(occ, 4), (nslow + 127) / 128);
+        const long long per_block = 128 * (cells_cap * 3 + 4LL * (max1 + 1));
+        blocks = std::max<long long>(1, std::min<long long>(blocks, (8LL << 30) / std::max<long long>(per_block, 1)));
+        if (c->s_idx.ensure(4 * (size_t)nslow) ||
+            c->s_V.ensure((size_t)blocks * 128 * (size_t)cells_cap * 2) || c->s_I.ensure((size_t)blocks * 128 * (size_t)cells_cap) ||
+            c->s_F.ensure((size_t)blocks * 128 * 4 * (size_t)(max1 + 1))) return INDELGPU_ENOMEM;
+        CU(cudaMemcpyAsync(c->s_idx.p, slow.data(), 4 * (size_t)nslow, cudaMemcpyHostToDevice, st));
+        SupportArgs a;
+        a.n = nslow;
+        a.index = c->s_idx.as<int32_t>();
+        a.targets = c->s_tgt.as<uint8_t>(); a.target_off = c->s_toff.as<int64_t>();
+        a.queries = c->s_qry.as<uint8_t>(); a.query_off = c->s_qoff.as<int64_t>();
+        a.subs = d_subs; a.indels = d_indels; a.aligned = d_aligned;
+        a.V = c->s_V.as<int16_t>(); a.I = c->s_I.as<int8_t>(); a.F = c->s_F.as<int32_t>();
+        a.cells_cap = cells_cap; a.max_len1 = max1; a.max_len2 = max2;
+        a.cell_total = ctr_cells(c); a.error_flag = ctr_err(c);
+        indel_support_kernel<<<(int)blocks, 128, 0, st>>>(a);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(c->ev_t1, st));
+    c->timed = true;
+    CU(cudaMemcpyAsync(h_subs, d_subs, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_indels, d_indels, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_aligned, d_aligned, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->pinned_small, c->counters.p, 64, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int err; memcpy(&err, (char*)c->pinned_small + 40, 4);
+    if (h_cells) *h_cells = cells;
+    if (err) return fail(INDELGPU_ELIMIT, "indel_support_batch: a task exceeds a size limit");
     return 0;
 }
 

@@ -16,7 +16,7 @@ EXPORTS = [
     "indelgpu_host_alloc", "indelgpu_host_free", "indelgpu_set_reference",
     "indelgpu_seg_bound", "indelgpu_realign_batch", "indelgpu_realign_batch_device",
     "indelgpu_last_counters", "indelgpu_last_launch_count", "indelgpu_last_kernel_ms", "indelgpu_int32_peak",
-    "indelgpu_find_best_band_batch", "indelgpu_band_align_batch",
+    "indelgpu_find_best_band_batch", "indelgpu_band_align_batch", "indelgpu_indel_support_batch",
     "local_align", "ALIGN", "DISPLAY", "fetch_cigar",
 ]
 
@@ -83,6 +83,7 @@ def load():
     L.indelgpu_find_best_band_batch.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 7
     L.indelgpu_band_align_batch.argtypes = ([C.c_void_p, C.c_int32] + [C.c_void_p] * 10
                                             + [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p])
+    L.indelgpu_indel_support_batch.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 8
     L.local_align.restype = C.c_int
     L.local_align.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
     L.ALIGN.restype = C.c_int

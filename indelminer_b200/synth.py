@@ -115,3 +115,37 @@ def make_band_tasks(n, band, seed=20261018, read_len=150, win_len=1410, ref_seed
     return dict(reads=np.ascontiguousarray(reads.reshape(-1)), read_off=np.arange(n + 1, dtype=np.int64) * M,
                 wins=np.ascontiguousarray(wins.reshape(-1)), win_off=np.arange(n + 1, dtype=np.int64) * N,
                 low=low, up=up)
+
+
+def make_support_tasks(n, seed=20261018, read_len=150, max_indel=50, ref_len=1 << 22, sub_rate=0.01):
+    """Row f1 (annotate mode): n (target, query) pairs in the shape check_for_indel builds them
+    (variant.c:1520-1548): a known 1-50 bp insertion or deletion, a 150 bp read overlapping it -- half of
+    the reads carry the variant, half are reference reads -- and the target = the reference interval
+    [read start - size, read end + size) with the variant spliced in (variant.c:1259-1275)."""
+    rng = np.random.default_rng(seed)
+    ref = make_reference(ref_len, seed=3)
+    M = read_len
+    vstart = rng.integers(1000, ref_len - 2000, size=n)
+    size = rng.integers(1, max_indel + 1, size=n)
+    isdel = rng.random(n) < 0.5
+    carries = rng.random(n) < 0.5
+    back = rng.integers(5, M - 5, size=n)              # read start = vstart - back
+    ins_bases = ACGT[rng.integers(0, 4, size=(n, max_indel), dtype=np.uint8)]
+    subs = rng.random((n, M)) < sub_rate
+    sub_bases = ACGT[rng.integers(0, 4, size=(n, M), dtype=np.uint8)]
+    targets, queries = [], []
+    for k in range(n):
+        v, sz, s = int(vstart[k]), int(size[k]), int(vstart[k] - back[k])
+        if isdel[k]:
+            mut = np.concatenate([ref[s - sz:v + 1], ref[v + 1 + sz:s + M + 2 * sz + 1]])
+        else:
+            mut = np.concatenate([ref[s - sz:v + 1], ins_bases[k, :sz], ref[v + 1:s + M + sz]])
+        targets.append(mut)
+        q = (mut[sz:sz + M] if carries[k] else ref[s:s + M]).copy()
+        q[subs[k]] = sub_bases[k][subs[k]]
+        queries.append(q)
+    toff = np.zeros(n + 1, dtype=np.int64)
+    toff[1:] = np.cumsum([len(t) for t in targets])
+    qoff = np.arange(n + 1, dtype=np.int64) * M
+    return dict(targets=np.ascontiguousarray(np.concatenate(targets)), target_off=toff,
+                queries=np.ascontiguousarray(np.concatenate(queries)), query_off=qoff)

@@ -774,3 +774,87 @@ long orc_realign_batch(const orc_params* p, const char* refseq, int reflength, i
     free(o);
     return total;
 }
+
+
+/* ======================================================================================
+ * row f1: realign_with_indel (variant.c:1246-1424)
+ * ====================================================================================== */
+#include <ctype.h>
+
+char* orc_indel_target(const char* reference, int rstart, int rstop, int vtype, int vstart, int vstop,
+                       const char* alternate)
+{
+    const size_t len0 = (size_t)(rstop - rstart);
+    size_t cap = len0 + 1;
+    char* target = calloc(cap, 1);                               /* copy_partial_string, strings.c:3-8 */
+    memcpy(target, reference + rstart, len0);
+    if (vtype == 1) {                                            /* DELETION, variant.c:1261-1264 */
+        memmove(target + vstart - rstart, target + vstop - rstart - 1, (size_t)(rstop - vstop + 2));
+    } else {                                                     /* INSERTION, :1265-1271 */
+        const size_t alen = strlen(alternate) - 1;
+        target = realloc(target, cap + alen);
+        memset(target + cap, 0, alen);                           /* ckreallocz, memalloc.c:45-55 */
+        char* at = target + vstart - rstart;
+        memmove(at + alen, at, strlen(at));
+        memcpy(at, alternate + 1, alen);
+    }
+    return target;
+}
+
+void orc_indel_support_dp(const char* t1, int len1, const char* t2, int len2,
+                          int* psubs, int* pindels, int* paligned, long long* cells)
+{
+    enum { SUB = 0, INS = 1, DEL = 2 };
+    const int match = 2, mismatch = 1, gopen = 4, gextend = 1;   /* variant.c:1289-1292 */
+    const size_t W = (size_t)len1 + 1;
+    int* V = calloc(((size_t)len2 + 1) * W, sizeof(int));
+    char* I = calloc(((size_t)len2 + 1) * W, 1);
+    int* F = calloc(W, sizeof(int));                             /* starts at 0 (:1305) */
+    for (int i = 0; i <= len2; i++) V[(size_t)i * W] = -gopen - i * gextend;
+    for (int j = 0; j <= len1; j++) V[j] = -gopen - j * gextend;
+    int max_score = 0, max_i = -1, max_j = -1;
+    for (int i = 1; i <= len2; i++) {
+        int E = 0;                                               /* restarts on every row (:1322) */
+        for (int j = 1; j <= len1; j++) {
+            int ifsub = V[(size_t)(i - 1) * W + j - 1];
+            ifsub = toupper((unsigned char)t1[j - 1]) == toupper((unsigned char)t2[i - 1]) ? ifsub + match : ifsub - mismatch;
+            const int vup = V[(size_t)(i - 1) * W + j] - gopen;
+            const int ifins = (F[j] > vup ? F[j] : vup) - gextend;
+            F[j] = ifins;
+            const int vleft = V[(size_t)i * W + j - 1] - gopen;
+            const int ifdel = (E > vleft ? E : vleft) - gextend;
+            E = ifdel;
+            const int ifindel = ifins > ifdel ? ifins : ifdel;
+            int v = ifsub; char d = SUB;
+            if (v < ifindel) { d = (ifins >= ifdel) ? INS : DEL; v = ifindel; }   /* :1336-1342 */
+            V[(size_t)i * W + j] = v; I[(size_t)i * W + j] = d;
+            if (v > max_score) { max_score = v; max_i = i; max_j = j; }          /* strict: first maximum */
+        }
+    }
+    if (cells) *cells += (long long)len1 * len2;
+    /* traceback while the score stays positive (:1377-1398), counting as :1403-1417 does: every column
+       plus the terminating NUL, which is neither a gap nor a mismatch */
+    int subs = 0, ins = 0, dels = 0, aligned = 1;
+    int score = max_score, i = max_i, j = max_j;
+    while (score > 0) {
+        const char d = I[(size_t)i * W + j];
+        if (d == SUB) { if (t1[j - 1] != t2[i - 1]) subs++; aligned++; i--; j--; }
+        else if (d == INS) { ins++; aligned++; i--; }
+        else { dels++; j--; }
+        score = V[(size_t)i * W + j];
+    }
+    free(V); free(I); free(F);
+    *psubs = subs; *pindels = ins + dels; *paligned = aligned;
+}
+
+void orc_realign_with_indel(const char* reference, int rstart, int rstop, const char* query, int qstart,
+                            int qstop, int vtype, int vstart, int vstop, const char* alternate,
+                            int* subs, int* indels, int* aligned)
+{
+    char* target = orc_indel_target(reference, rstart, rstop, vtype, vstart, vstop, alternate);
+    const char* t2 = query + qstart;
+    int len2 = qstop - qstart;
+    if ((int)strlen(t2) < len2) len2 = (int)strlen(t2);          /* :1281-1283 */
+    orc_indel_support_dp(target, (int)strlen(target), t2, len2, subs, indels, aligned, NULL);
+    free(target);
+}

@@ -113,6 +113,29 @@ long orc_realign_batch(const orc_params* p, const char* refseq, int reflength, i
                        const char* reads, const long long* off, const int* position,
                        const int* range1, int* nseg_out);
 
+/* ---- row f1 of SURVEY.md section 8: realign_with_indel (variant.c:1246-1424) ------------------
+ * "Would this read support the known indel?"  The reference splices the variant into a copy of the
+ * reference interval [rstart, rstop) (the target), aligns query[qstart, qstop) against it with a
+ * full-matrix affine DP (match +2, mismatch -1, gap open 4, gap extend 1; E restarts at 0 on every
+ * row and F starts at 0: both kept), traces back from the first maximum while the score stays
+ * positive, and counts substitutions, gap columns and aligned columns (one more than there are:
+ * the counting loop starts ON the terminating NUL, variant.c:1405-1417; kept).
+ * vtype: 0 = INSERTION, 1 = DELETION (varianttype, evidence.h:14-18). */
+
+/* the target the reference builds (variant.c:1259-1275); returns a malloc'ed NUL-terminated string */
+char* orc_indel_target(const char* reference, int rstart, int rstop, int vtype, int vstart, int vstop,
+                       const char* alternate);
+
+/* the DP + traceback + counting on an already built target (variant.c:1277-1423);
+ * *cells (optional) += len1 * len2 */
+void orc_indel_support_dp(const char* target, int len1, const char* query, int len2,
+                          int* subs, int* indels, int* aligned, long long* cells);
+
+/* both, with the reference's own argument list */
+void orc_realign_with_indel(const char* reference, int rstart, int rstop, const char* query, int qstart,
+                            int qstop, int vtype, int vstart, int vstop, const char* alternate,
+                            int* subs, int* indels, int* aligned);
+
 #ifdef __cplusplus
 }
 #endif

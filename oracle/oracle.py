@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_DP_SO = os.path.join(HERE, "_ref", "libref_dp.so")
 REF_ALIGN_SO = os.path.join(HERE, "_ref", "libref_align.so")
+REF_VARIANT_SO = os.path.join(HERE, "_ref", "libref_variant.so")
 ORC_MAXSEG = 1024
 
 
@@ -58,6 +59,7 @@ def default_params(k=6, g=0, maxdel=1000, ethr=10):
 _lib = None
 _ref_dp = None
 _ref_align = None
+_ref_variant = None
 
 
 def lib():
@@ -70,6 +72,7 @@ def lib():
         _lib.orc_global_align.restype = C.c_int
         _lib.orc_fetch_cigar.restype = C.c_int
         _lib.orc_attempt_band_alignment.restype = C.c_int
+        _lib.orc_indel_target.restype = C.c_void_p
     return _lib
 
 
@@ -257,3 +260,55 @@ def ref_realign(ref, position, range1, read, reflength=None):
     n = f(ref, len(ref) if reflength is None else reflength, position, range1, read,
           op, ln, st, en, mx, C.byref(nev))
     return [(op[i], ln[i], st[i], en[i]) for i in range(n)], nev.value
+
+
+# ------------------------------------------------------------------ row f1: realign_with_indel (variant.c:1246-1424)
+INSERTION, DELETION = 0, 1          # varianttype, evidence.h:14-18
+
+
+def have_ref_variant():
+    return os.path.exists(REF_VARIANT_SO)
+
+
+def ref_variant():
+    global _ref_variant
+    if _ref_variant is None:
+        _ref_variant = C.CDLL(REF_VARIANT_SO)
+    return _ref_variant
+
+
+def indel_target(reference, rstart, rstop, vtype, vstart, vstop, alternate):
+    """the target string variant.c:1259-1275 builds (reference interval with the variant spliced in)"""
+    L = lib()
+    p = L.orc_indel_target(_b(reference), rstart, rstop, vtype, vstart, vstop, _b(alternate))
+    out = C.string_at(p)
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    libc.free(p)
+    return out
+
+
+def indel_support_dp(target, query, cells=None):
+    """(subs, indels, aligned) of variant.c:1277-1423 for an already built target and query slice"""
+    t, q = _b(target), _b(query)
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    cc = C.c_longlong(0)
+    lib().orc_indel_support_dp(t, len(t), q, len(q), C.byref(a), C.byref(b), C.byref(c), C.byref(cc))
+    if cells is not None:
+        cells[0] += cc.value
+    return a.value, b.value, c.value
+
+
+def realign_with_indel(reference, rstart, rstop, query, qstart, qstop, vtype, vstart, vstop, alternate):
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    lib().orc_realign_with_indel(_b(reference), rstart, rstop, _b(query), qstart, qstop, vtype, vstart, vstop,
+                                 _b(alternate), C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+def ref_realign_with_indel(reference, rstart, rstop, query, qstart, qstop, vtype, vstart, vstop, alternate):
+    """the reference's own static function, through oracle/ref_shim_variant.c"""
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    ref_variant().refshim_realign_with_indel(_b(reference), rstart, rstop, _b(query), qstart, qstop, vtype, vstart,
+                                             vstop, _b(alternate), C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value

@@ -1,0 +1,91 @@
+"""GPU parity for row f1 of SURVEY.md section 8: the known-indel support check, realign_with_indel
+(variant.c:1246-1424), through indelgpu_indel_support_batch of the C ABI, against the reference's
+committed outputs (tests/golden/indel_support.tsv.gz) and against the oracle on seeded cases.
+Bit-exact: three integer counters per task."""
+import numpy as np
+import pytest
+
+from tests.util import indel_support_cases, load_indel_support_golden, make_rng, rseq
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from indelminer_b200 import build
+    build.build()
+    import indelminer_b200
+    return indelminer_b200
+
+
+def split(oracle, c):
+    ref, rstart, rstop, read, qstart, qstop, vtype, vstart, vstop, alt = c
+    return oracle.indel_target(ref, rstart, rstop, vtype, vstart, vstop, alt), read[qstart:qstop].encode()
+
+
+def test_golden_reference_outputs(gpu, oracle):
+    g = load_indel_support_golden()
+    pairs = [split(oracle, c) for c, _ in g]
+    R = gpu.Realigner()
+    out = R.indel_support_batch([t for t, _ in pairs], [q for _, q in pairs])
+    for i, (_c, want) in enumerate(g):
+        assert (out["subs"][i], out["indels"][i], out["aligned"][i]) == want, i
+    assert out["cells"] == sum(len(t) * len(q) for t, q in pairs)
+    R.close()
+
+
+def test_seeded_cases_against_oracle(gpu, oracle):
+    cases = indel_support_cases(make_rng(77), 5000)
+    pairs = [split(oracle, c) for c in cases]
+    R = gpu.Realigner()
+    out = R.indel_support_batch([t for t, _ in pairs], [q for _, q in pairs])
+    for i, (t, q) in enumerate(pairs):
+        assert (out["subs"][i], out["indels"][i], out["aligned"][i]) == oracle.indel_support_dp(t, q), i
+    R.close()
+
+
+def test_edge_shapes(gpu, oracle):
+    """empty and one-base sequences, nothing in common (score 0: no traceback), N and lower case,
+    ragged lengths in one batch, a long pair"""
+    rng = make_rng(3)
+    T = [b"", b"A", b"", b"ACGT", b"AAAA", b"acgtnACGTN", rseq(rng, 700, "ACGT").encode(), b"ACGTACGTAC" * 30]
+    Q = [b"", b"", b"C", b"ACGT", b"CCCC", b"ACGTNacgtn", rseq(rng, 250, "ACGT").encode(), b"ACGTACGTAC" * 12]
+    long_t = rseq(rng, 3000, "ACGT")
+    T.append(long_t.encode())
+    Q.append((long_t[500:900] + long_t[930:1500]).encode())
+    R = gpu.Realigner()
+    out = R.indel_support_batch(T, Q)
+    for i, (t, q) in enumerate(zip(T, Q)):
+        assert (out["subs"][i], out["indels"][i], out["aligned"][i]) == oracle.indel_support_dp(t, q), i
+    assert tuple(int(out[k][4]) for k in ("subs", "indels", "aligned")) == (0, 0, 1)     # the NUL column only
+    with pytest.raises(gpu.IndelGpuError):
+        R.indel_support_batch([b"A" * 8001], [b"A"])
+    out = R.indel_support_batch([], [])
+    assert len(out["subs"]) == 0
+    R.close()
+
+
+def test_batch_larger_than_resident_threads(gpu, oracle):
+    """more tasks than threads in flight: the grid-stride loop reuses each thread's scratch"""
+    rng = np.random.default_rng(11)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    n = 200_000
+    T, Q = [], []
+    base = acgt[rng.integers(0, 4, size=4096)]
+    for i in range(n):
+        s = int(rng.integers(0, 3900))
+        t = base[s:s + int(rng.integers(20, 60))]
+        q = t[int(rng.integers(0, 5)):].copy()
+        if len(q) > 8 and i % 3 == 0:
+            q = np.delete(q, 5)
+        T.append(t.tobytes())
+        Q.append(q.tobytes())
+    R = gpu.Realigner()
+    out = R.indel_support_batch(T, Q)
+    for i in range(0, n, 97):
+        assert (out["subs"][i], out["indels"][i], out["aligned"][i]) == oracle.indel_support_dp(T[i], Q[i]), i
+    assert out["cells"] == sum(len(t) * len(q) for t, q in zip(T, Q))
+    R.close()

@@ -101,3 +101,31 @@ def test_realign_two_rounds(O, k, g):
         seen.add(a.status)
     assert {1, 2, 3, 4, 5, 6} <= seen
     O.ref_set_params()
+
+
+# ---------------------------------------------------------------- row f1: realign_with_indel (variant.c:1246-1424)
+def test_realign_with_indel_against_reference(oracle):
+    if not oracle.have_ref_variant():
+        pytest.skip("oracle/_ref/libref_variant.so not built")
+    from tests.util import indel_support_cases
+    n = 0
+    for c in indel_support_cases(make_rng(5), 2500):
+        assert oracle.realign_with_indel(*c) == oracle.ref_realign_with_indel(*c), c
+        n += 1
+    assert n == 2500
+
+
+def test_realign_with_indel_golden(oracle):
+    """the committed outputs of the reference (oracle/make_golden_support.py); also checks that the split
+    the GPU entry point uses (target built on the host, DP on the slices) is the same function"""
+    from tests.util import load_indel_support_golden
+    g = load_indel_support_golden()
+    assert len(g) == 600
+    seen = set()
+    for c, want in g:
+        assert oracle.realign_with_indel(*c) == want
+        ref, rstart, rstop, read, qstart, qstop, vtype, vstart, vstop, alt = c
+        target = oracle.indel_target(ref, rstart, rstop, vtype, vstart, vstop, alt)
+        assert oracle.indel_support_dp(target, read[qstart:qstop]) == want
+        seen.add((vtype, want[1] > 0))
+    assert len(seen) == 4            # insertions and deletions, with and without gap columns

@@ -88,3 +88,54 @@ def split_read_case(rng, L=None, alpha=None):
 
 def make_rng(seed):
     return random.Random(seed)
+
+
+def indel_support_cases(rng, n, lower_frac=0.2):
+    """Seeded (reference, rstart, rstop, read, qstart, qstop, vtype, vstart, vstop, alternate) tuples in the
+    shape check_for_indel hands to realign_with_indel (variant.c:1520-1548): a known 1-40 bp insertion
+    (vtype 0) or deletion (1) in VCF convention (the alternate / reference allele starts with the base at
+    vstart), a read that carries it or not, 3 % substitutions, some reads in lower case, trimmed ends."""
+    out = []
+    while len(out) < n:
+        L = rng.randrange(400, 900)
+        ref = "".join(rng.choice("ACGT") for _ in range(L))
+        vtype = rng.randrange(2)
+        vstart = rng.randrange(120, L - 220)
+        if vtype == 1:
+            vstop = vstart + rng.randrange(1, 40) + 1
+            alt = ref[vstart]
+            size = vstop - vstart - 1
+        else:
+            vstop = vstart + 1
+            alt = ref[vstart] + "".join(rng.choice("ACGT") for _ in range(rng.randrange(1, 40)))
+            size = len(alt) - 1
+        M = rng.randrange(40, 120)
+        s = max(0, vstart - rng.randrange(5, M - 5))
+        if rng.random() < 0.5:
+            mut = ref[:vstart + 1] + (alt[1:] if vtype == 0 else "") + ref[(vstop - 1 if vtype == 1 else vstart + 1):]
+            read = mut[s:s + M]
+        else:
+            read = ref[s:s + M]
+        read = "".join(rng.choice("ACGT") if rng.random() < 0.03 else c for c in read)
+        if rng.random() < lower_frac:
+            read = read.lower()
+        rstart = max(0, s - size)
+        rstop = min(L, s + M + size + rng.randrange(0, 5))
+        if not (rstart <= vstart and vstop < rstop):
+            continue
+        qstart = rng.randrange(0, 5)
+        qstop = len(read) - rng.randrange(0, 5)
+        out.append((ref, rstart, rstop, read, qstart, qstop, vtype, vstart, vstop, alt))
+    return out
+
+
+def load_indel_support_golden():
+    """tests/golden/indel_support.tsv.gz (oracle/make_golden_support.py): the reference's own
+    realign_with_indel on seeded cases -> list of (case tuple, (subs, indels, aligned))."""
+    out = []
+    with gzip.open(os.path.join(GOLDEN, "indel_support.tsv.gz"), "rt") as f:
+        for line in f:
+            t = line.rstrip("\n").split("\t")
+            case = (t[0], int(t[1]), int(t[2]), t[3], int(t[4]), int(t[5]), int(t[6]), int(t[7]), int(t[8]), t[9])
+            out.append((case, (int(t[10]), int(t[11]), int(t[12]))))
+    return out
