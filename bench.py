@@ -7,6 +7,7 @@ of the cfg3 shape (64 Mb contig, planted 1-50 bp indels, 2x150 bp pairs; SURVEY.
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, libindelgpu.so)
   python bench.py --impl reference ...                            the reference's own CPU code
   python bench.py --workload band --band 33                       banded-DP micro-bench (D1): GCUPS
+  python bench.py --workload support                              known-indel support check (row f1): GCUPS
 
 Under torchrun (N > 1) every rank realigns its own region's candidates (weak scaling, no
 data-path collective); NCCL carries only the tiny per-read-group insert-range all-reduce.
