@@ -481,6 +481,7 @@ def run_support(a, R, L, torch):
             "roofline": {"bound": "int32", "achieved": gcups * SUPPORT_OPS_PER_CELL, "peak": gops.value, "unit": "Gop/s",
                          "frac": gcups * SUPPORT_OPS_PER_CELL / gops.value if gops.value else None,
                          "int_ops_per_cell": SUPPORT_OPS_PER_CELL,
+                         "frac_at_10_ops_per_cell": gcups * INT_OPS_PER_CELL / gops.value if gops.value else None,
                          "peak_source": "measured here: indelgpu_int32_peak (independent add + max chains)"},
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

@@ -89,3 +89,30 @@ def test_batch_larger_than_resident_threads(gpu, oracle):
         assert (out["subs"][i], out["indels"][i], out["aligned"][i]) == oracle.indel_support_dp(T[i], Q[i]), i
     assert out["cells"] == sum(len(t) * len(q) for t, q in zip(T, Q))
     R.close()
+
+
+def test_every_columns_per_lane_variant(gpu, oracle):
+    """target lengths 1..512 exercise every register-tile width of the wavefront kernel (2..16 columns per
+    lane, both instantiations); queries up to the 500-base limit; lengths just past the limits take the
+    thread-per-pair kernel in the same batch"""
+    rng = make_rng(19)
+    T, Q = [], []
+    for len1 in list(range(1, 513, 5)) + [255, 256, 257, 511, 512, 513, 520]:
+        t = rseq(rng, len1, "ACGT")
+        lo = rng.randrange(0, max(1, len1 // 3))
+        q = t[lo:lo + rng.randrange(1, 500)]
+        if len(q) > 30:
+            cut = rng.randrange(10, len(q) - 10)
+            q = q[:cut] + (rseq(rng, rng.randrange(1, 12), "ACGT") if rng.random() < 0.5 else "") + q[cut + rng.randrange(0, 8):]
+        q = "".join(rng.choice("ACGT") if rng.random() < 0.04 else ch for ch in q)[:500]
+        T.append(t.encode())
+        Q.append(q.encode())
+    T += [rseq(rng, 300, "ACGT").encode(), rseq(rng, 512, "AC").encode()]
+    Q += [rseq(rng, 501, "ACGT").encode(), rseq(rng, 500, "AC").encode()]
+    for small_first in (True, False):                      # MAXCPL = 8 and 16 kernels
+        sel = [i for i in range(len(T)) if (len(T[i]) <= 256) == small_first or not small_first]
+        R = gpu.Realigner()
+        out = R.indel_support_batch([T[i] for i in sel], [Q[i] for i in sel])
+        for k, i in enumerate(sel):
+            assert (out["subs"][k], out["indels"][k], out["aligned"][k]) == oracle.indel_support_dp(T[i], Q[i]), (i, len(T[i]), len(Q[i]))
+        R.close()
