@@ -233,10 +233,20 @@ IG_HD inline void dc_sweep_reg(DcCtx<STRIDE>& x, DcFrame& f)
         else x.mp[0][fr] = x.mp[1][fr] = x.mp[2][fr] = -1;
     }
     int c = 0, d = 0, e = 0;                                     // values of the last cell of the last row
+    // the row's W2 bytes of B in a byte-shifted register window: byte q - 1 = B[q + low - 1 + i] (0 outside 1..N)
+    constexpr int NW = (W2 + 3) / 4;
+    uint32_t wr[NW];
+#pragma unroll
+    for (int k = 0; k < NW; k++) wr[k] = 0;
+#pragma unroll
+    for (int q = 1; q <= W2; q++) {
+        const int ib = q + low;
+        if (ib >= 1 && ib <= N) wr[(q - 1) >> 2] |= (uint32_t)b1[ib] << (8 * ((q - 1) & 3));
+    }
     for (int i = 1; i <= M; i++) {
         if (i > N - up) rightd--;
         if (leftd > 1) leftd--;
-        const uint8_t ai = a1[i];
+        const uint32_t ai = a1[i];
         x.cells += rightd - leftd + 1;
         int cl = kNeg, el = kNeg;                                // horizontal inputs of the row's first cell
 #pragma unroll
@@ -244,6 +254,7 @@ IG_HD inline void dc_sweep_reg(DcCtx<STRIDE>& x, DcFrame& f)
             if (q >= leftd && q <= rightd) {
                 const bool first = q == leftd;
                 const int ib = q + low - 1 + i;
+                const uint32_t bq = (wr[(q - 1) >> 2] >> (8 * ((q - 1) & 3))) & 0xFFu;
                 // horizontal
                 int openh = cl - m, en = el - h;
                 const bool eopen = openh > en;
@@ -256,7 +267,7 @@ IG_HD inline void dc_sweep_reg(DcCtx<STRIDE>& x, DcFrame& f)
                 if (dopen) dn = openv;
                 const int dpn = dopen ? CP[q + 1] : DP[q + 1];
                 // diagonal (column 0 and below has none: CC[q] is -infinity there)
-                int cn = CC[q] + ((ib > 0 && ai == b1[ib > 0 ? ib : 1]) ? x.P->match : x.P->mismatch);
+                int cn = CC[q] + ((ib > 0 && ai == bq) ? x.P->match : x.P->mismatch);
                 if (ib <= 0) cn = kNeg;
                 int cpn = CP[q], kind = 0;                       // 0 diagonal, 1 came from d, 2 came from e
                 if (cn < dn || cn < en) {
@@ -281,6 +292,10 @@ IG_HD inline void dc_sweep_reg(DcCtx<STRIDE>& x, DcFrame& f)
                 c = cn; d = dn; e = el;
             }
         }
+#pragma unroll
+        for (int k = 0; k < NW; k++) wr[k] = (wr[k] >> 8) | ((k + 1 < NW) ? (wr[k + 1] << 24) : 0u);
+        const int xb = W2 + low + i;                             // new top byte for row i + 1
+        if (xb >= 1 && xb <= N) wr[(W2 - 1) >> 2] |= (uint32_t)b1[xb] << (8 * ((W2 - 1) & 3));
     }
     int k, l;
     int dpr = DP[1], cpr = CP[1];
