@@ -61,6 +61,8 @@ const char* indelgpu_last_error(void);
 
 /* One context per host worker thread / GPU (the reference's ALIGN keeps file-scope state,
  * globalalign.c:19-37; this library keeps none). */
+/* number of CUDA devices this process can see (0 when there is none: every other entry point then fails) */
+int           indelgpu_device_count(void);
 indelgpu_ctx* indelgpu_create(int device, const indelgpu_params* p);
 void          indelgpu_destroy(indelgpu_ctx* ctx);
 int           indelgpu_device(const indelgpu_ctx* ctx);

@@ -44,6 +44,13 @@ static int fail(int code, const char* fmt, ...)
     } while (0)
 
 extern "C" const char* indelgpu_last_error(void) { return g_err; }
+
+extern "C" int indelgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 extern "C" int indelgpu_version(void) { return INDELGPU_VERSION; }
 
 extern "C" void indelgpu_default_params(indelgpu_params* p)
@@ -245,6 +252,19 @@ extern "C" int64_t indelgpu_seg_bound(int32_t n, int64_t total_read_bases)
 }
 
 
+// The dynamic shared-memory limit is a property of the FUNCTION on a device, shared by every context and
+// host thread of the process: it is only ever raised to the device's opt-in maximum, never set to what
+// one launch needs, so that concurrent contexts with different window sizes cannot lower it under
+// each other's launches.
+template <class Kern>
+static cudaError_t allow_max_smem(indelgpu_ctx* c, Kern kern)
+{
+    cudaFuncAttributes fa;
+    const cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - (int)fa.sharedSizeBytes);
+}
+
 // Persistent warp-per-read kernels: pick the CTA size that puts the most warps on an SM given the
 // per-warp shared-memory slice.
 typedef WarpPlanFwd WarpPlan;
@@ -256,24 +276,21 @@ static int plan_warps(indelgpu_ctx* c, Kern kern, int bytes_per_warp, int* warps
     for (const WarpPlan& w : c->plans)
         if (w.kern == (const void*)kern && w.bytes_per_warp == bytes_per_warp) {
             *warps_per_cta = w.warps_per_cta; *ctas_per_sm = w.ctas_per_sm;
-            // the limit is per function, not per context: another configuration may have lowered it
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, w.warps_per_cta * bytes_per_warp));
             return 0;
         }
     static const int cand[] = {8, 7, 6, 5, 4, 3, 2, 1};       // __launch_bounds__(256)
+    CU(allow_max_smem(c, kern));
     int best = 0;
     *warps_per_cta = 0; *ctas_per_sm = 0;
     for (int w : cand) {
         const long long smem = (long long)w * bytes_per_warp;
         if (smem > c->max_smem_optin) continue;
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, w * 32, (size_t)smem));
         if (occ * w > best) { best = occ * w; *warps_per_cta = w; *ctas_per_sm = occ; }
     }
     if (best == 0) return fail(INDELGPU_ELIMIT, "window/read sizes need %d bytes of shared memory per warp (limit %d): range1 + maxdelsize or the read length is too large",
                                bytes_per_warp, c->max_smem_optin);
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, *warps_per_cta * bytes_per_warp));
     if (const char* e = getenv("INDELGPU_MAX_WARPS_PER_SM")) {   // occupancy experiments only
         const int cap = atoi(e);
         if (cap > 0) {
@@ -339,7 +356,7 @@ static int launch_pipeline(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_
     int cw = 8;
     while (cw > 1 && (size_t)cw * cper > (size_t)c->max_smem_optin) cw >>= 1;
     if ((size_t)cw * cper > (size_t)c->max_smem_optin) return fail(INDELGPU_ELIMIT, "reads too long for the combine kernel's shared memory");
-    CU(cudaFuncSetAttribute(pipe_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cw * cper));
+    CU(allow_max_smem(c, pipe_combine_kernel));
     int cocc = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cocc, pipe_combine_kernel, cw * 32, (size_t)cw * cper));
     if (cocc < 1) return fail(INDELGPU_ELIMIT, "combine kernel does not fit on an SM");
@@ -773,7 +790,7 @@ extern "C" int indelgpu_band_align_batch(indelgpu_ctx* c, int32_t n, const uint8
     } else {
         const SmemLayout L = make_layout(max_read, 0);
         if (L.total > c->max_smem_optin - 1024) return fail(INDELGPU_ELIMIT, "read too long for shared memory (%d bytes)", L.total);
-        CU(cudaFuncSetAttribute(align_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        CU(allow_max_smem(c, align_tasks_kernel));
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align_tasks_kernel, 32, L.total));
         if (occ < 1) return fail(INDELGPU_ELIMIT, "align kernel does not fit on an SM");

@@ -16,7 +16,7 @@ EXPORTS = [
     "indelgpu_host_alloc", "indelgpu_host_free", "indelgpu_set_reference",
     "indelgpu_seg_bound", "indelgpu_realign_batch", "indelgpu_realign_batch_device",
     "indelgpu_last_counters", "indelgpu_last_launch_count", "indelgpu_last_kernel_ms", "indelgpu_int32_peak",
-    "indelgpu_find_best_band_batch", "indelgpu_band_align_batch", "indelgpu_indel_support_batch",
+    "indelgpu_find_best_band_batch", "indelgpu_band_align_batch", "indelgpu_indel_support_batch", "indelgpu_device_count",
     "local_align", "ALIGN", "DISPLAY", "fetch_cigar",
 ]
 

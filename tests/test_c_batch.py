@@ -66,3 +66,34 @@ def test_c_driver_matches_oracle(driver, oracle, tmp_path, k, g, n):
             assert int(rs) == segs[0][2], i
         nsplit += o.status == 6
     assert nsplit > n // 10
+
+
+def test_c_driver_region_sharded_workers(driver, tmp_path):
+    """-G 3: three host worker threads, one context each (devices taken round-robin; on a one-GPU box they
+    share it), 2 kb regions dealt round-robin, results merged into input order: the output must be the
+    single-worker output byte for byte (row (e) of the scope table, and the library's thread safety)"""
+    rng = make_rng(5)
+    contigs = [rseq(rng, rng.randrange(20000, 40000), "ACGT") for _ in range(3)]
+    lines = []
+    for _ in range(6000):
+        t = rng.randrange(len(contigs))
+        ref = contigs[t]
+        M = rng.randrange(60, 151)
+        start = rng.randrange(0, len(ref) - M - 400)
+        if rng.random() < 0.6:
+            dl, cut = rng.randrange(1, 200), rng.randrange(5, M - 5)
+            read = ref[start:start + cut] + ref[start + cut + dl:start + dl + M]
+        else:
+            read = ref[start:start + M]
+        lines.append(f"{t}\t{max(0, start + rng.randrange(-400, 400))}\t{rng.randrange(300, 800)}\t{read}\n")
+    cpath, tpath = tmp_path / "contigs.txt", tmp_path / "cand.tsv"
+    cpath.write_text("".join(c + "\n" for c in contigs))
+    tpath.write_text("".join(lines))
+    one = subprocess.run([driver, str(cpath), str(tpath)], capture_output=True, text=True, timeout=600)
+    assert one.returncode == 0, one.stderr[-2000:]
+    many = subprocess.run([driver, "-G", "3", "-R", "2000", str(cpath), str(tpath)], capture_output=True, text=True, timeout=600)
+    assert many.returncode == 0, many.stderr[-2000:]
+    assert many.stdout == one.stdout
+    assert len(one.stdout.splitlines()) == len(lines)
+    counts = [int(x) for x in __import__("re").findall(r"worker \d+ \(device \d+\): (\d+)", many.stderr)]
+    assert len(counts) == 3 and sum(counts) == len(lines) and min(counts) > len(lines) // 6
