@@ -235,6 +235,7 @@ static void flush_recorded(void)
 static char g_auto_path[64] = "";    /* temporary replay file of INDELGPU_MODE=auto */
 static int32_t* g_replay = NULL;     /* the whole replay file after its header, as 32-bit words */
 static int64_t g_replay_words = 0, g_replay_pos = 0, g_replay_left = 0;
+static int g_replay_loaded = 0;
 
 static void load_replay(void)
 {
@@ -290,6 +291,23 @@ static int fork_recording_run(void)
     return MODE_REPLAY;
 }
 
+/* The operating mode of this process (0 direct, 1 record, 2 replay), decided once -- INDELGPU_MODE=auto
+ * forks here, at the first GPU-bound call of either glue file (host/indelgpu_support.c shares it). */
+int indelgpu_glue_mode(void)
+{
+    if (g_mode < 0) {
+        const char* m = getenv("INDELGPU_MODE");
+        g_mode = (m && strcmp(m, "record") == 0) ? MODE_RECORD : (m && strcmp(m, "replay") == 0) ? MODE_REPLAY : MODE_DIRECT;
+        if (m && strcmp(m, "auto") == 0) g_mode = fork_recording_run();
+    }
+    return g_mode;
+}
+
+/* path of the replay file (INDELGPU_REPLAY_FILE, or the temporary one of auto mode) */
+const char* indelgpu_glue_replay_path(void) { return replay_path(); }
+/* 1 when this process created the replay file itself (auto mode) and should remove it after loading */
+int indelgpu_glue_replay_is_temporary(void) { return g_auto_path[0] != '\0'; }
+
 evidence* attempt_pe_alignment(char** const sequences,
                                const int32_t tid,
                                const int32_t position,
@@ -300,12 +318,7 @@ evidence* attempt_pe_alignment(char** const sequences,
     const char* read = rln->segments->sequence;          /* the single S segment (readaln.c:258-264) */
     const int64_t readlength = (int64_t)strlen(read);
 
-    if (g_mode < 0) {
-        const char* m = getenv("INDELGPU_MODE");
-        g_mode = (m && strcmp(m, "record") == 0) ? MODE_RECORD : (m && strcmp(m, "replay") == 0) ? MODE_REPLAY : MODE_DIRECT;
-        if (m && strcmp(m, "auto") == 0) g_mode = fork_recording_run();
-        if (g_mode == MODE_REPLAY) load_replay();
-    }
+    if (g_replay_loaded == 0 && indelgpu_glue_mode() == MODE_REPLAY) { load_replay(); g_replay_loaded = 1; }
 
     if (g_mode == MODE_REPLAY) {
         if (g_replay_left <= 0 || g_replay_pos + 4 > g_replay_words) fatalf("libindelgpu: replay file exhausted (different command line than the recording run?)");

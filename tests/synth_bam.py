@@ -42,8 +42,10 @@ def _cigar_from_refcoords(rc):
 
 
 def make_dataset(path_prefix, length=1_000_000, depth=20, read_len=150, insert_mean=500.0, insert_sd=50.0,
-                 spacing=2000, max_indel=50, sub_rate=0.01, seed=7, contig="chrS"):
-    """Writes <prefix>.fa, <prefix>.sam, <prefix>.config; returns dict(sites=..., npairs=..., nrecords=...)."""
+                 spacing=2000, max_indel=50, sub_rate=0.01, seed=7, contig="chrS", keep_frac=1.0, read_seed=None):
+    """Writes <prefix>.fa, <prefix>.sam, <prefix>.config; returns dict(sites=..., npairs=..., nrecords=...).
+    keep_frac < 1 plants only that fraction of the sites (same reference, same site list: the "normal" of a
+    tumor/normal pair); read_seed draws different reads from the same genome."""
     rng = np.random.default_rng(seed)
     acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
     ref = acgt[rng.integers(0, 4, size=length)]
@@ -52,13 +54,19 @@ def make_dataset(path_prefix, length=1_000_000, depth=20, read_len=150, insert_m
     spos = 2000 + np.arange(nsites) * spacing + rng.integers(0, spacing // 2, size=nsites)
     slen = rng.integers(1, max_indel + 1, size=nsites)
     sdel = rng.random(nsites) < 0.5
+    ins_all = [acgt[rng.integers(0, 4, size=ln)] for ln in slen]      # drawn for every site so that subsets agree
+    site_kept = np.random.default_rng(seed + 1000).random(nsites) < keep_frac
+    if read_seed is not None:
+        rng = np.random.default_rng(read_seed)
     seq_parts, rc_parts, prev = [], [], 0
-    for p, ln, isdel in zip(spos, slen, sdel):
+    for p, ln, isdel, ins, keep in zip(spos, slen, sdel, ins_all, site_kept):
+        if not keep:
+            continue
         seq_parts.append(ref[prev:p]); rc_parts.append(np.arange(prev, p, dtype=np.int64))
         if isdel:
             prev = p + ln
         else:
-            seq_parts.append(acgt[rng.integers(0, 4, size=ln)]); rc_parts.append(np.full(ln, -1, dtype=np.int64))
+            seq_parts.append(ins); rc_parts.append(np.full(ln, -1, dtype=np.int64))
             prev = p
     seq_parts.append(ref[prev:]); rc_parts.append(np.arange(prev, length, dtype=np.int64))
     samp = np.concatenate(seq_parts); rcmap = np.concatenate(rc_parts)
@@ -163,4 +171,4 @@ def make_dataset(path_prefix, length=1_000_000, depth=20, read_len=150, insert_m
             f.write(line + "\n")
     with open(path_prefix + ".config", "w") as f:
         f.write(f"IL generic {int(insert_mean - 6 * insert_sd)} {int(insert_mean + 4 * insert_sd)}\nRC {contig} {depth}\n")
-    return dict(nsites=int(nsites), ndel=int(sdel.sum()), nins=int((~sdel).sum()), npairs=npairs, nrecords=nrec)
+    return dict(nsites=int(site_kept.sum()), ndel=int((sdel & site_kept).sum()), nins=int((~sdel & site_kept).sum()), npairs=npairs, nrecords=nrec)
