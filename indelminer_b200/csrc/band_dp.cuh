@@ -8,6 +8,7 @@
 // arrays are shared by all levels exactly as in the reference (a child only touches rows below
 // the ones its parent still reads, globalalign.c:280).
 #pragma once
+#include <type_traits>
 
 #include "kernels.cuh"
 
@@ -249,6 +250,8 @@ IG_HD inline void dc_sweep_reg(DcCtx<STRIDE>& x, DcFrame& f)
         if (leftd > 1) leftd--;
         const uint32_t ai = anext;
         if (i < M) anext = a1[i + 1];
+        const int xb = W2 + low + i;                             // new top byte for row i + 1, fetched now, merged below
+        const uint32_t wnew = (xb >= 1 && xb <= N) ? (uint32_t)b1[xb] : 0u;
         x.cells += rightd - leftd + 1;
         int cl = kNeg, el = kNeg;                                // horizontal inputs of the row's first cell
 #pragma unroll
@@ -296,8 +299,7 @@ IG_HD inline void dc_sweep_reg(DcCtx<STRIDE>& x, DcFrame& f)
         }
 #pragma unroll
         for (int k = 0; k < NW; k++) wr[k] = (wr[k] >> 8) | ((k + 1 < NW) ? (wr[k + 1] << 24) : 0u);
-        const int xb = W2 + low + i;                             // new top byte for row i + 1
-        if (xb >= 1 && xb <= N) wr[(W2 - 1) >> 2] |= (uint32_t)b1[xb] << (8 * ((W2 - 1) & 3));
+        wr[(W2 - 1) >> 2] |= wnew << (8 * ((W2 - 1) & 3));
     }
     int k, l;
     int dpr = DP[1], cpr = CP[1];
@@ -437,6 +439,9 @@ IG_HD inline int global_align_script(DcCtx<STRIDE>& x, DcFrame* st, int M, int N
     return x.ns;
 }
 
+// the script of an alignment without gaps: every entry is a replacement
+struct ZeroScript { IG_HD int operator[](int) const { return 0; } };
+
 // fetch_cigar (globalalign.c:507-604): A, B 0-based first ALIGNED symbols
 template <class Script>
 IG_HD inline int script_to_cigar(const uint8_t* A, const uint8_t* B, int M, int N, const Script& S,
@@ -446,6 +451,23 @@ IG_HD inline int script_to_cigar(const uint8_t* A, const uint8_t* B, int M, int 
     const int clip = AP - 1;
     if (clip > 0) cig[n++] = ((uint32_t)clip << 4) | OP_SOFT;
     int run_op = -1, run_len = 0, total = clip, pending = 0;
+    auto emit = [&](int op) {
+        if (run_op != -1 && run_op != op) { cig[n++] = ((uint32_t)run_len << 4) | (uint32_t)run_op; total += run_len; run_len = 0; }
+        run_op = op; run_len++;
+    };
+    if (std::is_same<Script, ZeroScript>::value) {
+        // gap-free script (every entry a replacement, so M == N): nothing to read but the two sequences;
+        // four columns per step with the eight loads issued together, instead of a load-compare chain per base
+        const int L = ig_min(M, N);
+        for (; i + 4 <= L; i += 4) {
+            const uint8_t a0 = A[i], a1 = A[i + 1], a2 = A[i + 2], a3 = A[i + 3];
+            const uint8_t b0 = B[i], b1 = B[i + 1], b2 = B[i + 2], b3 = B[i + 3];
+            emit(a0 == b0 ? OP_EQ : OP_X); emit(a1 == b1 ? OP_EQ : OP_X);
+            emit(a2 == b2 ? OP_EQ : OP_X); emit(a3 == b3 ? OP_EQ : OP_X);
+        }
+        for (; i < L; i++) emit(A[i] == B[i] ? OP_EQ : OP_X);
+        j = i;
+    }
     while (i < M || j < N) {
         int op;
         if (pending == 0 && S[k] == 0) { k++; op = (A[i] == B[j]) ? OP_EQ : OP_X; i++; j++; }
@@ -454,8 +476,7 @@ IG_HD inline int script_to_cigar(const uint8_t* A, const uint8_t* B, int M, int 
             if (pending > 0) { pending--; j++; op = OP_DEL; }
             else             { pending++; i++; op = OP_INS; }
         }
-        if (run_op != -1 && run_op != op) { cig[n++] = ((uint32_t)run_len << 4) | (uint32_t)run_op; total += run_len; run_len = 0; }
-        run_op = op; run_len++;
+        emit(op);
     }
     if (run_op != -1 && run_len > 0) { cig[n++] = ((uint32_t)run_len << 4) | (uint32_t)run_op; total += run_len; }
     if (total < readlength) cig[n++] = ((uint32_t)(readlength - total) << 4) | OP_SOFT;
@@ -502,6 +523,8 @@ IG_HD inline void local_sweeps_reg(const DevParams& P, const uint8_t* read, int 
         const int tlo = ig_max(0, -i - low), thi = ig_min(band - 1, N - i - low);
         const uint32_t ai = anext;
         if (i < ei) anext = read[i];
+        const int xn = i + low + W - 1;                             // new top byte for row i + 1, fetched now, merged below
+        const uint32_t wnew = (xn >= 0 && xn < N) ? (uint32_t)win[xn] : 0u;
         int e = kNeg, left = kNeg;
 #pragma unroll
         for (int t = 0; t < W; t++) {
@@ -519,8 +542,7 @@ IG_HD inline void local_sweeps_reg(const DevParams& P, const uint8_t* read, int 
         cf += thi - tlo + 1;
 #pragma unroll
         for (int k = 0; k < NW; k++) wr[k] = (wr[k] >> 8) | ((k + 1 < NW) ? (wr[k + 1] << 24) : 0u);
-        const int x = i + low + W - 1;                              // new top byte for row i + 1
-        if (x >= 0 && x < N) wr[(W - 1) >> 2] |= (uint32_t)win[x] << (8 * ((W - 1) & 3));
+        wr[(W - 1) >> 2] |= wnew << (8 * ((W - 1) & 3));
     }
     const int endj = endi + low + endt;
     best_o = best; endi_o = endi; endj_o = (best > 0) ? endj : si + low; cf_o = cf;
@@ -553,6 +575,8 @@ IG_HD inline void local_sweeps_reg(const DevParams& P, const uint8_t* read, int 
         const int tlo = ig_max(0, 1 - i - low);
         const uint32_t ai = anext;
         if (i > 1) anext = read[i - 2];
+        const int xn = i + low - 2;                                 // new bottom byte for row i - 1, fetched now, merged below
+        const uint32_t wnew = (xn >= 0 && xn < N) ? (uint32_t)win[xn] : 0u;
         int e = kNeg, right = kNeg;
 #pragma unroll
         for (int t = W - 1; t >= 0; t--) {
@@ -573,8 +597,7 @@ IG_HD inline void local_sweeps_reg(const DevParams& P, const uint8_t* read, int 
         if (!found) cr += ig_max(0, thi - tlo + 1);
 #pragma unroll
         for (int k = NW - 1; k >= 0; k--) wr[k] = (wr[k] << 8) | ((k > 0) ? (wr[k - 1] >> 24) : 0u);
-        const int x = i + low - 2;                                  // new bottom byte for row i - 1
-        if (x >= 0 && x < N) wr[0] |= (uint32_t)win[x];
+        wr[0] |= wnew;
     }
     starti_o = starti; startj_o = starti + low + startt; found_o = found; cr_o = cr;
 }
@@ -597,7 +620,6 @@ struct BandLocal {
 };
 
 // a script of zeros that needs no memory (all-REP alignments)
-struct ZeroScript { IG_HD int operator[](int) const { return 0; } };
 
 // phase 1a: the two sweeps of local_align
 template <int STRIDE>
