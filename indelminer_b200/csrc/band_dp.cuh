@@ -38,8 +38,8 @@ struct BandScratch {
 __host__ __device__ inline long long band_scratch_ints(int max_band, int max_rows)
 {
     // band region: cc dd cp dp (ALIGN), aliased by the two rolling (H, D) rows of local_align
-    // rows region: mp[3] fp | mt[3] ft | script
-    return 4LL * (max_band + 4) + 8LL * (max_rows + 2) + (2LL * max_rows + max_band + 16);
+    // rows region: rec[3] (crossing pointer + type per row and state) | fl (forward link + type) | script
+    return 4LL * (max_band + 4) + 4LL * (max_rows + 2) + (2LL * max_rows + max_band + 16);
 }
 
 
@@ -66,10 +66,15 @@ struct DcCtx {
     const uint8_t* A;        // read slice, 0-based
     const uint8_t* B;        // window, 0-based
     IArr<STRIDE> cc, dd, cp, dp;
-    IArr<STRIDE> mp[3], mt[3], fp, ft;
+    // crossing records of align() (MP/MT, FP/FT of globalalign.c:33-36), a row index (>= -1) and a path type
+    // (0..2) packed in one int each: the D&C chases these pointers through memory, so bytes are latency
+    IArr<STRIDE> rec[3], fl;
     IArr<STRIDE> S; int ns; int last;
     int cells;
 };
+IG_HD inline int dc_pack(int ptr, int type) { return ((ptr + 1) << 2) | type; }
+IG_HD inline int dc_ptr(int packed) { return (packed >> 2) - 1; }
+IG_HD inline int dc_type(int packed) { return packed & 3; }
 
 template <int STRIDE>
 IG_HD inline void put_del(DcCtx<STRIDE>& x, int k)      // globalalign.c:40-46
@@ -105,15 +110,15 @@ IG_HD inline void dc_sweep(DcCtx<STRIDE>& x, DcFrame& f)
     if (leftd < midd) {
         for (int j = 0; j < midd; j++) CP[j] = DP[j] = -1;
         for (int j = midd; j <= rightd; j++) CP[j] = DP[j] = 0;
-        x.mp[0][0] = x.mp[1][0] = x.mp[2][0] = -1;
+        x.rec[0][0] = x.rec[1][0] = x.rec[2][0] = dc_pack(-1, 0);
     } else if (leftd > midd) {
         const int fr = leftd - midd;
         for (int j = 0; j <= midd; j++) CP[j] = DP[j] = fr;
         for (int j = midd + 1; j <= rightd; j++) CP[j] = DP[j] = -1;
-        x.mp[0][fr] = x.mp[1][fr] = x.mp[2][fr] = -1;
+        x.rec[0][fr] = x.rec[1][fr] = x.rec[2][fr] = dc_pack(-1, 0);
     } else {
         for (int j = 0; j <= rightd; j++) CP[j] = DP[j] = 0;
-        x.mp[0][0] = x.mp[1][0] = x.mp[2][0] = -1;
+        x.rec[0][0] = x.rec[1][0] = x.rec[2][0] = dc_pack(-1, 0);
     }
     CC[leftd] = 0;
     {
@@ -159,20 +164,20 @@ IG_HD inline void dc_sweep(DcCtx<STRIDE>& x, DcFrame& f)
                 CC[q] = c; DD[q] = d;
             } else {
                 int open = c - m; e -= h;
-                if (open > e) { e = open; x.mp[1][i] = CP[q - 1]; }
-                else          { x.mp[1][i] = IP; }
-                x.mt[1][i] = 2;
+                int mp0, mt0, mp1, mt1 = 2, mp2, mt2 = 1;
+                if (open > e) { e = open; mp1 = CP[q - 1]; }
+                else          { mp1 = IP; }
                 open = CC[q + 1] - m; d = DD[q + 1] - h;
-                if (open > d) { d = open; x.mp[2][i] = CP[q + 1]; }
-                else          { x.mp[2][i] = DP[q + 1]; }
-                x.mt[2][i] = 1;
+                if (open > d) { d = open; mp2 = CP[q + 1]; }
+                else          { mp2 = DP[q + 1]; }
                 c = CC[q] + sub;
                 if (c < d || c < e) {
-                    if (e > d) { c = e; x.mp[0][i] = x.mp[1][i]; x.mt[0][i] = 2; }
-                    else       { c = d; x.mp[0][i] = x.mp[2][i]; x.mt[0][i] = 1; }
-                } else { x.mp[0][i] = i - 1; x.mt[0][i] = 0; }
-                if (c - g > e) { x.mp[1][i] = x.mp[0][i]; x.mt[1][i] = x.mt[0][i]; }
-                if (c - g > d) { x.mp[2][i] = x.mp[0][i]; x.mt[2][i] = x.mt[0][i]; }
+                    if (e > d) { c = e; mp0 = mp1; mt0 = 2; }
+                    else       { c = d; mp0 = mp2; mt0 = 1; }
+                } else { mp0 = i - 1; mt0 = 0; }
+                if (c - g > e) { mp1 = mp0; mt1 = mt0; }
+                if (c - g > d) { mp2 = mp0; mt2 = mt0; }
+                x.rec[0][i] = dc_pack(mp0, mt0); x.rec[1][i] = dc_pack(mp1, mt1); x.rec[2][i] = dc_pack(mp2, mt2);
                 CP[q] = DP[q] = IP = i;
                 CC[q] = c; DD[q] = d;
             }
@@ -185,14 +190,14 @@ IG_HD inline void dc_sweep(DcCtx<STRIDE>& x, DcFrame& f)
     if (rmid > N - M) l = 2; else if (rmid < N - M) l = 1;
     int r = -1;
     while (k > -1) {
-        x.fp[k] = r; x.ft[k] = l;
+        x.fl[k] = dc_pack(r, l);
         r = k;
-        const int nk = x.mp[l][r], nl = x.mt[l][r];
-        k = nk; l = nl;
+        const int nxt = x.rec[l][r];
+        k = dc_ptr(nxt); l = dc_type(nxt);
     }
     f.rmid = rmid;
     f.k = r;
-    if (r != -1) { f.l = x.fp[r]; f.kt = x.ft[r]; }
+    if (r != -1) { const int v = x.fl[r]; f.l = dc_ptr(v); f.kt = dc_type(v); }
     f.t2 = up - rmid - 1; f.t3 = low - rmid + 1;
 }
 
@@ -230,8 +235,8 @@ IG_HD inline void dc_sweep_reg(DcCtx<STRIDE>& x, DcFrame& f)
             else if (j > leftd && j <= rightd) { cc = t0 - h * (j - leftd); dd = cc - g; }
             CC[j] = cc; DD[j] = dd;
         }
-        if (leftd < midd || leftd == midd) x.mp[0][0] = x.mp[1][0] = x.mp[2][0] = -1;
-        else x.mp[0][fr] = x.mp[1][fr] = x.mp[2][fr] = -1;
+        if (leftd < midd || leftd == midd) x.rec[0][0] = x.rec[1][0] = x.rec[2][0] = dc_pack(-1, 0);
+        else x.rec[0][fr] = x.rec[1][fr] = x.rec[2][fr] = dc_pack(-1, 0);
     }
     int c = 0, d = 0, e = 0;                                     // values of the last cell of the last row
     // the row's W2 bytes of B in a byte-shifted register window: byte q - 1 = B[q + low - 1 + i] (0 outside 1..N)
@@ -286,9 +291,7 @@ IG_HD inline void dc_sweep_reg(DcCtx<STRIDE>& x, DcFrame& f)
                     else                { mp0 = i - 1; mt0 = 0; }
                     if (cn - g > en) { mp1 = mp0; mt1 = mt0; }
                     if (cn - g > dn) { mp2 = mp0; mt2 = mt0; }
-                    x.mp[0][i] = mp0; x.mt[0][i] = mt0;
-                    x.mp[1][i] = mp1; x.mt[1][i] = mt1;
-                    x.mp[2][i] = mp2; x.mt[2][i] = mt2;
+                    x.rec[0][i] = dc_pack(mp0, mt0); x.rec[1][i] = dc_pack(mp1, mt1); x.rec[2][i] = dc_pack(mp2, mt2);
                 }
                 IP = first ? cpn : ipn;                          // :164 IP = CP[leftd] ; else the carried insert pointer
                 if (q == midd) { cpn = i; IP = i; DP[q] = i; } else DP[q] = dpn;
@@ -311,14 +314,14 @@ IG_HD inline void dc_sweep_reg(DcCtx<STRIDE>& x, DcFrame& f)
     if (rmid > N - M) l = 2; else if (rmid < N - M) l = 1;
     int r = -1;
     while (k > -1) {
-        x.fp[k] = r; x.ft[k] = l;
+        x.fl[k] = dc_pack(r, l);
         r = k;
-        const int nk = x.mp[l][r], nl = x.mt[l][r];
-        k = nk; l = nl;
+        const int nxt = x.rec[l][r];
+        k = dc_ptr(nxt); l = dc_type(nxt);
     }
     f.rmid = rmid;
     f.k = r;
-    if (r != -1) { f.l = x.fp[r]; f.kt = x.ft[r]; }
+    if (r != -1) { const int v = x.fl[r]; f.l = dc_ptr(v); f.kt = dc_type(v); }
     f.t2 = up - rmid - 1; f.t3 = low - rmid + 1;
 }
 
@@ -372,7 +375,7 @@ IG_HD inline void dc_align(DcCtx<STRIDE>& x, DcFrame* st, int a0, int b0, int M0
         case 3: {
             if (f.l > -1) {                                  // :280-293
                 const int t1 = f.l - f.k - 1;
-                if (f.kt == 0) { put_rep(x); f.k = f.l; f.l = x.fp[f.k]; f.kt = x.ft[f.k]; }
+                if (f.kt == 0) { put_rep(x); f.k = f.l; { const int v = x.fl[f.k]; f.l = dc_ptr(v); f.kt = dc_type(v); } }
                 else if (f.kt == 1) {
                     put_ins(x, 1); f.stage = 4;
                     dc_push(st, sp, f.a + f.k, f.b + f.k + f.rmid + 1, t1, t1, 0, ig_min(t1, f.t2), 2, 1);
@@ -394,8 +397,8 @@ IG_HD inline void dc_align(DcCtx<STRIDE>& x, DcFrame* st, int a0, int b0, int M0
             }
             break;
         }
-        case 4: put_del(x, 1); f.k = f.l; f.l = x.fp[f.k]; f.kt = x.ft[f.k]; f.stage = 3; break;   // :286
-        case 5: put_ins(x, 1); f.k = f.l; f.l = x.fp[f.k]; f.kt = x.ft[f.k]; f.stage = 3; break;   // :291
+        case 4: put_del(x, 1); f.k = f.l; { const int v = x.fl[f.k]; f.l = dc_ptr(v); f.kt = dc_type(v); } f.stage = 3; break;   // :286
+        case 5: put_ins(x, 1); f.k = f.l; { const int v = x.fl[f.k]; f.l = dc_ptr(v); f.kt = dc_type(v); } f.stage = 3; break;   // :291
         default: sp--; break;
         }
     }
@@ -445,7 +448,7 @@ struct ZeroScript { IG_HD int operator[](int) const { return 0; } };
 // fetch_cigar (globalalign.c:507-604): A, B 0-based first ALIGNED symbols
 template <class Script>
 IG_HD inline int script_to_cigar(const uint8_t* A, const uint8_t* B, int M, int N, const Script& S,
-                                 int AP, int readlength, uint32_t* cig)
+                                 int AP, int readlength, uint32_t* cig, int ns = 0)
 {
     int n = 0, i = 0, j = 0, k = 0;
     const int clip = AP - 1;
@@ -469,6 +472,19 @@ IG_HD inline int script_to_cigar(const uint8_t* A, const uint8_t* B, int M, int 
         j = i;
     }
     while (i < M || j < N) {
+        // four replacements at a time when the script says so (`ns` = its length, 0 = unknown): the script
+        // lives in memory the D&C just wrote, and one round trip for twelve loads beats twelve round trips
+        if (pending == 0 && k + 4 <= ns && i + 4 <= M && j + 4 <= N) {
+            const int s0 = S[k], s1 = S[k + 1], s2 = S[k + 2], s3 = S[k + 3];
+            const uint8_t a0 = A[i], a1 = A[i + 1], a2 = A[i + 2], a3 = A[i + 3];
+            const uint8_t b0 = B[j], b1 = B[j + 1], b2 = B[j + 2], b3 = B[j + 3];
+            if ((s0 | s1 | s2 | s3) == 0) {
+                emit(a0 == b0 ? OP_EQ : OP_X); emit(a1 == b1 ? OP_EQ : OP_X);
+                emit(a2 == b2 ? OP_EQ : OP_X); emit(a3 == b3 ? OP_EQ : OP_X);
+                k += 4; i += 4; j += 4;
+                continue;
+            }
+        }
         int op;
         if (pending == 0 && S[k] == 0) { k++; op = (A[i] == B[j]) ? OP_EQ : OP_X; i++; j++; }
         else {
@@ -609,7 +625,7 @@ IG_HD inline void local_sweeps_reg(const DevParams& P, const uint8_t* read, int 
 // few gapped alignments would otherwise serialise against the many that finish after phase 1.
 // `low`/`up` are already clamped (localalign.c:70-71).
 //   bands : 4 * (max_band + 4) ints (shared memory when it fits, else the head of the global slice)
-//   rowsb : 8 * (max_rows + 2) ints + the script
+//   rowsb : 4 * (max_rows + 2) ints + the script
 // ---------------------------------------------------------------------------------------
 // an alignment waiting for its ALIGN phase (banded_two_phase_loop)
 struct DcTask { int idx, best, endi, endj, starti, startj; };
@@ -759,13 +775,12 @@ IG_HD inline void band_global(const DevParams& P, IArr<STRIDE> bands, IArr<STRID
     DcCtx<STRIDE> x;
     x.P = &P; x.cells = 0; x.ns = 0; x.last = 0;
     x.cc = bands; x.dd = bands + wb; x.cp = bands + 2 * wb; x.dp = bands + 3 * wb;
-    x.mp[0] = rowsb; x.mp[1] = rowsb + wr; x.mp[2] = rowsb + 2 * wr; x.fp = rowsb + 3 * wr;
-    x.mt[0] = rowsb + 4 * wr; x.mt[1] = rowsb + 5 * wr; x.mt[2] = rowsb + 6 * wr; x.ft = rowsb + 7 * wr;
-    x.S = rowsb + 8 * wr;
+    x.rec[0] = rowsb; x.rec[1] = rowsb + wr; x.rec[2] = rowsb + 2 * wr; x.fl = rowsb + 3 * wr;
+    x.S = rowsb + 4 * wr;
     const int M2 = L.endi - L.starti + 1, N2 = L.endj - L.startj + 1;
     x.A = read + L.starti - 1; x.B = win + L.startj - 1;
     global_align_script(x, st, M2, N2, low - (L.startj - L.starti), up - (L.startj - L.starti));
-    *ncig = script_to_cigar(x.A, x.B, M2, N2, x.S, L.starti, M, cig);
+    *ncig = script_to_cigar(x.A, x.B, M2, N2, x.S, L.starti, M, cig, x.ns);
     *cells_glob = x.cells; *nscript = x.ns;
 }
 
@@ -781,7 +796,7 @@ IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> bands, IA
     if (!L.none) {
         if (band_unique_diagonal(P, read, M, win, low, up, L, cig, &n, &cg)) {
             ns = L.endi - L.starti + 1;
-            const IArr<STRIDE> S = rowsb + 8 * (max_rows + 2);
+            const IArr<STRIDE> S = rowsb + 4 * (max_rows + 2);
             for (int i = 0; i < ns; i++) S[i] = 0;
         } else {
             band_global<STRIDE>(P, bands, rowsb, max_band, max_rows, st, read, M, win, low, up, L, cig, &n, &cg, &ns);

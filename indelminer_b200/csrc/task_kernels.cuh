@@ -213,7 +213,7 @@ band_tasks_kernel(const __grid_constant__ TaskArgs a)
         cg += (unsigned long long)cells;
         if (a.script) {
             int32_t* so = a.script + (int64_t)idx * a.script_stride;
-            const IArr<32> S = rowsb + 8 * (a.scratch.max_rows + 2);
+            const IArr<32> S = rowsb + 4 * (a.scratch.max_rows + 2);
             for (int u = 0; u < min(ns, a.script_stride); u++) so[u] = S[u];
             if (ns < a.script_stride) so[ns] = 0x7FFFFFFF;
         }
@@ -243,8 +243,7 @@ __global__ void global_align_one_kernel(DevParams P, BandScratch scr, const uint
     x.P = &P; x.A = A; x.B = B; x.cells = 0;
     x.cc = base; x.dd = base + wb; x.cp = base + 2 * wb; x.dp = base + 3 * wb;
     const IArr<1> rows = base + 4 * wb;
-    x.mp[0] = rows; x.mp[1] = rows + wr; x.mp[2] = rows + 2 * wr; x.fp = rows + 3 * wr;
-    x.mt[0] = rows + 4 * wr; x.mt[1] = rows + 5 * wr; x.mt[2] = rows + 6 * wr; x.ft = rows + 7 * wr;
+    x.rec[0] = rows; x.rec[1] = rows + wr; x.rec[2] = rows + 2 * wr; x.fl = rows + 3 * wr;
     x.S = IArr<1>{out_script};
     DcFrame st[kDcFrames];
     const int ns = global_align_script(x, st, M, N, low, up);

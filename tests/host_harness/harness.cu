@@ -21,7 +21,7 @@ extern "C" int hh_band_align(const int* prm, const uint8_t* read, int M, const u
     std::vector<int> scratch((size_t)band_scratch_ints(mb, M));
     DcFrame st[kDcFrames];
     align_banded_serial<1>(P, IArr<1>{scratch.data()}, IArr<1>{scratch.data() + 4 * (mb + 4)}, mb, M, st, read, M, win, N, lo, hi, cig, out10);
-    const int* S = scratch.data() + 4 * (mb + 4) + 8 * (M + 2);
+    const int* S = scratch.data() + 4 * (mb + 4) + 4 * (M + 2);
     for (int t = 0; t < out10[9] && t < script_cap; t++) script[t] = S[t];
     return 0;
 }
@@ -41,7 +41,7 @@ extern "C" int hh_band_align_interleaved(const int* prm, const uint8_t* read, in
     DcFrame st[kDcFrames];
     const IArr<32> base{scratch.data() + lane};
     align_banded_serial<32>(P, base, base + 4 * (mb + 4), mb, M, st, read, M, win, N, lo, hi, cig, out10);
-    const IArr<32> S = base + 4 * (mb + 4) + 8 * (M + 2);
+    const IArr<32> S = base + 4 * (mb + 4) + 4 * (M + 2);
     for (int t = 0; t < out10[9] && t < script_cap; t++) script[t] = S[t];
     // the other 31 lanes' elements must be untouched
     for (size_t i = 0; i < scratch.size(); i++) if ((int)(i & 31) != lane && scratch[i] != 0x5A5A5A5A) return -2;
