@@ -371,6 +371,16 @@ def run_ours(a, rank, world, local_rank):
                                else "pipe_vote / pipe_dp / pipe_combine (5 launches per step; time = whole step)",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_s * 1e3, "peak_source": peak_src},
     }
+    if a.numgaps == 0 and clocks.get("sm_mhz"):
+        # why the HBM fraction is small: the kernel is bound by instruction issue (k-mer vote), not by bytes.
+        # Executed warp instructions per read come from the committed ncu capture; the rate is measured here.
+        sms = R.sm_count
+        peak_issue = sms * 4 * clocks["sm_mhz"] * 1e6                     # 4 schedulers per SM, 1 warp instruction / clk each
+        line["roofline"]["issue"] = {
+            "warp_instr_per_read": NCU_WARP_INSTR_PER_READ, "source": "profiles/r01_v5_realign_kernel_by_region.txt (ncu)",
+            "achieved_gwarp_instr_s": NCU_WARP_INSTR_PER_READ * (n / kernel_s) / 1e9,
+            "peak_gwarp_instr_s": peak_issue / 1e9,
+            "frac": NCU_WARP_INSTR_PER_READ * (n / kernel_s) / peak_issue}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof) and a.numgaps == 0 and a.reads == 1 << 20:
         try:
@@ -432,6 +442,7 @@ def run_band(a, R, L, torch, dev, peak, peak_src):
     print(json.dumps(line), flush=True)
 
 
+NCU_WARP_INSTR_PER_READ = 4704  # realign_kernel: 4 932 500 669 executed warp instructions / 1 048 576 reads (ncu, r01 v5)
 SUPPORT_OPS_PER_CELL = 26      # integer instructions per DP cell of the wavefront kernel (SASS count)
 
 
@@ -441,17 +452,19 @@ def run_support(a, R, L, torch):
     issue rate measured here, and the oracle's C port timed on a sample of the same pairs."""
     from indelminer_b200 import synth
     t = synth.make_support_tasks(a.tasks)
-    packed = (t["targets"], t["target_off"], t["queries"], t["query_off"])
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()      # noqa: E731  (host buffers, pinned)
+    packed = (pin(t["targets"]), pin(t["target_off"]), pin(t["queries"]), pin(t["query_off"]))
+    outbuf = tuple(pin(np.zeros(a.tasks, dtype=np.int32)) for _ in range(3))
     gops = C.c_double(0)
     if L.indelgpu_int32_peak(R._ctx, C.byref(gops)) != 0:
         raise RuntimeError(_liberr())
     for _ in range(a.warmup):
-        out = R.indel_support_batch(None, None, packed=packed)
+        out = R.indel_support_batch(None, None, packed=packed, out=outbuf)
     torch.cuda.synchronize()
     kms, wall = [], []
     for _ in range(a.steps):
         t0 = time.perf_counter()
-        out = R.indel_support_batch(None, None, packed=packed)
+        out = R.indel_support_batch(None, None, packed=packed, out=outbuf)
         wall.append(time.perf_counter() - t0)
         kms.append(L.indelgpu_last_kernel_ms(R._ctx))
     cells = int(out["cells"])

@@ -226,10 +226,11 @@ class Realigner:
             cells.ctypes.data))
         return dict(score=score, ends=ends, ncigar=ncig, cigar=cig, script=script, cells=cells)
 
-    def indel_support_batch(self, targets, queries, packed=None):
+    def indel_support_batch(self, targets, queries, packed=None, out=None):
         """Batched realign_with_indel (variant.c:1246-1424) on already built targets (the reference interval
         with the variant spliced in, variant.c:1259-1275) and query slices (read[qstart:qstop], :1278-1283).
-        `packed` = (target bytes, target_off, query bytes, query_off) skips the packing.
+        `packed` = (target bytes, target_off, query bytes, query_off) skips the packing; `out` = three int32[n]
+        arrays to receive the counters (pinned host memory makes both directions asynchronous copies).
         Returns dict(subs, indels, aligned: int32[n]; cells: sum of len1 * len2)."""
         if packed is not None:
             tb, toff, qb, qoff = packed
@@ -241,7 +242,7 @@ class Realigner:
             qb, qoff = pack_sequences(queries)
         tb = tb if tb.size else np.zeros(1, dtype=np.uint8)
         qb = qb if qb.size else np.zeros(1, dtype=np.uint8)
-        subs, indels, aligned = (np.zeros(n, dtype=np.int32) for _ in range(3))
+        subs, indels, aligned = out if out is not None else (np.zeros(n, dtype=np.int32) for _ in range(3))
         cells = C.c_int64(0)
         _check(self._L.indelgpu_indel_support_batch(
             self._ctx, n, tb.ctypes.data, toff.ctypes.data, qb.ctypes.data, qoff.ctypes.data,

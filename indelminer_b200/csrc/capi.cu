@@ -102,7 +102,7 @@ struct indelgpu_ctx {
     DevBuf out_status, out_nseg, out_rstart, out_segoff, out_segs, out_detail, out_cig1, out_cig2;
     DevBuf counters;         // bytes: 0 work counter (int) | 8 seg count (u64) | 16 cells (3 x u64) | 40 error flag (int) | 48 algorithmic bytes (u64)
     DevBuf scratch;
-    DevBuf s_tgt, s_toff, s_qry, s_qoff, s_out, s_idx, s_V, s_I, s_F;   // known-indel support check (indel_support.cuh)
+    DevBuf s_tgt, s_toff, s_qry, s_qoff, s_out, s_ord, s_idx, s_V, s_I, s_F;   // known-indel support check (indel_support.cuh)
     DevBuf p_low, p_aln, p_cig, p_plan, p_flags;      // intermediates of the banded pipeline (realign_pipeline.cuh)
     // task API staging
     DevBuf t_reads, t_roff, t_refs, t_woff, t_packed, t_anchor, t_low, t_up, t_score, t_ends, t_ncig, t_cig, t_script;
@@ -180,7 +180,7 @@ extern "C" void indelgpu_destroy(indelgpu_ctx* c)
                      &c->in_pos, &c->in_rng, &c->out_status, &c->out_nseg, &c->out_rstart, &c->out_segoff,
                      &c->out_segs, &c->out_detail, &c->out_cig1, &c->out_cig2, &c->counters, &c->scratch,
                      &c->p_low, &c->p_aln, &c->p_cig, &c->p_plan, &c->p_flags,
-                     &c->s_tgt, &c->s_toff, &c->s_qry, &c->s_qoff, &c->s_out, &c->s_idx, &c->s_V, &c->s_I, &c->s_F,
+                     &c->s_tgt, &c->s_toff, &c->s_qry, &c->s_qoff, &c->s_out, &c->s_ord, &c->s_idx, &c->s_V, &c->s_I, &c->s_F,
                      &c->t_reads, &c->t_roff, &c->t_refs, &c->t_woff, &c->t_packed, &c->t_anchor, &c->t_low,
                      &c->t_up, &c->t_score, &c->t_ends, &c->t_ncig, &c->t_cig, &c->t_script};
     for (DevBuf* b : all) b->release();
@@ -830,44 +830,63 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
     if (n == 0) return 0;
     CU(cudaSetDevice(c->device));
     if (h_target_off[0] != 0 || h_query_off[0] != 0) return fail(INDELGPU_EINVAL, "offset arrays must start at 0");
-    // pairs the wavefront kernel's packing holds go there (all real reads); the rest, one pair per thread
+    // pairs the wavefront kernel's packing holds go there (all real reads), in three classes by target length
+    // (8, 16 or 32 lanes per pair) and sorted by that length inside a class; the rest, one pair per thread
     std::vector<int32_t> slow;
-    int max1 = 0, max2 = 0, fast1 = 0;
+    int max1 = 0, max2 = 0;
     long long cells = 0;
+    std::vector<int32_t> bucket(kWaveMaxTarget + 2, 0);
     for (int i = 0; i < n; i++) {
         const int64_t l1 = h_target_off[i + 1] - h_target_off[i], l2 = h_query_off[i + 1] - h_query_off[i];
         if (l1 < 0 || l2 < 0 || l1 > 8000 || l2 > 8000) return fail(INDELGPU_ELIMIT, "task %d: lengths %lld x %lld outside 0..8000", i, (long long)l1, (long long)l2);
         cells += l1 * l2;
         if (l1 > kWaveMaxTarget || l2 > kWaveMaxQuery) { slow.push_back(i); max1 = std::max(max1, (int)l1); max2 = std::max(max2, (int)l2); }
-        else fast1 = std::max(fast1, (int)l1);
+        else bucket[l1 + 1]++;
     }
-    const int nslow = (int)slow.size();
+    const int nslow = (int)slow.size(), nfast = n - nslow;
+    for (int l = 0; l <= kWaveMaxTarget; l++) bucket[l + 1] += bucket[l];                 // counting sort by target length
+    const int class_end[3] = {bucket[128 + 1], bucket[256 + 1], bucket[kWaveMaxTarget + 1]};   // <= 128 | <= 256 | <= 512 bases
+    std::vector<int32_t> order((size_t)std::max(nfast, 1));
+    {
+        std::vector<int32_t> at(bucket.begin(), bucket.end() - 1);
+        for (int i = 0; i < n; i++) {
+            const int64_t l1 = h_target_off[i + 1] - h_target_off[i], l2 = h_query_off[i + 1] - h_query_off[i];
+            if (l1 <= kWaveMaxTarget && l2 <= kWaveMaxQuery) order[at[l1]++] = i;
+        }
+    }
     const int64_t nt = h_target_off[n], nq = h_query_off[n];
     cudaStream_t st = c->stream;
     if (c->s_tgt.ensure((size_t)nt + 16) || c->s_toff.ensure(8 * (size_t)(n + 1)) || c->s_qry.ensure((size_t)nq + 16) ||
-        c->s_qoff.ensure(8 * (size_t)(n + 1)) || c->s_out.ensure(12 * (size_t)n)) return INDELGPU_ENOMEM;
+        c->s_qoff.ensure(8 * (size_t)(n + 1)) || c->s_out.ensure(12 * (size_t)n) || c->s_ord.ensure(4 * (size_t)std::max(nfast, 1))) return INDELGPU_ENOMEM;
     if (nt > 0) CU(cudaMemcpyAsync(c->s_tgt.p, h_targets, (size_t)nt, cudaMemcpyHostToDevice, st));
     if (nq > 0) CU(cudaMemcpyAsync(c->s_qry.p, h_queries, (size_t)nq, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->s_toff.p, h_target_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->s_qoff.p, h_query_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    if (nfast > 0) CU(cudaMemcpyAsync(c->s_ord.p, order.data(), 4 * (size_t)nfast, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
     int32_t* d_subs = c->s_out.as<int32_t>();
     int32_t* d_indels = d_subs + n;
     int32_t* d_aligned = d_indels + n;
     CU(cudaEventRecord(c->ev_t0, st));
-    if (nslow < n) {
+    for (int cls = 0; cls < 3; cls++) {
+        const int first = cls ? class_end[cls - 1] : 0, cnt = class_end[cls] - first;
+        if (cnt <= 0) continue;
         WaveArgs w;
-        w.n = n;
+        w.n = cnt;
+        w.order = c->s_ord.as<int32_t>() + first;
         w.targets = c->s_tgt.as<uint8_t>(); w.target_off = c->s_toff.as<int64_t>();
         w.queries = c->s_qry.as<uint8_t>(); w.query_off = c->s_qoff.as<int64_t>();
         w.subs = d_subs; w.indels = d_indels; w.aligned = d_aligned;
+        const int group = cls == 0 ? 4 : cls == 1 ? 2 : 1;                  // pairs per warp
         int occ = 0;
-        if (fast1 <= 256) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, indel_support_wave_kernel<8>, 128, 0));
-        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, indel_support_wave_kernel<16>, 128, 0));
+        if (cls == 0) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, indel_support_wave_kernel<8>, 128, 0));
+        else if (cls == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, indel_support_wave_kernel<16>, 128, 0));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, indel_support_wave_kernel<32>, 128, 0));
         if (occ < 1) return fail(INDELGPU_ELIMIT, "support kernel does not fit on an SM");
-        const int blocks = (int)std::min<long long>((long long)c->sms * occ, ((long long)n + 3) / 4);
-        if (fast1 <= 256) indel_support_wave_kernel<8><<<blocks, 128, 0, st>>>(w);
-        else indel_support_wave_kernel<16><<<blocks, 128, 0, st>>>(w);
+        const int blocks = (int)std::min<long long>((long long)c->sms * occ, ((long long)cnt + 4 * group - 1) / (4 * group));
+        if (cls == 0) indel_support_wave_kernel<8><<<blocks, 128, 0, st>>>(w);
+        else if (cls == 1) indel_support_wave_kernel<16><<<blocks, 128, 0, st>>>(w);
+        else indel_support_wave_kernel<32><<<blocks, 128, 0, st>>>(w);
         c->launches++;
         CU(cudaGetLastError());
     }

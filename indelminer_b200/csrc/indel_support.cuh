@@ -3,7 +3,8 @@
 //
 // Two kernels.
 //  * indel_support_wave_kernel -- the one that runs for real reads (target <= 512, query <= 500 bases).
-//    One WARP per (target, query) pair.  Lane l owns CPL consecutive target columns and sweeps the rows as
+//    A segment of 8, 16 or 32 lanes per (target, query) pair (4, 2 or 1 pairs per warp, by target length).
+//    Lane l of the segment owns CPL consecutive target columns and sweeps the rows as
 //    a wavefront (lane l works on row s - l + 1 at step s); its slice of the previous row, of F and of the
 //    path counters lives in registers, the row boundary travels to the right-hand lane with two shuffles
 //    per step.  The reference fills a score matrix and a direction matrix and then walks back from the
@@ -119,14 +120,18 @@ enum { kWaveMaxTarget = 512, kWaveMaxQuery = 500 };
 // path counters packed in one word: aligned columns (<= 500) | substitutions (<= 500) | gap columns (<= 1012)
 enum { kAln1 = 1, kSub1 = 1 << 9, kInd1 = 1 << 18 };
 
-template <int CPL>
+// One wavefront of SEG lanes (8, 16 or 32; a warp runs 32 / SEG pairs side by side, each on its own
+// segment of lanes): a short target on all 32 lanes would leave most of them without a column and pay
+// 31 steps of pipeline fill for nothing.
+template <int CPL, int SEG>
 __device__ __forceinline__ void support_wavefront(const uint8_t* __restrict__ t1, int len1,
                                                   const uint8_t* __restrict__ t2, int len2, int lane,
                                                   int& best_out, int& pos_out, int& c_out)
 {
     const unsigned FULL = 0xFFFFFFFFu;
     int araw[CPL], aup[CPL], V[CPL], F[CPL], Cn[CPL];
-    const int j0 = lane * CPL;                         // this lane owns columns j0+1 .. j0+CPL
+    const int li = lane & (SEG - 1);                   // lane within the segment
+    const int j0 = li * CPL;                           // this lane owns columns j0+1 .. j0+CPL
 #pragma unroll
     for (int c = 0; c < CPL; c++) {
         const int j = j0 + c;
@@ -139,19 +144,20 @@ __device__ __forceinline__ void support_wavefront(const uint8_t* __restrict__ t1
     int best = 0, bestpos = 0, bestC = 0;
     int vdiag = -4 - j0, cdiag = 0;                    // V and C of (row - 1, j0) for the row this lane does next
     unsigned out_pk = 0; int out_c = 0;                // boundary handed to lane + 1: V:12 | E:12 | query base:8, and C
-    const int nl = (len1 + CPL - 1) / CPL;             // lanes that own a column
+    const int nl = (len1 + CPL - 1) / CPL;             // lanes of the segment that own a column
     const int steps = (len1 > 0 && len2 > 0) ? len2 + nl - 1 : 0;
+    const int wsteps = __reduce_max_sync(FULL, steps); // the segments of a warp step together
     unsigned qreg = 0;
 #pragma unroll 1
-    for (int s = 0; s < steps; s++) {
-        if ((s & 31) == 0) qreg = (s + lane < len2) ? t2[s + lane] : 0;
-        const unsigned b0 = __shfl_sync(FULL, qreg, s & 31);
-        const unsigned in_pk = __shfl_up_sync(FULL, out_pk, 1);
-        const int in_c = __shfl_up_sync(FULL, out_c, 1);
-        const int i = s - lane + 1;
-        if (i >= 1 && i <= len2 && lane < nl) {
+    for (int s = 0; s < wsteps; s++) {
+        if ((s & (SEG - 1)) == 0) qreg = (s + li < len2) ? t2[s + li] : 0;
+        const unsigned b0 = __shfl_sync(FULL, qreg, s & (SEG - 1), SEG);
+        const unsigned in_pk = __shfl_up_sync(FULL, out_pk, 1, SEG);
+        const int in_c = __shfl_up_sync(FULL, out_c, 1, SEG);
+        const int i = s - li + 1;
+        if (i >= 1 && i <= len2 && li < nl) {
             int left, E, cleft; unsigned braw;
-            if (lane == 0) { left = -4 - i; E = 0; cleft = 0; braw = b0; }          // V[i][0]; E restarts per row
+            if (li == 0) { left = -4 - i; E = 0; cleft = 0; braw = b0; }            // V[i][0]; E restarts per row
             else { left = (int)in_pk >> 20; E = (int)(in_pk << 12) >> 20; braw = in_pk & 0xFFu; cleft = in_c; }
             const int bup = up_case((int)braw);
             int diag = vdiag, cd = cdiag;
@@ -182,40 +188,57 @@ __device__ __forceinline__ void support_wavefront(const uint8_t* __restrict__ t1
 }
 
 struct WaveArgs {
-    int n;
+    int n;                 // pairs in `order`
+    const int32_t* order;  // pair indices of this launch, sorted by target length (neighbours share a tile width)
     const uint8_t* targets; const int64_t* target_off;
     const uint8_t* queries; const int64_t* query_off;
     int32_t* subs; int32_t* indels; int32_t* aligned;
 };
 
-template <int MAXCPL>
-__global__ void __launch_bounds__(128, MAXCPL <= 8 ? 5 : 3)
+template <int SEG>
+__global__ void __launch_bounds__(128, 3)
 indel_support_wave_kernel(const __grid_constant__ WaveArgs a)
 {
+    constexpr int GROUP = 32 / SEG;                    // pairs per warp and pass
     const int lane = threadIdx.x & 31;
+    const int seg = lane / SEG;
     const long long gwarp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long idx = gwarp; idx < a.n; idx += nwarps) {
-        const uint8_t* t1 = a.targets + a.target_off[idx];
-        const uint8_t* t2 = a.queries + a.query_off[idx];
-        const int len1 = (int)(a.target_off[idx + 1] - a.target_off[idx]);
-        const int len2 = (int)(a.query_off[idx + 1] - a.query_off[idx]);
-        if (len1 > 32 * MAXCPL || len1 > kWaveMaxTarget || len2 > kWaveMaxQuery) continue;   // left to the thread-per-pair kernel
+    for (long long base = gwarp * GROUP; base < a.n; base += nwarps * GROUP) {
+        const long long k = base + seg;
+        const bool have = k < a.n;
+        const long long idx = have ? a.order[k] : 0;
+        const uint8_t* t1 = a.targets; const uint8_t* t2 = a.queries;
+        int len1 = 0, len2 = 0;
+        if (have) {
+            const int64_t to = a.target_off[idx], qo = a.query_off[idx];
+            t1 += to; t2 += qo;
+            len1 = (int)(a.target_off[idx + 1] - to);
+            len2 = (int)(a.query_off[idx + 1] - qo);
+        }
         int best, pos, cnt;
-        const int need = (len1 + 31) >> 5;             // columns per lane
-        if (need <= 2) support_wavefront<2>(t1, len1, t2, len2, lane, best, pos, cnt);
-        else if (need <= 4) support_wavefront<4>(t1, len1, t2, len2, lane, best, pos, cnt);
-        else if (need <= 6) support_wavefront<6>(t1, len1, t2, len2, lane, best, pos, cnt);
-        else if (MAXCPL <= 8 || need <= 8) support_wavefront<8>(t1, len1, t2, len2, lane, best, pos, cnt);
-        else if (need <= 10) support_wavefront<(MAXCPL > 8 ? 10 : 8)>(t1, len1, t2, len2, lane, best, pos, cnt);
-        else if (need <= 12) support_wavefront<(MAXCPL > 8 ? 12 : 8)>(t1, len1, t2, len2, lane, best, pos, cnt);
-        else support_wavefront<(MAXCPL > 8 ? 16 : 8)>(t1, len1, t2, len2, lane, best, pos, cnt);
-        // first maximum in row-major order over the lanes: largest score, then smallest (i, j)
+        const int need = (__reduce_max_sync(0xFFFFFFFFu, len1) + SEG - 1) / SEG;       // columns per lane, the warp's widest target
+#define WAVE(C) support_wavefront<C, SEG>(t1, len1, t2, len2, lane, best, pos, cnt)
+        switch (need) {
+            case 0: case 1: case 2: WAVE(2); break;
+            case 3: case 4: WAVE(4); break;
+            case 5: case 6: WAVE(6); break;
+            case 7: case 8: WAVE(8); break;
+            case 9: case 10: WAVE(10); break;
+            case 11: case 12: WAVE(12); break;
+            case 13: case 14: WAVE(14); break;
+            default: WAVE(16); break;
+        }
+#undef WAVE
+        // first maximum in row-major order over the lanes of the segment: largest score, then smallest (i, j)
         const unsigned key = best > 0 ? ((unsigned)best << 19) | (0x7FFFFu - (unsigned)pos) : 0u;
-        const unsigned top = __reduce_max_sync(0xFFFFFFFFu, key);
-        const int owner = __ffs(__ballot_sync(0xFFFFFFFFu, key == top)) - 1;
+        unsigned top = key;
+#pragma unroll
+        for (int o = SEG / 2; o > 0; o >>= 1) top = max(top, __shfl_xor_sync(0xFFFFFFFFu, top, o));
+        const unsigned segmask = (SEG == 32 ? 0xFFFFFFFFu : ((1u << SEG) - 1u)) << (seg * SEG);
+        const int owner = __ffs(__ballot_sync(0xFFFFFFFFu, key == top) & segmask) - 1;
         const int c = __shfl_sync(0xFFFFFFFFu, cnt, owner);
-        if (lane == 0) {
+        if ((lane & (SEG - 1)) == 0 && have) {
             const int cc = top ? c : 0;
             a.subs[idx] = (cc >> 9) & 0x1FF;
             a.indels[idx] = (cc >> 18) & 0x3FF;
