@@ -29,6 +29,7 @@
  */
 #define _GNU_SOURCE
 #include <dirent.h>
+#include <errno.h>
 #include <fcntl.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -151,16 +152,25 @@ static evidence* consume_segments(readaln* const rln, const char* read, const in
  *                         each and the results are written to $INDELGPU_REPLAY_FILE;
  *   INDELGPU_MODE=replay  every call is answered from that file, in order.
  * The second run prints the VCF; the GPU sees whole-contig batches instead of one read at a time.
- *   INDELGPU_MODE=auto    both in ONE run: at the first call the process forks; the child is the recording
- *                         run (stdout discarded), the parent waits for it and continues as the replay run.
- *                         Parent and child share the offsets of the open files (the BAM), so the parent
- *                         puts every regular file's offset back where it was before it goes on. */
+ *   INDELGPU_MODE=auto    both in ONE command, CONCURRENTLY: at the first call the process forks.  The
+ *                         child is the recording run (stdout discarded, its own CUDA context); it gives
+ *                         itself private descriptions of the open input files (parent and child would
+ *                         otherwise share their offsets), realigns its queue every
+ *                         $INDELGPU_STREAM_BATCH calls (default 16384) and streams the results through a
+ *                         pipe.  The parent is the replay run: it answers each call from the pipe,
+ *                         waiting only when it has caught up with the child, and prints the VCF.  Wall
+ *                         time is one pass over the BAM plus the lag of one batch, not two passes. */
 enum { MODE_DIRECT = 0, MODE_RECORD = 1, MODE_REPLAY = 2 };
 static int g_mode = -1;
+static int g_pipe_wr = -1;           /* auto mode, child: results go here instead of the replay file */
+static int g_pipe_rd = -1;           /* auto mode, parent: results come from here                     */
+static pid_t g_child = -1;
+static int64_t g_stream_batch = 16384;
 
 typedef struct { int32_t tid, position, range1, readlen; int64_t base_off; } cand;
 static cand* g_cands = NULL;  static int64_t g_ncands = 0, g_capcands = 0;
 static char* g_bases = NULL;  static int64_t g_nbases = 0, g_capbases = 0;
+static int64_t g_total_recorded = 0;
 
 static const char* replay_path(void)
 {
@@ -168,13 +178,21 @@ static const char* replay_path(void)
     return p ? p : "indelgpu_replay.bin";
 }
 
-static void flush_recorded(void)
+static void write_all(int fd, const void* buf, size_t bytes)
 {
-    FILE* f = fopen(replay_path(), "wb");
-    if (f == NULL) fatalf("libindelgpu: cannot write %s", replay_path());
-    const int64_t magic = 0x31594C5052474449LL;          /* "IDGRPLY1" */
-    fwrite(&magic, 8, 1, f); fwrite(&g_ncands, 8, 1, f);
-    /* results in call order */
+    const char* p = (const char*)buf;
+    while (bytes > 0) {
+        const ssize_t w = write(fd, p, bytes);
+        if (w < 0) { if (errno == EINTR) continue; fatalf("libindelgpu: cannot write the replay stream (%s)", strerror(errno)); }
+        p += w; bytes -= (size_t)w;
+    }
+}
+
+/* realigns everything queued so far -- one indelgpu_realign_batch per contig (or one in all when one
+ * context holds every contig) -- writes one record per call, in call order, and empties the queue.
+ * Record: position, read length, number of segment words, rstart, the words. */
+static void realign_queue(int fd)
+{
     int32_t* nseg = ckallocz(sizeof(int32_t) * (size_t)(g_ncands + 1));
     int32_t* rstart = ckallocz(sizeof(int32_t) * (size_t)(g_ncands + 1));
     uint32_t** words = ckallocz(sizeof(uint32_t*) * (size_t)(g_ncands + 1));
@@ -223,71 +241,167 @@ static void flush_recorded(void)
         ckfree(st); ckfree(ns); ckfree(rs); ckfree(so); ckfree(sg);
         if (g_all != NULL) break;
     }
+    /* one buffer, one write: the pipe's reader sees whole batches */
+    size_t total = 0;
+    for (int64_t i = 0; i < g_ncands; i++) total += 4 + (size_t)nseg[i];
+    int32_t* buf = ckalloc(sizeof(int32_t) * (total + 1));
+    size_t w = 0;
     for (int64_t i = 0; i < g_ncands; i++) {
-        fwrite(&g_cands[i].position, 4, 1, f); fwrite(&g_cands[i].readlen, 4, 1, f);
-        fwrite(&nseg[i], 4, 1, f); fwrite(&rstart[i], 4, 1, f);
-        if (nseg[i] > 0) fwrite(words[i], 4, (size_t)nseg[i], f);
+        buf[w++] = g_cands[i].position; buf[w++] = g_cands[i].readlen; buf[w++] = nseg[i]; buf[w++] = rstart[i];
+        if (nseg[i] > 0) { memcpy(buf + w, words[i], sizeof(uint32_t) * (size_t)nseg[i]); w += (size_t)nseg[i]; ckfree(words[i]); }
     }
-    if (fclose(f) != 0) fatalf("libindelgpu: error writing %s", replay_path());
-    fprintf(stderr, "libindelgpu: %lld candidate reads realigned in batches, results in %s\n", (long long)g_ncands, replay_path());
+    write_all(fd, buf, sizeof(int32_t) * total);
+    ckfree(buf); ckfree(nseg); ckfree(rstart); ckfree(words);
+    g_total_recorded += g_ncands;
+    g_ncands = 0; g_nbases = 0;
 }
 
-static char g_auto_path[64] = "";    /* temporary replay file of INDELGPU_MODE=auto */
-static int32_t* g_replay = NULL;     /* the whole replay file after its header, as 32-bit words */
-static int64_t g_replay_words = 0, g_replay_pos = 0, g_replay_left = 0;
-static int g_replay_loaded = 0;
+static const int64_t kReplayMagic = 0x32594C5052474449LL;          /* "IDGRPLY2" */
+
+static void flush_recorded(void)
+{
+    if (g_pipe_wr >= 0) {                                /* auto mode: the tail of the stream */
+        realign_queue(g_pipe_wr);
+        close(g_pipe_wr);
+        fprintf(stderr, "libindelgpu: %lld candidate reads realigned in batches, streamed to the replaying run\n", (long long)g_total_recorded);
+        return;
+    }
+    const int fd = open(replay_path(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) fatalf("libindelgpu: cannot write %s", replay_path());
+    write_all(fd, &kReplayMagic, 8);
+    realign_queue(fd);
+    if (close(fd) != 0) fatalf("libindelgpu: error writing %s", replay_path());
+    fprintf(stderr, "libindelgpu: %lld candidate reads realigned in batches, results in %s\n", (long long)g_total_recorded, replay_path());
+}
+
+/* the replay side reads records from a growing buffer: the whole file, or whatever the pipe has delivered */
+static int32_t* g_replay = NULL;
+static int64_t g_replay_words = 0, g_replay_pos = 0, g_replay_cap = 0;
+static int g_replay_loaded = 0, g_replay_eof = 0;
+static int64_t g_replay_tailbytes = 0;   /* bytes of an incomplete word at the end of the buffer */
 
 static void load_replay(void)
 {
+    if (g_pipe_rd >= 0) return;                          /* auto mode: the stream is read on demand */
     FILE* f = fopen(replay_path(), "rb");
     if (f == NULL) fatalf("libindelgpu: cannot read %s (run with INDELGPU_MODE=record first)", replay_path());
-    int64_t hdr[2];
-    if (fread(hdr, 8, 2, f) != 2 || hdr[0] != 0x31594C5052474449LL) fatalf("libindelgpu: %s is not a replay file", replay_path());
-    g_replay_left = hdr[1];
+    int64_t magic;
+    if (fread(&magic, 8, 1, f) != 1 || magic != kReplayMagic) fatalf("libindelgpu: %s is not a replay file", replay_path());
     fseek(f, 0, SEEK_END);
-    const long bytes = ftell(f) - 16;
-    fseek(f, 16, SEEK_SET);
+    const long bytes = ftell(f) - 8;
+    fseek(f, 8, SEEK_SET);
     g_replay = ckalloc((size_t)bytes + 4);
     g_replay_words = bytes / 4;
     if (bytes > 0 && fread(g_replay, 1, (size_t)bytes, f) != (size_t)bytes) fatalf("libindelgpu: short read on %s", replay_path());
     fclose(f);
-    if (g_auto_path[0] != '\0') unlink(g_auto_path);     /* the temporary file of INDELGPU_MODE=auto */
+    g_replay_eof = 1;
 }
 
-/* INDELGPU_MODE=auto: fork the recording run; returns the mode this process continues in */
+/* auto mode: block until `need` more words are buffered (or the stream ends); returns what is there */
+static int64_t replay_available(int64_t need)
+{
+    while (g_pipe_rd >= 0 && !g_replay_eof && g_replay_words - g_replay_pos < need) {
+        if (g_replay_pos > (1 << 20)) {                   /* drop what has been consumed */
+            const int64_t keep = g_replay_words - g_replay_pos;
+            memmove(g_replay, g_replay + g_replay_pos, (size_t)keep * 4 + (size_t)g_replay_tailbytes);
+            g_replay_words = keep; g_replay_pos = 0;
+        }
+        if ((g_replay_words + (1 << 18)) > g_replay_cap) {
+            g_replay_cap = 2 * g_replay_cap + (1 << 19);
+            g_replay = ckrealloc(g_replay, (size_t)g_replay_cap * 4);
+        }
+        char* dst = (char*)g_replay + g_replay_words * 4 + g_replay_tailbytes;
+        const ssize_t r = read(g_pipe_rd, dst, (size_t)(1 << 18) * 4 - (size_t)g_replay_tailbytes);
+        if (r < 0) { if (errno == EINTR) continue; fatalf("libindelgpu: cannot read the replay stream (%s)", strerror(errno)); }
+        if (r == 0) { g_replay_eof = 1; break; }
+        const int64_t bytes = g_replay_tailbytes + r;
+        g_replay_words += bytes / 4; g_replay_tailbytes = bytes % 4;
+    }
+    return g_replay_words - g_replay_pos;
+}
 
+/* auto mode, parent: take delivery of everything the recording run still has to say and wait for it to
+ * exit (its exit handlers write the files of the other glue, host/indelgpu_support.c) */
+static void reap_recording_run(void)
+{
+    if (g_child < 0) return;
+    if (g_pipe_rd >= 0) {
+        const int64_t consumed = g_replay_pos;
+        (void)consumed;
+        while (!g_replay_eof) replay_available(g_replay_words - g_replay_pos + 1);
+        close(g_pipe_rd); g_pipe_rd = -2;                /* -2: closed, the buffer stays valid */
+    }
+    int status = 0;
+    const pid_t pid = g_child;
+    g_child = -1;
+    if (waitpid(pid, &status, 0) != pid || !WIFEXITED(status) || WEXITSTATUS(status) != 0) {
+        fprintf(stderr, "libindelgpu: the recording run failed (status %d)\n", status);
+        fflush(stdout);
+        _exit(EXIT_FAILURE);
+    }
+}
+void indelgpu_glue_wait_recording(void) { reap_recording_run(); }
+
+/* every open regular file gets a description of its own (same file, same offset): after fork() parent
+ * and child share descriptions, so their reads would move each other's offsets */
+static void detach_input_files(void)
+{
+    enum { MAXFD = 256 };
+    int fds[MAXFD]; int nfd = 0;
+    DIR* d = opendir("/proc/self/fd");
+    if (d == NULL) fatalf("libindelgpu: INDELGPU_MODE=auto needs /proc/self/fd");
+    for (struct dirent* e; (e = readdir(d)) != NULL && nfd < MAXFD;) {
+        const int fd = atoi(e->d_name);
+        struct stat st;
+        if (e->d_name[0] < '0' || e->d_name[0] > '9' || fd == dirfd(d)) continue;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) continue;
+        if ((fcntl(fd, F_GETFL) & O_ACCMODE) != O_RDONLY) continue;
+        fds[nfd++] = fd;
+    }
+    closedir(d);
+    for (int i = 0; i < nfd; i++) {
+        char path[64];
+        snprintf(path, sizeof(path), "/proc/self/fd/%d", fds[i]);
+        const off_t at = lseek(fds[i], 0, SEEK_CUR);
+        const int fresh = open(path, O_RDONLY);
+        if (fresh < 0 || at == (off_t)-1) fatalf("libindelgpu: cannot reopen input file descriptor %d", fds[i]);
+        lseek(fresh, at, SEEK_SET);
+        if (dup2(fresh, fds[i]) < 0) fatalf("libindelgpu: dup2 failed");
+        close(fresh);
+    }
+}
+
+static char g_auto_path[64] = "";    /* temporary base name for the other glue's file in INDELGPU_MODE=auto */
+
+/* INDELGPU_MODE=auto: fork the recording run; returns the mode this process continues in */
 static int fork_recording_run(void)
 {
-    /* offsets of every open regular file: the child will move them */
-    enum { MAXFD = 256 };
-    int fds[MAXFD]; off_t offs[MAXFD]; int nfd = 0;
-    DIR* d = opendir("/proc/self/fd");
-    if (d != NULL) {
-        for (struct dirent* e; (e = readdir(d)) != NULL && nfd < MAXFD;) {
-            const int fd = atoi(e->d_name);
-            struct stat st;
-            if (e->d_name[0] < '0' || e->d_name[0] > '9' || fd == dirfd(d)) continue;
-            if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) continue;
-            fds[nfd] = fd; offs[nfd] = lseek(fd, 0, SEEK_CUR); nfd++;
-        }
-        closedir(d);
-    }
     if (getenv("INDELGPU_REPLAY_FILE") == NULL) {
         snprintf(g_auto_path, sizeof(g_auto_path), "/tmp/indelgpu_replay_%d.bin", (int)getpid());
         setenv("INDELGPU_REPLAY_FILE", g_auto_path, 1);
     }
+    const char* sb = getenv("INDELGPU_STREAM_BATCH");
+    if (sb != NULL && atoll(sb) > 0) g_stream_batch = atoll(sb);
+    int p[2];
+    if (pipe(p) != 0) fatalf("libindelgpu: pipe failed");
+    /* room for a few batches: a writer stuck on a full pipe cannot collect the next batch, and the two
+     * passes would take turns instead of overlapping (1 MiB is the unprivileged maximum; best effort) */
+    (void)fcntl(p[1], F_SETPIPE_SZ, 1 << 20);
     fflush(stdout); fflush(stderr);
     const pid_t pid = fork();
     if (pid < 0) fatalf("libindelgpu: fork failed");
     if (pid == 0) {                                      /* child: the recording run, its VCF goes nowhere */
+        close(p[0]);
+        g_pipe_wr = p[1];
+        detach_input_files();
         const int nul = open("/dev/null", O_WRONLY);
         if (nul >= 0) { dup2(nul, STDOUT_FILENO); close(nul); }
         return MODE_RECORD;
     }
-    int status = 0;
-    if (waitpid(pid, &status, 0) != pid || !WIFEXITED(status) || WEXITSTATUS(status) != 0)
-        fatalf("libindelgpu: the recording run failed (status %d)", status);
-    for (int i = 0; i < nfd; i++) if (offs[i] != (off_t)-1) lseek(fds[i], offs[i], SEEK_SET);
+    close(p[1]);
+    g_pipe_rd = p[0];
+    g_child = pid;
+    atexit(reap_recording_run);                          /* a failed recording run fails this run */
     return MODE_REPLAY;
 }
 
@@ -307,6 +421,8 @@ int indelgpu_glue_mode(void)
 const char* indelgpu_glue_replay_path(void) { return replay_path(); }
 /* 1 when this process created the replay file itself (auto mode) and should remove it after loading */
 int indelgpu_glue_replay_is_temporary(void) { return g_auto_path[0] != '\0'; }
+/* 1 in the replaying parent of auto mode while its recording child may still be running */
+int indelgpu_glue_recording_runs(void) { return g_child >= 0; }
 
 evidence* attempt_pe_alignment(char** const sequences,
                                const int32_t tid,
@@ -321,11 +437,13 @@ evidence* attempt_pe_alignment(char** const sequences,
     if (g_replay_loaded == 0 && indelgpu_glue_mode() == MODE_REPLAY) { load_replay(); g_replay_loaded = 1; }
 
     if (g_mode == MODE_REPLAY) {
-        if (g_replay_left <= 0 || g_replay_pos + 4 > g_replay_words) fatalf("libindelgpu: replay file exhausted (different command line than the recording run?)");
+        if (replay_available(4) < 4) fatalf("libindelgpu: replay data exhausted (different command line than the recording run?)");
+        const int32_t nseg = g_replay[g_replay_pos + 2];
+        if (replay_available(4 + (int64_t)nseg) < 4 + (int64_t)nseg) fatalf("libindelgpu: replay data truncated");
         const int32_t* r = g_replay + g_replay_pos;
         if (r[0] != position || r[1] != (int32_t)readlength) fatalf("libindelgpu: replay out of step at position %d", position);
-        const int32_t nseg = r[2], rstart = r[3];
-        g_replay_pos += 4 + nseg; g_replay_left--;
+        const int32_t rstart = r[3];
+        g_replay_pos += 4 + nseg;
         return consume_segments(rln, read, nseg, rstart, (const uint32_t*)(r + 4));
     }
 
@@ -343,6 +461,7 @@ evidence* attempt_pe_alignment(char** const sequences,
         c->tid = tid; c->position = position; c->range1 = range[1]; c->readlen = (int32_t)readlength; c->base_off = g_nbases;
         memcpy(g_bases + g_nbases, read, (size_t)readlength);
         g_nbases += readlength;
+        if (g_pipe_wr >= 0 && g_ncands >= g_stream_batch) realign_queue(g_pipe_wr);    /* auto mode: stream this batch */
         return NULL;                                     /* rln untouched, as on a failed alignment */
     }
 

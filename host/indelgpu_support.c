@@ -26,7 +26,8 @@
  *                         queue with ONE indelgpu_indel_support_batch into $INDELGPU_REPLAY_FILE.support;
  *   INDELGPU_MODE=replay  answers every call from that file, skipping the records of the calls it no
  *                         longer makes (each record carries the call's coordinates);
- *   INDELGPU_MODE=auto    both in one run (the fork lives in indelgpu_attempt.c).
+ *   INDELGPU_MODE=auto    both in one command (the fork lives in indelgpu_attempt.c); the replaying parent
+ *                         waits for the recording child before its first call here.
  * Without INDELGPU_MODE every call is a 1-pair batch.
  */
 #include <limits.h>
@@ -46,6 +47,8 @@
 int indelgpu_glue_mode(void);
 const char* indelgpu_glue_replay_path(void);
 int indelgpu_glue_replay_is_temporary(void);
+int indelgpu_glue_recording_runs(void);
+void indelgpu_glue_wait_recording(void);
 enum { MODE_DIRECT = 0, MODE_RECORD = 1, MODE_REPLAY = 2 };
 
 static indelgpu_ctx* g_ctx = NULL;
@@ -100,6 +103,9 @@ static record* g_rec = NULL;  static int64_t g_nrec = 0, g_pos = 0;  static int 
 
 static void load_support(void)
 {
+    /* auto mode: the recording run writes this file when it exits; take delivery of the rest of its stream
+     * and wait for it (it is usually far ahead: it answers every call at once) */
+    if (indelgpu_glue_recording_runs()) indelgpu_glue_wait_recording();
     FILE* f = fopen(support_path(), "rb");
     if (f == NULL) fatalf("libindelgpu: cannot read %s (run with INDELGPU_MODE=record first)", support_path());
     int64_t hdr[2];

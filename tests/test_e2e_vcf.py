@@ -79,8 +79,9 @@ def test_record_replay_batched_mode_prints_the_same_vcf(tmp_path, flags, golden)
 
 @pytest.mark.parametrize("flags,golden", [([], "testdata_refrun.vcf"), (["-g", "16"], "testdata_refrun_g16.vcf")])
 def test_auto_mode_single_run_batched(flags, golden):
-    """INDELGPU_MODE=auto: one command; the process forks its own recording run at the first call and
-    continues as the replay run (file offsets of the open BAM restored)"""
+    """INDELGPU_MODE=auto: one command; the process forks its own recording run at the first call (which
+    gives itself private descriptions of the open BAM and streams its batches through a pipe) and
+    continues, concurrently, as the replay run"""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")

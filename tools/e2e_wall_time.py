@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """End-to-end VCF wall time on a synthetic contig (BASELINE.json: "end-to-end VCF wall time"): the
 unmodified reference program against the same program with the GPU alignment path (batched record /
-replay, and per-read), same command line, same BAM; VCFs must be identical.
+replay as two runs, auto = both concurrently in one command, and per-read), same command line, same BAM; VCFs must be identical.
   python tools/e2e_wall_time.py [--length 4000000] [--depth 20] [--out profiles/r01_e2e_wall_time.json]
 Needs oracle/_ref/{indelminer_ref,indelminer_gpu,sam2bam} (built where /root/reference exists)."""
 import argparse
@@ -51,6 +51,9 @@ def main():
                        candidates=next((int(w) for ln in err.splitlines() if "candidate reads realigned" in ln for w in ln.split() if w.isdigit()), None),
                        identical_vcf=(vcf == ref_vcf),
                        wall_s=dict(reference=t_ref, gpu_record=t_rec, gpu_replay=t_rep, gpu_total=t_rec + t_rep))
+            v3, t_auto, _ = run("indelminer_gpu", d, flags, dict(INDELGPU_MODE="auto"))     # both passes at once, one command
+            row["wall_s"]["gpu_auto"] = t_auto
+            row["identical_vcf_auto"] = (v3 == ref_vcf)
             if a.per_read:
                 v2, t_dir, _ = run("indelminer_gpu", d, flags)
                 row["wall_s"]["gpu_per_read"] = t_dir
