@@ -808,14 +808,187 @@ IG_HD inline void align_banded_serial(const DevParams& P, IArr<STRIDE> bands, IA
     out[9] = L.none ? 0 : ns;         // script entries, left in rowsb
 }
 
+// ---------------------------------------------------------------------------------------
+// local_align's two sweeps for WIDE bands (41..160 diagonals), one alignment per WARP: lane l owns the C
+// consecutive diagonals t = l*C .. l*C+C-1 and the warp does one row per step.  The row's horizontal
+// recurrence  e_t = max(c_{t-1} - (G+H), e_{t-1} - H)  unrolls to a prefix maximum,
+//     e_t = max_{t' < t} (h_{t'} - (G+H) + (t'+1) H) - t H ,   h = the cell value without its e term,
+// (a gap opened from a cell that was itself reached by e is never better than extending that gap, G >= 0),
+// so a row is: the vertical and diagonal terms in registers (the neighbour lane's edge by shuffle), one
+// warp max-scan, the combine.  Same values, end points and cell counts as local_sweeps_reg (the serial
+// statement of the same recurrence); 32 alignments per warp in rolling memory rows were 2.5x slower per cell.
+// All arguments are warp-uniform; every lane returns the same result.
+// ---------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ BandLocal local_sweeps_warp(const DevParams& P, const uint8_t* read, int M, const uint8_t* win,
+                                                       int N, int low, int up)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int G = P.G, Hh = P.H, m = G + Hh;
+    const int band = up - low + 1;
+    const int si = ig_max(0, -up), ei = ig_min(M, N - low);
+    const int t0 = lane * C;
+    const int kLow = 2 * kNeg;                                    // "no candidate" of the scans
+    int Hr[C], Dr[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const int t = t0 + c, j = si + low + t;
+        const bool v = t < band && j >= 0 && j <= N;
+        Hr[c] = v ? 0 : kNeg; Dr[c] = v ? -G : kNeg;
+    }
+    int best = 0, endi = si, endt = 0, cf = 0;
+#pragma unroll 1
+    for (int i = si + 1; i <= ei; i++) {
+        const int tlo = ig_max(0, -i - low), thi = ig_min(band - 1, N - i - low);
+        const uint32_t ai = read[i - 1];
+        int hnext = __shfl_down_sync(FULL, Hr[0], 1), dnext = __shfl_down_sync(FULL, Dr[0], 1);
+        if (lane == 31) { hnext = kNeg; dnext = kNeg; }
+        int hq[C], dq[C], laneA = kLow;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const int t = t0 + c;
+            const int hup = (c + 1 < C) ? Hr[c + 1] : hnext, dup = (c + 1 < C) ? Dr[c + 1] : dnext;
+            const int d = ig_max(hup - m, dup - Hh);
+            const int x = i + low + t - 1;
+            const uint32_t b = (x >= 0 && x < N) ? (uint32_t)win[x] : 0u;
+            hq[c] = ig_max(Hr[c] + (b == ai ? P.match : P.mismatch), ig_max(d, 0));
+            dq[c] = d;
+            if (t >= tlo && t <= thi) laneA = ig_max(laneA, hq[c] - m + (t + 1) * Hh);
+        }
+        int incl = laneA;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl = ig_max(incl, v); }
+        int run = __shfl_up_sync(FULL, incl, 1);
+        if (lane == 0) run = kLow;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const int t = t0 + c;
+            if (t >= tlo && t <= thi) {
+                const int e = run - t * Hh;
+                const int cv = ig_max(hq[c], e);
+                run = ig_max(run, hq[c] - m + (t + 1) * Hh);
+                Hr[c] = cv; Dr[c] = dq[c];
+                if (cv > best) { best = cv; endi = i; endt = t; }
+            }
+        }
+        cf += thi - tlo + 1;
+    }
+    {   // first maximum in row-major order: largest score, then smallest row, then smallest diagonal
+        const int top = __reduce_max_sync(FULL, best);
+        const unsigned pos = best == top ? ((unsigned)endi << 12) | (unsigned)endt : 0xFFFFFFFFu;
+        const unsigned first = __reduce_min_sync(FULL, pos);
+        best = top; endi = (int)(first >> 12); endt = (int)(first & 0xFFFu);
+        if (top <= 0) { endi = si; endt = 0; }
+    }
+    BandLocal L;
+    const int endj = endi + low + endt;
+    L.best = best; L.endi = endi; L.endj = (best > 0) ? endj : si + low; L.cf = cf; L.cr = 0;
+    L.starti = 0; L.startj = 0; L.none = true;
+    if (best <= 0) return L;
+
+    // reverse (localalign.c:132-176)
+    const int tend = (endj - endi) - low;
+    {
+        const int tl = ig_max(0, -endi - low);
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const int t = t0 + c;
+            const bool v = t <= tend && t >= tl;
+            const int acc = -(G + Hh * (tend - t));
+            Hr[c] = (t == tend) ? 0 : (v ? acc : kNeg);
+            Dr[c] = (t == tend) ? -G : (v ? acc - G : kNeg);
+        }
+    }
+    int starti = 0, startt = 0, cr = 0; bool found = false;
+#pragma unroll 1
+    for (int i = endi; i >= 1 && !found; i--) {
+        const int thi = ig_min(band - 1, tend + (endi - i) + 1);
+        const int tlo = ig_max(0, 1 - i - low);
+        const uint32_t ai = read[i - 1];
+        int hprev = __shfl_up_sync(FULL, Hr[C - 1], 1), dprev = __shfl_up_sync(FULL, Dr[C - 1], 1);
+        if (lane == 0) { hprev = kNeg; dprev = kNeg; }
+        int hq[C], dq[C], laneB = kLow;
+#pragma unroll
+        for (int c = C - 1; c >= 0; c--) {
+            const int t = t0 + c;
+            const int hdn = (c > 0) ? Hr[c - 1] : hprev, ddn = (c > 0) ? Dr[c - 1] : dprev;
+            const int d = ig_max(hdn - m, ddn - Hh);
+            const int x = i + low + t - 1;
+            const uint32_t b = (x >= 0 && x < N) ? (uint32_t)win[x] : 0u;
+            hq[c] = ig_max(Hr[c] + (b == ai ? P.match : P.mismatch), d);
+            dq[c] = d;
+            if (t >= tlo && t <= thi) laneB = ig_max(laneB, hq[c] - m - (t - 1) * Hh);
+        }
+        int incl = laneB;                                         // suffix maximum over the lanes above
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_down_sync(FULL, incl, o); if (lane + o < 32) incl = ig_max(incl, v); }
+        int run = __shfl_down_sync(FULL, incl, 1);
+        if (lane == 31) run = kLow;
+        int hit = -1;                                             // largest own diagonal whose value equals the optimum
+#pragma unroll
+        for (int c = C - 1; c >= 0; c--) {
+            const int t = t0 + c;
+            if (t >= tlo && t <= thi) {
+                const int e = run + t * Hh;
+                const int cv = ig_max(hq[c], e);
+                run = ig_max(run, hq[c] - m - (t - 1) * Hh);
+                Hr[c] = cv; Dr[c] = dq[c];
+                if (cv == best && hit < 0) hit = t;
+            } else if (t < tlo) { Hr[c] = kNeg; Dr[c] = kNeg; }   // left the window: stale values must not be read
+        }
+        const int tophit = __reduce_max_sync(FULL, hit);
+        if (tophit >= 0) { found = true; starti = i; startt = tophit; cr += thi - tophit + 1; }
+        else cr += ig_max(0, thi - tlo + 1);
+    }
+    L.cr = cr; L.starti = starti; L.startj = starti + low + startt;
+    L.none = !found || starti > M || L.startj > N || L.endi - starti == 0 || L.endj - L.startj == 0;   // localalign.c:180-193
+    return L;
+}
+
+constexpr int kWarpBandMin = 41, kWarpBandMax = 160;
+
+__device__ __forceinline__ BandLocal local_sweeps_warp_any(const DevParams& P, const uint8_t* read, int M, const uint8_t* win,
+                                                           int N, int low, int up)
+{
+    const int band = up - low + 1;
+    if (band <= 64) return local_sweeps_warp<2>(P, read, M, win, N, low, up);
+    if (band <= 96) return local_sweeps_warp<3>(P, read, M, win, N, low, up);
+    if (band <= 128) return local_sweeps_warp<4>(P, read, M, win, N, low, up);
+    return local_sweeps_warp<5>(P, read, M, win, N, low, up);
+}
+
+// The warp-per-alignment sweeps for the tasks of one pass of banded_two_phase_loop: every lane says whether
+// its task wants them (`mine`: valid task, band in [kWarpBandMin, kWarpBandMax], G >= 0); the warp then
+// serves the lanes one after the other.  fetch(idx, &read, &M, &win, &N, &lo, &hi) reloads a task's
+// geometry from its index (warp-uniform).
+template <class Fetch>
+__device__ __forceinline__ void warp_serve_wide_bands(const DevParams& P, int idx, bool mine, Fetch fetch, BandLocal& L)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t todo = __ballot_sync(0xFFFFFFFFu, mine);
+#pragma unroll 1
+    while (todo) {
+        const int q = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int idxq = __shfl_sync(0xFFFFFFFFu, idx, q);
+        const uint8_t* read; const uint8_t* win; int M, N, lo, hi;
+        fetch(idxq, &read, &M, &win, &N, &lo, &hi);
+        const BandLocal R = local_sweeps_warp_any(P, read, M, win, N, lo, hi);
+        if (lane == q) L = R;
+    }
+}
+
 #ifdef __CUDACC__
 // Warp-level scheduling of the two phases (used by band_tasks_kernel and pipe_dp_kernel).  Every lane
 // runs phase 1 (sweeps + shortcut) on its own task; tasks that need ALIGN are collected in a per-warp
 // buffer and phase 2 runs whenever 32 are waiting (and once more for the tail), so that the divide and
 // conquer always executes with a full warp while other warps of the SM hide its latency.
-// phase1(idx, DcTask&) -> bool "needs phase 2"; phase2(const DcTask&).  `pend` holds 64 DcTask per warp.
-template <class P1, class P2>
-__device__ __forceinline__ void banded_two_phase_loop(int n, DcTask* pend, P1 phase1, P2 phase2)
+// phase0(idx, valid, BandLocal&) -> bool "sweeps done by the warp" (called by all 32 lanes together);
+// phase1(idx, DcTask&, const BandLocal* pre) -> bool "needs phase 2"; phase2(const DcTask&).
+// `pend` holds 64 DcTask per warp.
+template <class P0, class P1, class P2>
+__device__ __forceinline__ void banded_two_phase_loop(int n, DcTask* pend, P0 phase0, P1 phase1, P2 phase2)
 {
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -827,7 +1000,9 @@ __device__ __forceinline__ void banded_two_phase_loop(int n, DcTask* pend, P1 ph
             const int idx = idx0 + lane;
             DcTask t;
             t.idx = idx;
-            const bool q = (idx < n) ? phase1(idx, t) : false;
+            BandLocal pre;
+            const bool have = phase0(idx, idx < n, pre);         // warp-cooperative part (wide bands); all lanes call it
+            const bool q = (idx < n) ? phase1(idx, t, have ? &pre : nullptr) : false;
             const uint32_t qm = __ballot_sync(0xFFFFFFFFu, q);
             if (q) pend[waiting + __popc(qm & ((1u << lane) - 1u))] = t;
             waiting += __popc(qm);

@@ -137,7 +137,28 @@ pipe_dp_kernel(const __grid_constant__ RealignArgs a, const PipeBufs p, const in
     const IArr<32> rowsb = gbase + wb4;
     DcFrame st[kDcFrames];
 
-    auto phase1 = [&](int idx, DcTask& t) -> bool {
+    auto geometry = [&](int idx, const uint8_t** read, int* M, const uint8_t** win, int* N, int* lo, int* hi) -> bool {
+        ReadCtx c; uint32_t zs1 = 0, e1 = 0, zs2 = 0, e2 = 0; int low = 0;
+        const bool active = pipe_task(a, p, round, idx, &c, &zs1, &e1, &zs2, &e2, &low);
+        *N = (int)(e1 - zs1); *M = (int)(e2 - zs2);
+        *lo = max(-*M, low); *hi = min(*N, low + a.P.g);                   // localalign.c:70-71
+        *read = a.reads + c.roff + zs2; *win = a.ref.raw + c.cbase + zs1;
+        return active;
+    };
+    auto phase0 = [&](int idx, bool valid, BandLocal& L) -> bool {
+        bool mine = false;
+        if (valid && a.P.g + 1 >= kWarpBandMin) {
+            const uint8_t* read; const uint8_t* win; int M, N, lo, hi;
+            const bool active = geometry(idx, &read, &M, &win, &N, &lo, &hi);
+            const int band = hi - lo + 1;
+            mine = active && band >= kWarpBandMin && band <= kWarpBandMax && a.P.G >= 0 && a.P.H >= 0 &&
+                   2 * band <= a.scratch.max_band && M <= a.scratch.max_rows && 2 * M + band + 4 <= p.cig_stride;
+        }
+        if (a.P.g + 1 >= kWarpBandMin)                                      // warp-uniform: narrow-band runs skip the pass
+            warp_serve_wide_bands(a.P, idx, mine, geometry, L);
+        return mine;
+    };
+    auto phase1 = [&](int idx, DcTask& t, const BandLocal* pre) -> bool {
         ReadCtx c; uint32_t zs1 = 0, e1 = 0, zs2 = 0, e2 = 0; int low = 0;
         bool active = pipe_task(a, p, round, idx, &c, &zs1, &e1, &zs2, &e2, &low);
         const int N = (int)(e1 - zs1), M = (int)(e2 - zs2);
@@ -153,7 +174,7 @@ pipe_dp_kernel(const __grid_constant__ RealignArgs a, const PipeBufs p, const in
         if (active) {
             const uint8_t* read = a.reads + c.roff + zs2;
             const uint8_t* win = a.ref.raw + c.cbase + zs1;
-            const BandLocal L = band_local<32>(a.P, bands, a.scratch.max_band, read, M, win, N, lo, hi);
+            const BandLocal L = pre ? *pre : band_local<32>(a.P, bands, a.scratch.max_band, read, M, win, N, lo, hi);
             r.low = low; r.up = low + a.P.g;
             r.cells_fwd = L.cf; r.cells_rev = L.cr;
             if (!L.none) {                                                // :385-388
@@ -187,7 +208,7 @@ pipe_dp_kernel(const __grid_constant__ RealignArgs a, const PipeBufs p, const in
         Aln* r = p.aln + (int64_t)round * a.n + idx;
         r->n = n; r->cells_glob = cells;
     };
-    banded_two_phase_loop(a.n, s_pend[warp], phase1, phase2);
+    banded_two_phase_loop(a.n, s_pend[warp], phase0, phase1, phase2);
 }
 
 // ---- warp per read: combine + results ----------------------------------------------------------

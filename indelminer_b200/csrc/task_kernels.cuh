@@ -159,7 +159,25 @@ band_tasks_kernel(const __grid_constant__ TaskArgs a)
     unsigned long long cf = 0, cr = 0, cg = 0;
     DcFrame st[kDcFrames];
 
-    auto phase1 = [&](int idx, DcTask& t) -> bool {
+    auto geometry = [&](int idx, const uint8_t** read, int* M, const uint8_t** win, int* N, int* lo, int* hi) {
+        const int64_t roff = a.read_off[idx], woff = a.ref_off[idx];
+        *M = (int)(a.read_off[idx + 1] - roff); *N = (int)(a.ref_off[idx + 1] - woff);
+        *lo = max(-*M, a.low[idx]); *hi = min(*N, a.up[idx]);                // localalign.c:70-71
+        *read = a.reads + roff; *win = a.refs + woff;
+    };
+    auto phase0 = [&](int idx, bool valid, BandLocal& L) -> bool {
+        bool mine = false;
+        if (valid) {
+            const uint8_t* read; const uint8_t* win; int M, N, lo, hi;
+            geometry(idx, &read, &M, &win, &N, &lo, &hi);
+            const int band = hi - lo + 1;
+            mine = M > 0 && N > 0 && band >= kWarpBandMin && band <= kWarpBandMax && a.P.G >= 0 && a.P.H >= 0 &&
+                   2 * band <= a.scratch.max_band && M <= a.scratch.max_rows && 2 * M + band + 4 <= a.cigar_stride;
+        }
+        warp_serve_wide_bands(a.P, idx, mine, geometry, L);
+        return mine;
+    };
+    auto phase1 = [&](int idx, DcTask& t, const BandLocal* pre) -> bool {
         const int64_t roff = a.read_off[idx], woff = a.ref_off[idx];
         const int M = (int)(a.read_off[idx + 1] - roff), N = (int)(a.ref_off[idx + 1] - woff);
         const int lo = max(-M, a.low[idx]), hi = min(N, a.up[idx]);       // localalign.c:70-71
@@ -174,7 +192,7 @@ band_tasks_kernel(const __grid_constant__ TaskArgs a)
         }
         const uint8_t* read = a.reads + roff;
         const uint8_t* win = a.refs + woff;
-        const BandLocal L = band_local<32>(a.P, bands, a.scratch.max_band, read, M, win, N, lo, hi);
+        const BandLocal L = pre ? *pre : band_local<32>(a.P, bands, a.scratch.max_band, read, M, win, N, lo, hi);
         const int score = L.none ? 0 : L.best;
         a.score[idx] = score;
         a.ends[4 * idx + 0] = score > 0 ? L.starti : 0; a.ends[4 * idx + 1] = score > 0 ? L.startj : 0;
@@ -218,7 +236,7 @@ band_tasks_kernel(const __grid_constant__ TaskArgs a)
             if (ns < a.script_stride) so[ns] = 0x7FFFFFFF;
         }
     };
-    banded_two_phase_loop(a.n, s_pend[warp], phase1, phase2);
+    banded_two_phase_loop(a.n, s_pend[warp], phase0, phase1, phase2);
 
     __syncwarp();
     cf = warp_sum_u64(cf);

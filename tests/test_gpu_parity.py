@@ -63,7 +63,7 @@ def test_golden_attempt_pe_alignment_calls(gpu):
 
 
 # ----------------------------------------------------------------------------- oracle, two rounds
-@pytest.mark.parametrize("k,g", [(6, 0), (8, 0), (4, 0), (11, 0), (15, 0), (6, 3), (5, 8), (6, 32)])
+@pytest.mark.parametrize("k,g", [(6, 0), (8, 0), (4, 0), (11, 0), (15, 0), (6, 3), (5, 8), (6, 32), (6, 47)])
 def test_realign_vs_oracle(gpu, oracle, k, g):
     rng = make_rng(1000 + 17 * k + g)
     p = oracle.default_params(k, g)
