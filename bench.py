@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--ref-mb", type=int, default=64, help="contig size in Mb")
     ap.add_argument("--band", type=int, default=33)
     ap.add_argument("--numgaps", type=int, default=0)
+    ap.add_argument("--maxdel", type=int, default=1000, help="-s of the reference (experiments only; the metric is quoted at 1000)")
     ap.add_argument("--tasks", type=int, default=1 << 17, help="alignments for --workload band")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -234,7 +235,7 @@ def run_ours(a, rank, world, local_rank):
 
     peak, peak_src = peaks()
     L = _lib.load()
-    R = indelminer_b200.Realigner(device=local_rank, numgaps=a.numgaps)
+    R = indelminer_b200.Realigner(device=local_rank, numgaps=a.numgaps, maxdelsize=a.maxdel)
     ref = synth.make_reference(a.ref_mb * 1_000_000, seed=1)
     R.set_reference([ref.tobytes()])
 
