@@ -547,7 +547,14 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
     const bool debug_out = o->detail || o->cigar1 || o->cigar2;
     int kChunkReads = 1 << 17;
     if (const char* e = getenv("INDELGPU_CHUNK_READS")) { const int v = atoi(e); if (v >= 64) kChunkReads = v; }
-    const int nchunks = (debug_out || n < 2 * kChunkReads) ? 1 : (n + kChunkReads - 1) / kChunkReads;
+    // chunk boundaries: the first chunks are small (1/8, 1/4, 1/2 of a chunk) so that the first kernel starts
+    // after a short copy instead of a full chunk's; then full chunks
+    std::vector<int> cuts(1, 0);
+    if (!(debug_out || n < 2 * kChunkReads)) {
+        for (int div = 8; div >= 2 && cuts.back() < n; div >>= 1) cuts.push_back(std::min(n, cuts.back() + std::max(64, kChunkReads / div)));
+        while (cuts.back() < n) cuts.push_back(std::min(n, cuts.back() + kChunkReads));
+    } else cuts.push_back(n);
+    const int nchunks = (int)cuts.size() - 1;
     if (nchunks > 1) {
         while ((int)c->ev_in.size() < nchunks) {
             cudaEvent_t e1, e2;
@@ -568,7 +575,7 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
         }
         unsigned long long* counts = reinterpret_cast<unsigned long long*>(c->pinned_counts);
         for (int ch = 0; ch < nchunks; ch++) {
-            const int c0 = ch * kChunkReads, c1 = std::min(n, c0 + kChunkReads), m = c1 - c0;
+            const int c0 = cuts[ch], c1 = cuts[ch + 1], m = c1 - c0;
             int max_read = 0, max_range = 0;
             if (int rcs = scan_range(c0, c1, &max_read, &max_range)) { cudaDeviceSynchronize(); return rcs; }
             const int64_t b0 = h->read_off[c0], b1 = h->read_off[c1];

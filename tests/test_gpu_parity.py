@@ -353,7 +353,7 @@ def test_chunked_host_path_equals_single_launch(gpu, monkeypatch):
     a = R.attempt_pe_alignment_batch(*args, packed=(w["read_bases"], w["read_off"]))
     monkeypatch.setenv("INDELGPU_CHUNK_READS", "1000")
     b = R.attempt_pe_alignment_batch(*args, packed=(w["read_bases"], w["read_off"]))
-    assert b.launches == 6 and a.launches == 1
+    assert b.launches == 9 and a.launches == 1          # 125 + 250 + 500 reads (ramp-up), then six chunks of up to 1000
     assert np.array_equal(a.status, b.status) and np.array_equal(a.nseg, b.nseg) and np.array_equal(a.rstart, b.rstart)
     assert a.seg_count == b.seg_count == int(a.nseg.sum())
     assert a.cells == b.cells and a.alg_bytes == b.alg_bytes
