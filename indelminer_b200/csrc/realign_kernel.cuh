@@ -233,7 +233,7 @@ __device__ __forceinline__ void stage_read(const RealignArgs& a, WarpView& V, co
     bulk_g2s(win_buf(V, buf), a.ref.packed + sw0, wbytes, bar);
 }
 
-constexpr int kWorkChunk = 8;
+constexpr int kWorkChunk = 2;     // batch entries a warp takes per atomic: larger values lengthen every launch's tail (8 cost the chunked host path 8 %)
 
 #ifndef REALIGN_MIN_BLOCKS
 #define REALIGN_MIN_BLOCKS 3      // caps the kernel at 85 registers so that three CTAs of 7 warps fit an SM
