@@ -545,12 +545,12 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
     // Chunks share the reference, the segment allocator and the counters; read offsets stay absolute.
     int64_t segs_copied = 0;                         // segment words the chunked path has already brought back
     const bool debug_out = o->detail || o->cigar1 || o->cigar2;
-    int kChunkReads = 1 << 17;
+    int kChunkReads = 1 << 18;
     if (const char* e = getenv("INDELGPU_CHUNK_READS")) { const int v = atoi(e); if (v >= 64) kChunkReads = v; }
     // chunk boundaries: the first chunks are small (1/8, 1/4, 1/2 of a chunk) so that the first kernel starts
     // after a short copy instead of a full chunk's; then full chunks
     std::vector<int> cuts(1, 0);
-    if (!(debug_out || n < 2 * kChunkReads)) {
+    if (!(debug_out || n < kChunkReads)) {
         for (int div = 8; div >= 2 && cuts.back() < n; div >>= 1) cuts.push_back(std::min(n, cuts.back() + std::max(64, kChunkReads / div)));
         while (cuts.back() < n) cuts.push_back(std::min(n, cuts.back() + kChunkReads));
     } else cuts.push_back(n);
