@@ -148,8 +148,10 @@ static evidence* consume_segments(readaln* const rln, const char* read, const in
  * (flags, CIGAR, mate quality; indelminer.c:384-492), never from earlier alignment results, so two runs
  * of the same command make the same calls in the same order:
  *   INDELGPU_MODE=record  every call is queued and answered NULL (the VCF of this run is discarded); at
- *                         exit the queue is realigned contig by contig with ONE indelgpu_realign_batch
- *                         each and the results are written to $INDELGPU_REPLAY_FILE;
+ *                         exit -- and whenever $INDELGPU_RECORD_BATCH calls (default 2^20) are waiting,
+ *                         which bounds the queue's memory -- the queue is realigned contig by contig with
+ *                         ONE indelgpu_realign_batch each and the results are appended to
+ *                         $INDELGPU_REPLAY_FILE;
  *   INDELGPU_MODE=replay  every call is answered from that file, in order.
  * The second run prints the VCF; the GPU sees whole-contig batches instead of one read at a time.
  *   INDELGPU_MODE=auto    both in ONE command, CONCURRENTLY: at the first call the process forks.  The
@@ -166,6 +168,7 @@ static int g_pipe_wr = -1;           /* auto mode, child: results go here instea
 static int g_pipe_rd = -1;           /* auto mode, parent: results come from here                     */
 static pid_t g_child = -1;
 static int64_t g_stream_batch = 16384;
+static int64_t g_record_batch = 1 << 20;  /* record mode: the queue is realigned and written out at this size (memory bound) */
 
 typedef struct { int32_t tid, position, range1, readlen; int64_t base_off; } cand;
 static cand* g_cands = NULL;  static int64_t g_ncands = 0, g_capcands = 0;
@@ -258,6 +261,18 @@ static void realign_queue(int fd)
 
 static const int64_t kReplayMagic = 0x32594C5052474449LL;          /* "IDGRPLY2" */
 
+/* record mode: the replay file, created at the first flush */
+static int replay_file_fd(void)
+{
+    static int fd = -1;
+    if (fd < 0) {
+        fd = open(replay_path(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (fd < 0) fatalf("libindelgpu: cannot write %s", replay_path());
+        write_all(fd, &kReplayMagic, 8);
+    }
+    return fd;
+}
+
 static void flush_recorded(void)
 {
     if (g_pipe_wr >= 0) {                                /* auto mode: the tail of the stream */
@@ -266,9 +281,7 @@ static void flush_recorded(void)
         fprintf(stderr, "libindelgpu: %lld candidate reads realigned in batches, streamed to the replaying run\n", (long long)g_total_recorded);
         return;
     }
-    const int fd = open(replay_path(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-    if (fd < 0) fatalf("libindelgpu: cannot write %s", replay_path());
-    write_all(fd, &kReplayMagic, 8);
+    const int fd = replay_file_fd();
     realign_queue(fd);
     if (close(fd) != 0) fatalf("libindelgpu: error writing %s", replay_path());
     fprintf(stderr, "libindelgpu: %lld candidate reads realigned in batches, results in %s\n", (long long)g_total_recorded, replay_path());
@@ -411,6 +424,8 @@ int indelgpu_glue_mode(void)
 {
     if (g_mode < 0) {
         const char* m = getenv("INDELGPU_MODE");
+        const char* rb = getenv("INDELGPU_RECORD_BATCH");
+        if (rb != NULL && atoll(rb) > 0) g_record_batch = atoll(rb);
         g_mode = (m && strcmp(m, "record") == 0) ? MODE_RECORD : (m && strcmp(m, "replay") == 0) ? MODE_REPLAY : MODE_DIRECT;
         if (m && strcmp(m, "auto") == 0) g_mode = fork_recording_run();
     }
@@ -461,7 +476,8 @@ evidence* attempt_pe_alignment(char** const sequences,
         c->tid = tid; c->position = position; c->range1 = range[1]; c->readlen = (int32_t)readlength; c->base_off = g_nbases;
         memcpy(g_bases + g_nbases, read, (size_t)readlength);
         g_nbases += readlength;
-        if (g_pipe_wr >= 0 && g_ncands >= g_stream_batch) realign_queue(g_pipe_wr);    /* auto mode: stream this batch */
+        if (g_pipe_wr >= 0) { if (g_ncands >= g_stream_batch) realign_queue(g_pipe_wr); }    /* auto mode: stream this batch */
+        else if (g_ncands >= g_record_batch) realign_queue(replay_file_fd());               /* record mode: bounded queue */
         return NULL;                                     /* rln untouched, as on a failed alignment */
     }
 
