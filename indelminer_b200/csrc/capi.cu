@@ -102,7 +102,8 @@ struct indelgpu_ctx {
     DevBuf out_status, out_nseg, out_rstart, out_segoff, out_segs, out_detail, out_cig1, out_cig2;
     DevBuf counters;         // bytes: 0 work counter (int) | 8 seg count (u64) | 16 cells (3 x u64) | 40 error flag (int) | 48 algorithmic bytes (u64)
     DevBuf scratch;
-    DevBuf s_tgt, s_toff, s_qry, s_qoff, s_out, s_ord, s_idx, s_V, s_I, s_F;   // known-indel support check (indel_support.cuh)
+    DevBuf s_tgt, s_toff, s_qry, s_qoff, s_out, s_ord, s_idx, s_V, s_I, s_F;
+    int32_t* h_order = nullptr; size_t h_order_cap = 0;            // pinned work list of the support check   // known-indel support check (indel_support.cuh)
     DevBuf p_low, p_aln, p_cig, p_plan, p_flags;      // intermediates of the banded pipeline (realign_pipeline.cuh)
     // task API staging
     DevBuf t_reads, t_roff, t_refs, t_woff, t_packed, t_anchor, t_low, t_up, t_score, t_ends, t_ncig, t_cig, t_script;
@@ -176,6 +177,7 @@ extern "C" void indelgpu_destroy(indelgpu_ctx* c)
     for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_out) cudaEventDestroy(e);
     if (c->pinned_counts) cudaFreeHost(c->pinned_counts);
+    if (c->h_order) cudaFreeHost(c->h_order);
     DevBuf* all[] = {&c->ref_raw, &c->ref_packed, &c->ref_off, &c->ref_len, &c->in_reads, &c->in_off, &c->in_tid,
                      &c->in_pos, &c->in_rng, &c->out_status, &c->out_nseg, &c->out_rstart, &c->out_segoff,
                      &c->out_segs, &c->out_detail, &c->out_cig1, &c->out_cig2, &c->counters, &c->scratch,
@@ -837,6 +839,17 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
     if (n == 0) return 0;
     CU(cudaSetDevice(c->device));
     if (h_target_off[0] != 0 || h_query_off[0] != 0) return fail(INDELGPU_EINVAL, "offset arrays must start at 0");
+    // the sequence copies start first: the host pass below (validation, classes, counting sort) runs under them
+    const int64_t nt = h_target_off[n], nq = h_query_off[n];
+    if (nt < 0 || nq < 0) return fail(INDELGPU_EINVAL, "indel_support_batch: negative offsets");
+    cudaStream_t st = c->stream;
+    if (c->s_tgt.ensure((size_t)nt + 16) || c->s_toff.ensure(8 * (size_t)(n + 1)) || c->s_qry.ensure((size_t)nq + 16) ||
+        c->s_qoff.ensure(8 * (size_t)(n + 1)) || c->s_out.ensure(12 * (size_t)n) || c->s_ord.ensure(4 * (size_t)n)) return INDELGPU_ENOMEM;
+    if (nt > 0) CU(cudaMemcpyAsync(c->s_tgt.p, h_targets, (size_t)nt, cudaMemcpyHostToDevice, st));
+    if (nq > 0) CU(cudaMemcpyAsync(c->s_qry.p, h_queries, (size_t)nq, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->s_toff.p, h_target_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->s_qoff.p, h_query_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
     // pairs the wavefront kernel's packing holds go there (all real reads), in three classes by target length
     // (8, 16 or 32 lanes per pair) and sorted by that length inside a class; the rest, one pair per thread
     std::vector<int32_t> slow;
@@ -845,7 +858,10 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
     std::vector<int32_t> bucket(kWaveMaxTarget + 2, 0);
     for (int i = 0; i < n; i++) {
         const int64_t l1 = h_target_off[i + 1] - h_target_off[i], l2 = h_query_off[i + 1] - h_query_off[i];
-        if (l1 < 0 || l2 < 0 || l1 > 8000 || l2 > 8000) return fail(INDELGPU_ELIMIT, "task %d: lengths %lld x %lld outside 0..8000", i, (long long)l1, (long long)l2);
+        if (l1 < 0 || l2 < 0 || l1 > 8000 || l2 > 8000) {
+            cudaStreamSynchronize(st);                         // the copies read the caller's buffers
+            return fail(INDELGPU_ELIMIT, "task %d: lengths %lld x %lld outside 0..8000", i, (long long)l1, (long long)l2);
+        }
         cells += l1 * l2;
         if (l1 > kWaveMaxTarget || l2 > kWaveMaxQuery) { slow.push_back(i); max1 = std::max(max1, (int)l1); max2 = std::max(max2, (int)l2); }
         else bucket[l1 + 1]++;
@@ -853,7 +869,13 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
     const int nslow = (int)slow.size(), nfast = n - nslow;
     for (int l = 0; l <= kWaveMaxTarget; l++) bucket[l + 1] += bucket[l];                 // counting sort by target length
     const int class_end[3] = {bucket[128 + 1], bucket[256 + 1], bucket[kWaveMaxTarget + 1]};   // <= 128 | <= 256 | <= 512 bases
-    std::vector<int32_t> order((size_t)std::max(nfast, 1));
+    if (c->h_order_cap < (size_t)std::max(nfast, 1)) {           // pinned: the copy below must not wait for a staging pass
+        if (c->h_order) cudaFreeHost(c->h_order);
+        c->h_order = nullptr; c->h_order_cap = 0;
+        CU(cudaMallocHost((void**)&c->h_order, 4 * (size_t)std::max(n, 1)));
+        c->h_order_cap = (size_t)std::max(n, 1);
+    }
+    int32_t* order = c->h_order;
     {
         std::vector<int32_t> at(bucket.begin(), bucket.end() - 1);
         for (int i = 0; i < n; i++) {
@@ -861,16 +883,7 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
             if (l1 <= kWaveMaxTarget && l2 <= kWaveMaxQuery) order[at[l1]++] = i;
         }
     }
-    const int64_t nt = h_target_off[n], nq = h_query_off[n];
-    cudaStream_t st = c->stream;
-    if (c->s_tgt.ensure((size_t)nt + 16) || c->s_toff.ensure(8 * (size_t)(n + 1)) || c->s_qry.ensure((size_t)nq + 16) ||
-        c->s_qoff.ensure(8 * (size_t)(n + 1)) || c->s_out.ensure(12 * (size_t)n) || c->s_ord.ensure(4 * (size_t)std::max(nfast, 1))) return INDELGPU_ENOMEM;
-    if (nt > 0) CU(cudaMemcpyAsync(c->s_tgt.p, h_targets, (size_t)nt, cudaMemcpyHostToDevice, st));
-    if (nq > 0) CU(cudaMemcpyAsync(c->s_qry.p, h_queries, (size_t)nq, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->s_toff.p, h_target_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->s_qoff.p, h_query_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
-    if (nfast > 0) CU(cudaMemcpyAsync(c->s_ord.p, order.data(), 4 * (size_t)nfast, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
+    if (nfast > 0) CU(cudaMemcpyAsync(c->s_ord.p, order, 4 * (size_t)nfast, cudaMemcpyHostToDevice, st));
     int32_t* d_subs = c->s_out.as<int32_t>();
     int32_t* d_indels = d_subs + n;
     int32_t* d_aligned = d_indels + n;
