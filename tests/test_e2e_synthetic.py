@@ -63,3 +63,18 @@ def test_synthetic_vcf_identical(dataset, flags):
         with open(os.path.join(out, "e2e_synthetic.json"), "a") as f:
             f.write(json.dumps(dict(flags=flags, dataset=dataset["info"], variants=len(body),
                                     wall_s=dict(reference=t_ref, gpu_record=t_rec, gpu_replay=t_rep, gpu_per_read=t_dir, gpu_auto=t_auto))) + "\n")
+
+
+def test_region_runs_match_the_reference(dataset):
+    """the reference's own scale-out: one process per region (-c, indelminer.c:711); the GPU-linked program
+    run the same way (INDELGPU_MODE=auto, INDELGPU_DEVICE chosen per process, as on a multi-GPU box) must
+    print the reference's VCF for every region"""
+    import torch
+    ndev = torch.cuda.device_count()
+    total = 0
+    for r, region in enumerate(["chrS:1-200000", "chrS:200001-400000"]):
+        ref_vcf, _ = run("indelminer_ref", dataset, ["-c", region])
+        gpu_vcf, _ = run("indelminer_gpu", dataset, ["-c", region], dict(INDELGPU_MODE="auto", INDELGPU_DEVICE=str(r % ndev)))
+        assert gpu_vcf == ref_vcf, region
+        total += sum(1 for ln in ref_vcf.splitlines() if not ln.startswith("#"))
+    assert total > 150
