@@ -378,7 +378,7 @@ def run_ours(a, rank, world, local_rank):
         sms = R.sm_count
         peak_issue = sms * 4 * clocks["sm_mhz"] * 1e6                     # 4 schedulers per SM, 1 warp instruction / clk each
         line["roofline"]["issue"] = {
-            "warp_instr_per_read": NCU_WARP_INSTR_PER_READ, "source": "profiles/r01_v5_realign_kernel_by_region.txt (ncu)",
+            "warp_instr_per_read": NCU_WARP_INSTR_PER_READ, "source": "profiles/r01_v11_realign_kernel_ncu_full.csv (ncu)",
             "achieved_gwarp_instr_s": NCU_WARP_INSTR_PER_READ * (n / kernel_s) / 1e9,
             "peak_gwarp_instr_s": peak_issue / 1e9,
             "frac": NCU_WARP_INSTR_PER_READ * (n / kernel_s) / peak_issue}
@@ -443,7 +443,7 @@ def run_band(a, R, L, torch, dev, peak, peak_src):
     print(json.dumps(line), flush=True)
 
 
-NCU_WARP_INSTR_PER_READ = 4704  # realign_kernel: 4 932 500 669 executed warp instructions / 1 048 576 reads (ncu, r01 v5)
+NCU_WARP_INSTR_PER_READ = 4710  # realign_kernel: 4 938 399 073 executed warp instructions / 1 048 576 reads (ncu, r01 v11)
 SUPPORT_OPS_PER_CELL = 26      # integer instructions per DP cell of the wavefront kernel (SASS count)
 
 
