@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--band", type=int, default=33)
     ap.add_argument("--numgaps", type=int, default=0)
     ap.add_argument("--maxdel", type=int, default=1000, help="-s of the reference (experiments only; the metric is quoted at 1000)")
-    ap.add_argument("--tasks", type=int, default=1 << 17, help="alignments for --workload band")
+    ap.add_argument("--tasks", type=int, default=1 << 17, help="alignments / pairs for --workload band / support (SURVEY D1 size: 1048576)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return ap.parse_args()
