@@ -44,6 +44,9 @@
 #include "errors.h"
 
 #include "indelgpu.h"
+#include "indelgpu_glue.h"
+
+pthread_mutex_t indelgpu_glue_gpu_mu = PTHREAD_MUTEX_INITIALIZER;
 
 /* the flags alignment.c reads (alignment.c:3-9; defined in indelminer.c:31-44) */
 extern uint klength;
@@ -111,6 +114,13 @@ static indelgpu_ctx* ctx_for_contig(char** const sequences, const int32_t tid, i
     return g_slots[tid].ctx;
 }
 
+indelgpu_ctx* indelgpu_glue_ctx_peek(int32_t tid, int32_t* ptid)
+{
+    if (g_all != NULL) { *ptid = tid; return g_all; }
+    *ptid = 0;
+    return (tid >= 0 && tid < g_nslots) ? g_slots[tid].ctx : NULL;
+}
+
 /* segment words -> rln->segments -> evidence list: what the reference does once its alignments are known */
 static evidence* consume_segments(readaln* const rln, const char* read, const int32_t nseg, const int32_t rstart,
                                   const uint32_t* words)
@@ -162,8 +172,7 @@ static evidence* consume_segments(readaln* const rln, const char* read, const in
  *                         pipe.  The parent is the replay run: it answers each call from the pipe,
  *                         waiting only when it has caught up with the child, and prints the VCF.  Wall
  *                         time is one pass over the BAM plus the lag of one batch, not two passes. */
-enum { MODE_DIRECT = 0, MODE_RECORD = 1, MODE_REPLAY = 2 };
-static int g_mode = -1;
+static int g_mode = -1;            /* MODE_* of indelgpu_glue.h */
 static int g_pipe_wr = -1;           /* auto mode, child: results go here instead of the replay file */
 static int g_pipe_rd = -1;           /* auto mode, parent: results come from here                     */
 static pid_t g_child = -1;
@@ -389,6 +398,11 @@ static char g_auto_path[64] = "";    /* temporary base name for the other glue's
 /* INDELGPU_MODE=auto: fork the recording run; returns the mode this process continues in */
 static int fork_recording_run(void)
 {
+    /* a CUDA context does not survive fork(): the recording child must create its own, so the optional
+     * up-front upload (indelgpu_host_init) cannot be combined with this mode */
+    if (g_all != NULL)
+        fatalf("libindelgpu: INDELGPU_MODE=auto forks its recording run and cannot inherit the GPU context that "
+               "indelgpu_host_init() created; drop the indelgpu_host_init() call or use INDELGPU_MODE=inline");
     if (getenv("INDELGPU_REPLAY_FILE") == NULL) {
         snprintf(g_auto_path, sizeof(g_auto_path), "/tmp/indelgpu_replay_%d.bin", (int)getpid());
         setenv("INDELGPU_REPLAY_FILE", g_auto_path, 1);
@@ -426,7 +440,8 @@ int indelgpu_glue_mode(void)
         const char* m = getenv("INDELGPU_MODE");
         const char* rb = getenv("INDELGPU_RECORD_BATCH");
         if (rb != NULL && atoll(rb) > 0) g_record_batch = atoll(rb);
-        g_mode = (m && strcmp(m, "record") == 0) ? MODE_RECORD : (m && strcmp(m, "replay") == 0) ? MODE_REPLAY : MODE_DIRECT;
+        g_mode = (m && strcmp(m, "record") == 0) ? MODE_RECORD : (m && strcmp(m, "replay") == 0) ? MODE_REPLAY :
+                 (m && strcmp(m, "inline") == 0) ? MODE_INLINE : MODE_DIRECT;
         if (m && strcmp(m, "auto") == 0) g_mode = fork_recording_run();
     }
     return g_mode;
@@ -462,8 +477,18 @@ evidence* attempt_pe_alignment(char** const sequences,
         return consume_segments(rln, read, nseg, rstart, (const uint32_t*)(r + 4));
     }
 
+    if (g_mode == MODE_INLINE) {                         /* row f2: the answer was prefetched with the record's block */
+        int32_t nseg = 0, rstart = 0;
+        const uint32_t* words = NULL;
+        if (indelgpu_inline_lookup(tid, position, range[1], read, (int32_t)readlength, &nseg, &rstart, &words))
+            return consume_segments(rln, read, nseg, rstart, words);
+        indelgpu_inline_learn(range[1]);                 /* not foreseen (or nothing known yet): the per-read path below */
+    }
+
     int32_t dtid = 0;
+    pthread_mutex_lock(&indelgpu_glue_gpu_mu);
     indelgpu_ctx* ctx = ctx_for_contig(sequences, tid, &dtid);   /* uploads the contig the first time it is seen */
+    pthread_mutex_unlock(&indelgpu_glue_gpu_mu);
 
     if (g_mode == MODE_RECORD) {
         /* exit handlers run in reverse order of registration: this one must be registered AFTER the CUDA
@@ -495,6 +520,9 @@ evidence* attempt_pe_alignment(char** const sequences,
     memset(&out, 0, sizeof(out));
     out.status = &status; out.nseg = &nseg; out.rstart = &rstart; out.seg_off = &segoff;
     out.segs = g_segs; out.seg_capacity = g_segcap;
-    if (indelgpu_realign_batch(ctx, &in, &out) != 0) gpu_die("indelgpu_realign_batch");
+    pthread_mutex_lock(&indelgpu_glue_gpu_mu);
+    const int rc = indelgpu_realign_batch(ctx, &in, &out);
+    pthread_mutex_unlock(&indelgpu_glue_gpu_mu);
+    if (rc != 0) gpu_die("indelgpu_realign_batch");
     return consume_segments(rln, read, nseg, rstart, g_segs + segoff);
 }

@@ -28,6 +28,14 @@
  *                         longer makes (each record carries the call's coordinates);
  *   INDELGPU_MODE=auto    both in one command (the fork lives in indelgpu_attempt.c); the replaying parent
  *                         waits for the recording child before its first call here.
+ *   INDELGPU_MODE=inline  no second run and no fork: is_indel_supported's bam_fetch (variant.c:1567; the hooked
+ *                         variant.c is compiled with -Dbam_fetch=indelgpu_bam_fetch_support) reads the records
+ *                         of the variant's region once and shows them to check_for_indel TWICE.  The first time
+ *                         this file answers "does not support" and queues the pairs; if no read supported the
+ *                         variant by its CIGAR alone, the queue is scored with one indelgpu_indel_support_batch
+ *                         and the second pass answers from it, in call order.  The only result of the loop is
+ *                         variant->diffsample_support, an OR over the reads (variant.c:1444-1448, :1549-1553),
+ *                         so showing the records twice changes nothing else.
  * Without INDELGPU_MODE every call is a 1-pair batch.
  */
 #include <limits.h>
@@ -43,13 +51,7 @@
 #include "indelgpu.h"
 #include "indelgpu_support.h"
 
-/* shared with host/indelgpu_attempt.c */
-int indelgpu_glue_mode(void);
-const char* indelgpu_glue_replay_path(void);
-int indelgpu_glue_replay_is_temporary(void);
-int indelgpu_glue_recording_runs(void);
-void indelgpu_glue_wait_recording(void);
-enum { MODE_DIRECT = 0, MODE_RECORD = 1, MODE_REPLAY = 2 };
+#include "indelgpu_glue.h"      /* shared with host/indelgpu_attempt.c: the operating mode */
 
 static indelgpu_ctx* g_ctx = NULL;
 
@@ -71,9 +73,16 @@ static char* support_path(void)
 static void support_ctx(void)
 {
     if (g_ctx != NULL) return;
-    g_ctx = indelgpu_create(0, NULL);
+    const char* dev = getenv("INDELGPU_DEVICE");       /* same device as the realignment glue (one process per GPU) */
+    g_ctx = indelgpu_create(dev ? atoi(dev) : 0, NULL);
     if (g_ctx == NULL) fatalf("libindelgpu: %s", indelgpu_last_error());
 }
+
+/* inline mode: which pass of indelgpu_bam_fetch_support is running */
+enum { PASS_NONE = 0, PASS_COLLECT = 1, PASS_ANSWER = 2 };
+static int g_pass = PASS_NONE;
+static int32_t* g_ans = NULL;   static int64_t g_anscap = 0, g_anspos = 0;     /* subs, indels, aligned per queued pair */
+static long long g_inl_variants = 0, g_inl_batches = 0, g_inl_pairs = 0;
 
 static void flush_support(void)
 {
@@ -182,9 +191,19 @@ void realign_with_indel(const char* const reference, const int rstart, const int
     key.len1 = len1;
 
     support_ctx();
-    if (mode == MODE_RECORD) {
+    if (mode == MODE_INLINE && g_pass == PASS_ANSWER) {
+        if (g_anspos >= g_n) fatalf("libindelgpu: inline support: the second pass makes more calls than the first");
+        const callkey* k = &g_keys[g_anspos];
+        if (k->rstart != key.rstart || k->rstop != key.rstop || k->qstart != key.qstart || k->qstop != key.qstop ||
+            k->len1 != key.len1 || k->len2 != key.len2) fatalf("libindelgpu: inline support: the second pass is out of step");
+        *alnsubs = g_ans[3 * g_anspos]; *alnindels = g_ans[3 * g_anspos + 1]; *alnaligned = g_ans[3 * g_anspos + 2];
+        g_anspos++;
+        ckfree(target);
+        return;
+    }
+    if (mode == MODE_RECORD || (mode == MODE_INLINE && g_pass == PASS_COLLECT)) {
         static int registered = 0;
-        if (!registered) { atexit(flush_support); registered = 1; }     /* after the CUDA runtime's own handler */
+        if (mode == MODE_RECORD && !registered) { atexit(flush_support); registered = 1; }     /* after the CUDA runtime's own handler */
         if (g_n + 2 > g_cap) {
             g_cap = g_cap ? 2 * g_cap : 4096;
             g_keys = ckrealloc(g_keys, sizeof(callkey) * (size_t)g_cap);
@@ -205,9 +224,67 @@ void realign_with_indel(const char* const reference, const int rstart, const int
     const int64_t toff[2] = {0, len1}, qoff[2] = {0, len2 > 0 ? len2 : 0};
     int32_t s = 0, g = 0, a = 0;
     const uint8_t dummy = 0;
-    if (indelgpu_indel_support_batch(g_ctx, 1, len1 > 0 ? (const uint8_t*)target : &dummy, toff,
-                                     len2 > 0 ? (const uint8_t*)t2 : &dummy, qoff, &s, &g, &a, NULL) != 0)
+    pthread_mutex_lock(&indelgpu_glue_gpu_mu);
+    const int rc = indelgpu_indel_support_batch(g_ctx, 1, len1 > 0 ? (const uint8_t*)target : &dummy, toff,
+                                                len2 > 0 ? (const uint8_t*)t2 : &dummy, qoff, &s, &g, &a, NULL);
+    pthread_mutex_unlock(&indelgpu_glue_gpu_mu);
+    if (rc != 0)
         fatalf("libindelgpu: indelgpu_indel_support_batch: %s", indelgpu_last_error());
     ckfree(target);
     *alnsubs = s; *alnindels = g; *alnaligned = a;
+}
+
+/* ---- inline mode: is_indel_supported's record loop (variant.c:1567) ---------------------------------- */
+static void print_inline_stats(void)
+{
+    fprintf(stderr, "libindelgpu: inline mode: %lld known variants checked, %lld (variant, read) pairs scored in %lld batches\n",
+            g_inl_variants, g_inl_pairs, g_inl_batches);
+}
+
+int indelgpu_bam_fetch_support(bamFile fp, const bam_index_t* idx, int tid, int beg, int end, void* data, bam_fetch_f func)
+{
+    if (indelgpu_glue_mode() != MODE_INLINE) return bam_fetch(fp, idx, tid, beg, end, data, func);
+    static bam1_t* recs = NULL; static int caprec = 0;
+    static int registered = 0;
+    if (!registered) { atexit(print_inline_stats); registered = 1; }
+    int nrec = 0, ret;
+    bam_iter_t iter = bam_iter_query(idx, tid, beg, end);
+    for (;;) {
+        if (nrec == caprec) {
+            const int ncap = caprec ? 2 * caprec : 256;
+            recs = ckrealloc(recs, sizeof(bam1_t) * (size_t)ncap);
+            memset(recs + caprec, 0, sizeof(bam1_t) * (size_t)(ncap - caprec));
+            caprec = ncap;
+        }
+        ret = bam_iter_read(fp, iter, &recs[nrec]);
+        if (ret < 0) break;
+        nrec++;
+    }
+    bam_iter_destroy(iter);
+    knownvariant* variant = data;
+    g_inl_variants++;
+    g_n = 0; g_ntgt = 0; g_nqry = 0;
+    g_pass = PASS_COLLECT;
+    for (int i = 0; i < nrec; i++) func(&recs[i], data);
+    g_pass = PASS_NONE;
+    if (!variant->diffsample_support && g_n > 0) {
+        if (3 * g_n > g_anscap) { g_anscap = 6 * g_n + 64; g_ans = ckrealloc(g_ans, sizeof(int32_t) * (size_t)g_anscap); }
+        int32_t* subs = ckalloc(sizeof(int32_t) * (size_t)g_n * 3);
+        g_toff[g_n] = g_ntgt; g_qoff[g_n] = g_nqry;
+        const uint8_t dummy = 0;
+        pthread_mutex_lock(&indelgpu_glue_gpu_mu);
+        const int rc = indelgpu_indel_support_batch(g_ctx, (int32_t)g_n, g_ntgt > 0 ? g_tgt : &dummy, g_toff, g_nqry > 0 ? g_qry : &dummy, g_qoff,
+                                                    subs, subs + g_n, subs + 2 * g_n, NULL);
+        pthread_mutex_unlock(&indelgpu_glue_gpu_mu);
+        if (rc != 0) fatalf("libindelgpu: indelgpu_indel_support_batch (inline mode): %s", indelgpu_last_error());
+        for (int64_t i = 0; i < g_n; i++) { g_ans[3 * i] = subs[i]; g_ans[3 * i + 1] = subs[g_n + i]; g_ans[3 * i + 2] = subs[2 * g_n + i]; }
+        ckfree(subs);
+        g_inl_batches++; g_inl_pairs += g_n;
+        g_anspos = 0;
+        g_pass = PASS_ANSWER;
+        for (int i = 0; i < nrec; i++) func(&recs[i], data);
+        g_pass = PASS_NONE;
+    }
+    g_n = 0; g_ntgt = 0; g_nqry = 0;
+    return ret == -1 ? 0 : ret;
 }

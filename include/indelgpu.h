@@ -162,6 +162,13 @@ int indelgpu_realign_batch_device(indelgpu_ctx* ctx, const indelgpu_batch* d_in,
  *   out[3]     algorithmic bytes: sum over alignments of N + M + 4 * (6 + ncigar) */
 int indelgpu_last_counters(indelgpu_ctx* ctx, int64_t out[4]);
 
+/* Error flag the kernels of the last batch left on the device (waits for them): 0 none; 1 at least one
+ * read was rejected (status INDELGPU_ST_ASSERT); 2 the segment buffer overflowed -- nseg / seg_off are
+ * set but the words were not written, compare *d_seg_count with seg_capacity; 3 a TMA bulk copy never
+ * completed and the outputs of the affected reads are undefined.  indelgpu_realign_batch checks this
+ * itself and returns an error; callers of indelgpu_realign_batch_device must ask.  < 0: INDELGPU_E*. */
+int indelgpu_last_error_flag(indelgpu_ctx* ctx);
+
 /* device time (CUDA events on the context's stream) of the kernel the last
  * indelgpu_band_align_batch call launched, in ms; < 0 when nothing was timed */
 double indelgpu_last_kernel_ms(indelgpu_ctx* ctx);

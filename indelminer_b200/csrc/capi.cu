@@ -100,6 +100,7 @@ struct indelgpu_ctx {
     // batch staging
     DevBuf in_reads, in_off, in_tid, in_pos, in_rng;
     DevBuf out_status, out_nseg, out_rstart, out_segoff, out_segs, out_detail, out_cig1, out_cig2;
+    DevBuf chunk_counts;     // chunked host path: segment count after each chunk's kernel, snapshot in stream order
     DevBuf counters;         // bytes: 0 work counter (int) | 8 seg count (u64) | 16 cells (3 x u64) | 40 error flag (int) | 48 algorithmic bytes (u64)
     DevBuf scratch;
     DevBuf s_tgt, s_toff, s_qry, s_qoff, s_out, s_ord, s_idx, s_V, s_I, s_F;
@@ -180,7 +181,7 @@ extern "C" void indelgpu_destroy(indelgpu_ctx* c)
     if (c->h_order) cudaFreeHost(c->h_order);
     DevBuf* all[] = {&c->ref_raw, &c->ref_packed, &c->ref_off, &c->ref_len, &c->in_reads, &c->in_off, &c->in_tid,
                      &c->in_pos, &c->in_rng, &c->out_status, &c->out_nseg, &c->out_rstart, &c->out_segoff,
-                     &c->out_segs, &c->out_detail, &c->out_cig1, &c->out_cig2, &c->counters, &c->scratch,
+                     &c->out_segs, &c->out_detail, &c->out_cig1, &c->out_cig2, &c->counters, &c->chunk_counts, &c->scratch,
                      &c->p_low, &c->p_aln, &c->p_cig, &c->p_plan, &c->p_flags,
                      &c->s_tgt, &c->s_toff, &c->s_qry, &c->s_qoff, &c->s_out, &c->s_ord, &c->s_idx, &c->s_V, &c->s_I, &c->s_F,
                      &c->t_reads, &c->t_roff, &c->t_refs, &c->t_woff, &c->t_packed, &c->t_anchor, &c->t_low,
@@ -492,6 +493,20 @@ extern "C" int indelgpu_last_counters(indelgpu_ctx* c, int64_t out[4])
     return 0;
 }
 
+// Error flag of the last batch launched on this context, after waiting for it: 0 none, 1 at least one read
+// was rejected (status 7), 2 the segment buffer overflowed (seg_off / nseg are set, the words are not),
+// 3 a TMA bulk copy never completed.  indelgpu_realign_batch checks it itself; callers of the
+// device-pointer entry point must ask.
+extern "C" int indelgpu_last_error_flag(indelgpu_ctx* c)
+{
+    if (!c) return fail(INDELGPU_EINVAL, "last_error_flag: NULL context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(c->pinned_small, c->counters.p, 64, cudaMemcpyDeviceToHost));
+    int err; memcpy(&err, (char*)c->pinned_small + 40, 4);
+    return err;
+}
+
 extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, indelgpu_result* o)
 {
     if (!c || !h || !o) return fail(INDELGPU_EINVAL, "realign_batch: NULL argument");
@@ -576,6 +591,8 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
             c->ev_out.push_back(e);
         }
         unsigned long long* counts = reinterpret_cast<unsigned long long*>(c->pinned_counts);
+        if (c->chunk_counts.ensure(8 * (size_t)(nchunks + 8))) return INDELGPU_ENOMEM;
+        unsigned long long* d_counts = c->chunk_counts.as<unsigned long long>();
         for (int ch = 0; ch < nchunks; ch++) {
             const int c0 = cuts[ch], c1 = cuts[ch + 1], m = c1 - c0;
             int max_read = 0, max_range = 0;
@@ -594,9 +611,14 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
             rc2.status = dout.status + c0; rc2.nseg = dout.nseg + c0; rc2.rstart = dout.rstart + c0; rc2.seg_off = dout.seg_off + c0;
             int rcl = launch_realign(c, &dc, max_read, max_range, &rc2, ctr_segs(c), st, ch > 0);
             if (rcl) { cudaDeviceSynchronize(); return rcl; }
+            // The segment allocator keeps counting while chunk ch+1 runs, and the words of a read are written
+            // one read later than they are allocated (realign_kernel's pend_* flush).  The count that bounds
+            // chunk ch's words is therefore snapshot ON THE KERNEL STREAM, between kernel ch and kernel ch+1:
+            // every word below it has been written when ev_k[ch] fires.
+            CU(cudaMemcpyAsync(d_counts + ch, ctr_segs(c), 8, cudaMemcpyDeviceToDevice, st));
             CU(cudaEventRecord(c->ev_k[ch], st));
             CU(cudaStreamWaitEvent(c->st_out, c->ev_k[ch], 0));
-            CU(cudaMemcpyAsync(counts + ch, ctr_segs(c), 8, cudaMemcpyDeviceToHost, c->st_out));
+            CU(cudaMemcpyAsync(counts + ch, d_counts + ch, 8, cudaMemcpyDeviceToHost, c->st_out));
             CU(cudaEventRecord(c->ev_out[ch], c->st_out));
             CU(cudaMemcpyAsync(o->status + c0, dout.status + c0, 4 * (size_t)m, cudaMemcpyDeviceToHost, c->st_out));
             CU(cudaMemcpyAsync(o->nseg + c0, dout.nseg + c0, 4 * (size_t)m, cudaMemcpyDeviceToHost, c->st_out));
@@ -902,7 +924,7 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
         if (cls == 0) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, indel_support_wave_kernel<8>, 128, 0));
         else if (cls == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, indel_support_wave_kernel<16>, 128, 0));
         else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, indel_support_wave_kernel<32>, 128, 0));
-        if (occ < 1) return fail(INDELGPU_ELIMIT, "support kernel does not fit on an SM");
+        if (occ < 1) { cudaStreamSynchronize(st); return fail(INDELGPU_ELIMIT, "support kernel does not fit on an SM"); }
         const int blocks = (int)std::min<long long>((long long)c->sms * occ, ((long long)cnt + 4 * group - 1) / (4 * group));
         if (cls == 0) indel_support_wave_kernel<8><<<blocks, 128, 0, st>>>(w);
         else if (cls == 1) indel_support_wave_kernel<16><<<blocks, 128, 0, st>>>(w);
@@ -913,7 +935,7 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
     if (nslow > 0) {
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, indel_support_kernel, 128, 0));
-        if (occ < 1) return fail(INDELGPU_ELIMIT, "support kernel does not fit on an SM");
+        if (occ < 1) { cudaStreamSynchronize(st); return fail(INDELGPU_ELIMIT, "support kernel does not fit on an SM"); }
         const long long cells_cap = (long long)(max1 + 1) * (max2 + 1);
         // resident threads are bounded by the scratch they need (3 bytes per DP cell per thread): at most ~8 GB
         long long blocks = std::min<long long>((long long)c->sms * std::min(occ, 4), (nslow + 127) / 128);
@@ -921,7 +943,7 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
         blocks = std::max<long long>(1, std::min<long long>(blocks, (8LL << 30) / std::max<long long>(per_block, 1)));
         if (c->s_idx.ensure(4 * (size_t)nslow) ||
             c->s_V.ensure((size_t)blocks * 128 * (size_t)cells_cap * 2) || c->s_I.ensure((size_t)blocks * 128 * (size_t)cells_cap) ||
-            c->s_F.ensure((size_t)blocks * 128 * 4 * (size_t)(max1 + 1))) return INDELGPU_ENOMEM;
+            c->s_F.ensure((size_t)blocks * 128 * 4 * (size_t)(max1 + 1))) { cudaStreamSynchronize(st); return INDELGPU_ENOMEM; }
         CU(cudaMemcpyAsync(c->s_idx.p, slow.data(), 4 * (size_t)nslow, cudaMemcpyHostToDevice, st));
         SupportArgs a;
         a.n = nslow;

@@ -324,7 +324,10 @@ realign_kernel(const __grid_constant__ RealignArgs a)
                     bool ok;
                     const int low = vote_band_warp<DIRECT, HB>(a.P, V, swin, sw0, cbase + zs1, (int)(e1 - zs1), (int)zs2,
                                                                (int)(e2 - zs2), (int)(anc - zs1), &ok);
-                    if (!ok) { if (lane == 0 && round == 1) s_final[0] = ST_ASSERT; break; }
+                    if (!ok) {                                       // numdiagonals <= numgaps: the reference aborts (alignment.c:405)
+                        if (lane == 0) { s_final[0] = ST_ASSERT; s_plan->status = ST_ASSERT; atomicExch(a.error_flag, 1); }
+                        break;
+                    }
                     band_alignment_warp(a, S, cbase, zs1, e1, zs2, e2, low, low + a.P.g,
                                                 round ? S.cig2 : S.cig1, s_aln + round, s_tmp);
                     if (round == 1) { done2 = true; break; }

@@ -101,6 +101,7 @@ pipe_vote_kernel(const __grid_constant__ RealignArgs a, const PipeBufs p, const 
                 p.low[(int64_t)round * a.n + idx] = low;
                 if (round == 0) p.flags[idx] = ok ? PF_VOTE1_OK : 0;
                 else p.flags[idx] = cur.flags | PF_GO | (ok ? PF_VOTE2_OK : 0);
+                if (!ok) atomicExch(a.error_flag, 1);         // numdiagonals <= numgaps: the reference aborts (alignment.c:405)
             }
             __syncwarp();
         }
