@@ -447,6 +447,12 @@ int indelgpu_glue_mode(void)
     return g_mode;
 }
 
+int indelgpu_glue_env_is_inline(void)
+{
+    const char* m = getenv("INDELGPU_MODE");
+    return m != NULL && strcmp(m, "inline") == 0;
+}
+
 /* path of the replay file (INDELGPU_REPLAY_FILE, or the temporary one of auto mode) */
 const char* indelgpu_glue_replay_path(void) { return replay_path(); }
 /* 1 when this process created the replay file itself (auto mode) and should remove it after loading */

@@ -15,6 +15,8 @@ enum { MODE_DIRECT = 0, MODE_RECORD = 1, MODE_REPLAY = 2, MODE_INLINE = 3 };
 
 /* operating mode of this process, decided once from $INDELGPU_MODE (indelgpu_attempt.c) */
 int indelgpu_glue_mode(void);
+/* 1 when $INDELGPU_MODE asks for the inline mode; unlike indelgpu_glue_mode() this never forks */
+int indelgpu_glue_env_is_inline(void);
 const char* indelgpu_glue_replay_path(void);
 int indelgpu_glue_replay_is_temporary(void);
 int indelgpu_glue_recording_runs(void);

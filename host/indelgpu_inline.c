@@ -240,8 +240,13 @@ static void* producer_main(void* arg)
 
 int indelgpu_bam_fetch(bamFile fp, const bam_index_t* idx, int tid, int beg, int end, void* data, bam_fetch_f func)
 {
-    if (g_in_fetch || indelgpu_glue_mode() != MODE_INLINE)
-        return bam_fetch(fp, idx, tid, beg, end, data, func);              /* nested call, or another mode: samtools' own loop */
+    /* nested call, or another mode: samtools' own loop.  The mode is read from the environment here, NOT through
+     * indelgpu_glue_mode(): that call decides the mode for good and, for INDELGPU_MODE=auto, forks -- which must
+     * happen inside the first attempt_pe_alignment call, where the replaying parent then blocks on the pipe
+     * until the recording child has given itself private descriptions of the open BAM */
+    if (g_in_fetch || !indelgpu_glue_env_is_inline())
+        return bam_fetch(fp, idx, tid, beg, end, data, func);
+    if (indelgpu_glue_mode() != MODE_INLINE) fatalf("libindelgpu: INDELGPU_MODE changed while running");
     if (!g_stats_registered) { atexit(print_stats); g_stats_registered = 1; }
     g_in_fetch = 1;
     producer_arg pa;

@@ -243,7 +243,7 @@ static void print_inline_stats(void)
 
 int indelgpu_bam_fetch_support(bamFile fp, const bam_index_t* idx, int tid, int beg, int end, void* data, bam_fetch_f func)
 {
-    if (indelgpu_glue_mode() != MODE_INLINE) return bam_fetch(fp, idx, tid, beg, end, data, func);
+    if (!indelgpu_glue_env_is_inline()) return bam_fetch(fp, idx, tid, beg, end, data, func);   /* no fork from here (see indelgpu_inline.c) */
     static bam1_t* recs = NULL; static int caprec = 0;
     static int registered = 0;
     if (!registered) { atexit(print_inline_stats); registered = 1; }

@@ -95,6 +95,8 @@ struct indelgpu_ctx {
     DevParams P;
     // reference
     DevBuf ref_raw, ref_packed, ref_off, ref_len;
+    DevBuf idx_off, idx_pos;                          // resident k-mer index (kmer_index.cuh), built by set_reference for k <= 6
+    int64_t idx_blocks = 0;
     int ncontigs = 0;
     int64_t ref_bases = 0;
     // batch staging
@@ -179,7 +181,7 @@ extern "C" void indelgpu_destroy(indelgpu_ctx* c)
     for (cudaEvent_t e : c->ev_out) cudaEventDestroy(e);
     if (c->pinned_counts) cudaFreeHost(c->pinned_counts);
     if (c->h_order) cudaFreeHost(c->h_order);
-    DevBuf* all[] = {&c->ref_raw, &c->ref_packed, &c->ref_off, &c->ref_len, &c->in_reads, &c->in_off, &c->in_tid,
+    DevBuf* all[] = {&c->ref_raw, &c->ref_packed, &c->ref_off, &c->ref_len, &c->idx_off, &c->idx_pos, &c->in_reads, &c->in_off, &c->in_tid,
                      &c->in_pos, &c->in_rng, &c->out_status, &c->out_nseg, &c->out_rstart, &c->out_segoff,
                      &c->out_segs, &c->out_detail, &c->out_cig1, &c->out_cig2, &c->counters, &c->chunk_counts, &c->scratch,
                      &c->p_low, &c->p_aln, &c->p_cig, &c->p_plan, &c->p_flags,
@@ -240,6 +242,28 @@ extern "C" int indelgpu_set_reference(indelgpu_ctx* c, int32_t ncontigs, const c
     c->launches = 0;
     if (pack_device(c, c->ref_raw.as<uint8_t>(), c->ref_packed.as<uint32_t>(), total / 16)) return INDELGPU_ECUDA;
     CU(cudaMemsetAsync(c->ref_packed.as<uint32_t>() + total / 16, 0, 16, c->stream));
+    // the k-mer index of the whole reference (kmer_index.cuh): 8 * 4^k + 2 * 4096 bytes per 4096 bases.
+    // EXPERIMENTAL, opt-in with INDELGPU_INDEX=1: measured on B200 (profiles/r02_index_vote.md) the index vote is exact
+    // but executes MORE instructions per read than the window scan (6.2 k vs 4.7 k warp instructions; 8.2 ms vs 6.7 ms
+    // per 1 Mi reads) -- per-bucket bookkeeping costs more than the scan's ~5 instructions per window position saves.
+    c->idx_blocks = 0;
+    if (c->P.k <= kIdxMaxK && getenv("INDELGPU_INDEX") != nullptr && atoi(getenv("INDELGPU_INDEX")) > 0) {
+        const int64_t nblocks = (total + kIdxBlock - 1) / kIdxBlock;
+        const size_t off_bytes = (size_t)nblocks * 8 * ((size_t)1 << (2 * c->P.k)), pos_bytes = (size_t)nblocks * 2 * kIdxBlock;
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = (off_bytes > c->idx_off.cap ? off_bytes : 0) + (pos_bytes > c->idx_pos.cap ? pos_bytes : 0);
+        if (need + (need >> 2) + ((size_t)2 << 30) < free_b) {                 // leave room for the batches
+            if (c->ref_packed.ensure((size_t)(nblocks * (kIdxBlock / 16) + 4) * 4)) return INDELGPU_ENOMEM;   // no-op: total / 16 + 4 words cover it
+            if (c->idx_off.ensure(off_bytes) || c->idx_pos.ensure(pos_bytes)) return INDELGPU_ENOMEM;
+            const int blocks = (int)std::min<int64_t>(nblocks, (int64_t)c->sms * 8);
+            build_kmer_index_kernel<<<blocks, 256, 0, c->stream>>>(c->ref_packed.as<uint32_t>(), nblocks, c->P.k, c->P.kmask,
+                                                                   c->idx_off.as<uint2>(), c->idx_pos.as<uint16_t>());
+            c->launches++;
+            CU(cudaGetLastError());
+            c->idx_blocks = nblocks;
+        }
+    }
     CU(cudaStreamSynchronize(c->stream));
     c->ncontigs = ncontigs; c->ref_bases = total;
     return 0;
@@ -318,6 +342,7 @@ static void fill_realign_args(indelgpu_ctx* c, RealignArgs& a, const indelgpu_ba
     a.detail = d_out->detail; a.cigar1 = d_out->cigar1; a.cigar2 = d_out->cigar2; a.cigar_stride = d_out->cigar_stride;
     a.work_counter = ctr_work(c); a.cell_totals = ctr_cells(c); a.error_flag = ctr_err(c);
     a.max_read = max_read; a.max_numdiag = max_numdiag; a.L = L;
+    a.idx.rec = c->idx_off.as<uint2>(); a.idx.pos = c->idx_pos.as<uint16_t>(); a.idx.nblocks = c->idx_blocks; a.idx.k = c->idx_blocks ? c->P.k : 0;
     a.scratch.base = nullptr; a.scratch.stride = 0; a.scratch.max_band = 0; a.scratch.max_rows = 0;
 }
 
@@ -396,12 +421,14 @@ static int launch_realign(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_r
     const bool banded = c->P.g > 0;
     // the banded pipeline only votes with this layout (its CIGARs live in HBM), so it takes the compact form too
     const long long vd = std::max(2LL * max_range1, (long long)max_range1 + c->P.maxdel) + max_read + 2;
-    const WarpLayout L = make_warp_layout(c->P, max_read, max_numdiag, (int)vd, 0);
+    const bool indexed = !banded && c->idx_blocks > 0;            // -g 0, k <= 6: the fused kernel votes through the resident index
+    const WarpLayout L = make_warp_layout(c->P, max_read, max_numdiag, (int)vd, 0, indexed ? 1 : 0);
     if (((uintptr_t)d_in->read_bases & 15) != 0) return fail(INDELGPU_EINVAL, "read_bases must be 16-byte aligned on the device (TMA bulk copies)");
     if (banded) return launch_pipeline(c, d_in, max_read, max_numdiag, L, d_out, d_seg_count, st, keep_totals);
     void (*kern)(RealignArgs);
-    if (L.hist_bits == 8) kern = L.direct ? realign_kernel<true, 8> : realign_kernel<false, 8>;
-    else                  kern = L.direct ? realign_kernel<true, 16> : realign_kernel<false, 16>;
+    if (L.indexed)        kern = L.hist_bits == 8 ? realign_kernel<true, 8, true> : realign_kernel<true, 16, true>;
+    else if (L.hist_bits == 8) kern = L.direct ? realign_kernel<true, 8, false> : realign_kernel<false, 8, false>;
+    else                  kern = L.direct ? realign_kernel<true, 16, false> : realign_kernel<false, 16, false>;
     int wpc = 0, occ = 0;
     if (int rc = plan_warps(c, kern, L.total, &wpc, &occ)) return rc;
     const int blocks = (int)std::min<long long>((long long)c->sms * occ, std::max(1, (d_in->n + wpc - 1) / wpc));

@@ -15,12 +15,14 @@
 #include "kernels.cuh"
 #include "band_dp.cuh"
 #include "warp_vote.cuh"
+#include "kmer_index.cuh"
 
 namespace indelgpu {
 
 struct RealignArgs {
     DevParams P;
     RefView ref;
+    KmerIndex idx;                     // resident k-mer index of the reference (used when L.indexed)
     int n;
     const uint8_t* reads; const int64_t* read_off;
     const int32_t* tid; const int32_t* position; const int32_t* range1;
@@ -228,6 +230,11 @@ __device__ __forceinline__ void stage_read(const RealignArgs& a, WarpView& V, co
     const uint32_t rbytes = (uint32_t)(((c.roff + c.readlen - r0) + 15) / 16 * 16);
     int64_t sw0;
     const uint32_t wbytes = window_span_bytes(c.cbase + c.left2, c.cbase + c.right2, &sw0);
+    if (a.L.indexed) {                                           // the vote reads the resident index: only the read is staged
+        mbar_arrive_expect_tx(bar, rbytes);
+        bulk_g2s(read_buf(V, buf), a.reads + r0, rbytes, bar);
+        return;
+    }
     mbar_arrive_expect_tx(bar, rbytes + wbytes);
     bulk_g2s(read_buf(V, buf), a.reads + r0, rbytes, bar);
     bulk_g2s(win_buf(V, buf), a.ref.packed + sw0, wbytes, bar);
@@ -238,13 +245,16 @@ constexpr int kWorkChunk = 2;     // batch entries a warp takes per atomic: larg
 #ifndef REALIGN_MIN_BLOCKS
 #define REALIGN_MIN_BLOCKS 3      // caps the kernel at 85 registers so that three CTAs of 7 warps fit an SM
 #endif
+#ifndef REALIGN_MIN_BLOCKS_INDEXED
+#define REALIGN_MIN_BLOCKS_INDEXED 4   // index vote: ~5.5 KB of shared memory per warp; 64 registers -> four CTAs of 8 warps
+#endif
 
 // The -g 0 kernel.  DIRECT: direct-address k-mer table (k <= 6); HB: bits per histogram counter and
 // table entry (8 when a slice has at most 255 k-mers).
 // The two rounds are ONE loop body so that the vote and the alignment exist once in the instruction
 // stream: warps of a CTA are in different phases and the kernel has to stay instruction-cache friendly.
-template <bool DIRECT, int HB>
-__global__ void __launch_bounds__(256, REALIGN_MIN_BLOCKS)
+template <bool DIRECT, int HB, bool INDEXED>
+__global__ void __launch_bounds__(256, INDEXED ? REALIGN_MIN_BLOCKS_INDEXED : REALIGN_MIN_BLOCKS)
 realign_kernel(const __grid_constant__ RealignArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -322,8 +332,10 @@ realign_kernel(const __grid_constant__ RealignArgs a)
 #pragma unroll 1
                 for (int round = 0; round < 2; round++) {
                     bool ok;
-                    const int low = vote_band_warp<DIRECT, HB>(a.P, V, swin, sw0, cbase + zs1, (int)(e1 - zs1), (int)zs2,
-                                                               (int)(e2 - zs2), (int)(anc - zs1), &ok);
+                    const int low = INDEXED
+                        ? vote_band_index<HB>(a.P, V, a.idx, cbase + zs1, (int)(e1 - zs1), (int)zs2, (int)(e2 - zs2), (int)(anc - zs1), &ok)
+                        : vote_band_warp<DIRECT, HB>(a.P, V, swin, sw0, cbase + zs1, (int)(e1 - zs1), (int)zs2,
+                                                     (int)(e2 - zs2), (int)(anc - zs1), &ok);
                     if (!ok) {                                       // numdiagonals <= numgaps: the reference aborts (alignment.c:405)
                         if (lane == 0) { s_final[0] = ST_ASSERT; s_plan->status = ST_ASSERT; atomicExch(a.error_flag, 1); }
                         break;

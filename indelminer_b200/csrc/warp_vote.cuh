@@ -13,6 +13,7 @@ namespace indelgpu {
 // per-warp shared-memory slice, computed identically on host and device
 // ---------------------------------------------------------------------------------------
 struct WarpLayout {
+    int indexed;         // 1: the vote reads the resident k-mer index of the reference (kmer_index.cuh): no table, no staged window
     int direct;          // 1: direct-address table of 4^k uint16 entries; 0: open-addressing hash
     int hash_slots;      // power of two (hash only)
     int hist_bits;       // 8 or 16 bits per diagonal counter
@@ -42,9 +43,11 @@ __host__ __device__ inline int cigar_cap(const DevParams& P, int max_read, int b
 // max_numdiag bounds the STAGED window (window 2, alignment.c:780-783) plus the read; max_votediag bounds
 // the diagonals one vote can address.  The two differ: round 1 votes on window 1 (2 * range1 bases) and
 // every round-2 window lies on one side of the anchor (alignment.c:606-706: at most range1 + maxdelsize).
-__host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int max_read, int max_numdiag, int max_votediag, int banded)
+__host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int max_read, int max_numdiag, int max_votediag, int banded,
+                                                       int indexed = 0)
 {
     WarpLayout L;
+    L.indexed = indexed && P.k <= 6;
     L.direct = P.k <= 6;
     int hs = 256;
     #pragma unroll 1
@@ -52,9 +55,10 @@ __host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int m
     L.hash_slots = L.direct ? 0 : hs;
     L.hist_bits = (max_read - P.k + 1 <= 255 && max_votediag <= 65535) ? 8 : 16;
     L.hist_cap = max_votediag;
-    const int tab_bytes = L.direct ? ((L.hist_bits / 8) << (2 * P.k)) : hs * 8;
+    // indexed: two bitmaps over the 4^k codes ("seen in the slice", "seen more than once")
+    const int tab_bytes = L.indexed ? 2 * (((1 << (2 * P.k)) + 31) / 32 * 4) : L.direct ? ((L.hist_bits / 8) << (2 * P.k)) : hs * 8;
     L.hist_words = round_up((max_votediag + 4) * (L.hist_bits / 8), 16) / 4;
-    L.win_bytes = round_up(max_numdiag / 4 + 64, 16);             // window <= max_numdiag bases, 64-base aligned start, hi word
+    L.win_bytes = L.indexed ? 0 : round_up(max_numdiag / 4 + 64, 16);   // window <= max_numdiag bases, 64-base aligned start, hi word
     L.read_bytes = round_up(max_read + 32, 16);
     L.pk_words = max_read / 16 + 3;
     L.ops_cap = cigar_cap(P, max_read, banded);
@@ -73,7 +77,8 @@ __host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int m
     L.off_misc = o;  o += 256;                                     // Aln x 2, Plan, scalars
     // the vote's hit list and the alignment's prefix sums / match bits are never live together: one region
     {
-        const int list_bytes = round_up((32 + 512 + 32) * (L.hist_bits == 8 ? 2 : 4), 16);       // kHitListCap entries
+        // kHitListCap entries (window scan) or kIdxListHits entries (kmer_index.cuh)
+        const int list_bytes = round_up((L.indexed ? 160 : 32 + 512 + 32) * (L.hist_bits == 8 ? 2 : 4), 16);
         const int psum_bytes = round_up((max_read + 2) * 4, 16);
         const int bits_bytes = round_up(((max_read + 127) / 128 * 4 + 4) * 4, 16);
         L.off_list = o; L.off_psum = o; L.off_bits = o + psum_bytes;
@@ -117,8 +122,9 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity)
     #pragma unroll 1
     for (int spin = 0; spin < (1 << 24); spin++) {
         uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        // the time hint lets the hardware suspend the warp until the phase completes instead of spinning on issue slots
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
         if (ok) return true;
     }
     return false;
@@ -241,6 +247,84 @@ __device__ __forceinline__ void tab_store(WarpView& V, uint32_t code, uint32_t v
 }
 
 // ---------------------------------------------------------------------------------------
+// pieces shared by the two votes (window scan below, reference index in kmer_index.cuh)
+// ---------------------------------------------------------------------------------------
+
+// Pass C: n (<= 32) entries of the hit list, one per lane: equal neighbours are merged by ballot and the leader
+// of a run issues ONE shared-memory atomic for the whole run.  For one-diagonal bands select_band
+// (alignment.c:142-181) rides along: the atomic that returns the largest count ever seen is the LAST vote of
+// its diagonal, so every lane keeps the largest count its own atomics produced and, among those, the smallest
+// tie key 2 * |a - i| + (i > a) (nearest to a, the lower index on equal distance).
+template <int HB>
+__device__ __forceinline__ void vote_hits_chunk(WarpView& V, const typename HitIdx<HB>::type* list, int n, int a,
+                                                uint32_t& lbest, uint32_t& lkey)
+{
+    const int lane = threadIdx.x & 31;
+    const bool valid = lane < n;
+    const int idx = valid ? (int)list[lane] : -1;
+    const int prev = __shfl_up_sync(0xFFFFFFFFu, idx, 1);
+    const bool leader = valid && (lane == 0 || idx != prev);
+    const uint32_t leaders = __ballot_sync(0xFFFFFFFFu, leader);
+    if (leader) {
+        const uint32_t rest = (lane == 31) ? 0u : (leaders >> (lane + 1));
+        const uint32_t cnt = (uint32_t)(rest ? __ffs(rest) : n - lane);
+        constexpr int LG = (HB == 8) ? 2 : 1;
+        const int sh = (idx & ((1 << LG) - 1)) * HB;
+        const uint32_t old = atomicAdd(&V.hist[idx >> LG], cnt << sh);
+        const uint32_t now = ((old >> sh) & ((1u << HB) - 1u)) + cnt;
+        const uint32_t key = 2u * (uint32_t)(a > idx ? a - idx : idx - a) + (idx > a ? 1u : 0u);
+        if (now > lbest) { lbest = now; lkey = key; }
+        else if (now == lbest) lkey = min(lkey, key);
+    }
+}
+
+// bin_bands + select_band (alignment.c:130-181) on the finished histogram, which is left zeroed.
+// a = anchor_rel clamped to [-1, numdiag]; lbest / lkey from vote_hits_chunk (used when g == 0).
+template <int HB>
+__device__ __forceinline__ int select_band_warp(WarpView& V, int numdiag, int g, int a, uint32_t lbest, uint32_t lkey)
+{
+    const int lane = threadIdx.x & 31;
+    int idx;
+    constexpr int PER = 32 / HB;                                  // counters per word
+    if (g == 0) {
+        const uint32_t cmax = __reduce_max_sync(0xFFFFFFFFu, lbest);
+        if (cmax == 0u) {                                         // no vote at all: the index nearest to a
+            idx = a < 0 ? 0 : (a > numdiag - 1 ? numdiag - 1 : a);
+        } else {
+            const uint32_t bestkey = __reduce_min_sync(0xFFFFFFFFu, lbest == cmax ? lkey : 0xFFFFFFFFu);
+            idx = (bestkey & 1u) ? a + (int)(bestkey >> 1) : a - (int)(bestkey >> 1);
+            const int nq = ((numdiag + PER - 1) / PER + 3) / 4;   // uint4 chunks
+            uint4* h4 = reinterpret_cast<uint4*>(V.hist);
+            #pragma unroll 1
+            for (int q = lane; q < nq; q += 32) h4[q] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    } else {
+        unsigned long long best = 0;
+        #pragma unroll 1
+        for (int i = lane; i < numdiag; i += 32) {
+            uint32_t b = 0;
+            if (i < numdiag - g)
+                #pragma unroll 1
+                for (int j = 0; j <= g; j++) {
+                    const int t = i + j;
+                    b += (HB == 8) ? ((V.hist[t >> 2] >> ((t & 3) * 8)) & 0xFFu) : ((V.hist[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu);
+                }
+            const uint32_t dist = (uint32_t)(a > i ? a - i : i - a);
+            const unsigned long long key = ((unsigned long long)b << 42) |
+                                           ((unsigned long long)(0x1FFFFFu - dist) << 21) |
+                                           (unsigned long long)(0x1FFFFFu - (uint32_t)i);
+            best = key > best ? key : best;
+        }
+        best = warp_max_u64(best);
+        __syncwarp();
+        #pragma unroll 1
+        for (int s = lane; s < (numdiag + PER - 1) / PER + 1 && s < V.L.hist_words; s += 32) V.hist[s] = 0;
+        idx = (int)(0x1FFFFFu - (uint32_t)(best & 0x1FFFFFu));
+    }
+    return idx;
+}
+
+// ---------------------------------------------------------------------------------------
 // find_best_band for one (window, read slice) pair, executed by one warp.
 //   swin / sw0  staged packed window: swin[w - sw0] is packed word w of the reference
 //   wabs, N     absolute base offset (in packed-reference coordinates) and length of the window
@@ -349,22 +433,7 @@ __device__ __forceinline__ int vote_band_warp(const DevParams& P, WarpView& V, c
 #pragma unroll 1
             while (fill - done >= 32 || (wb + 32 > w1 && fill - done > 0)) {
                 const int n = min(32, fill - done);
-                const bool valid = lane < n;
-                const int idx = valid ? (int)list[done + lane] : -1;
-                const int prev = __shfl_up_sync(0xFFFFFFFFu, idx, 1);
-                const bool leader = valid && (lane == 0 || idx != prev);
-                const uint32_t leaders = __ballot_sync(0xFFFFFFFFu, leader);
-                if (leader) {
-                    const uint32_t rest = (lane == 31) ? 0u : (leaders >> (lane + 1));
-                    const uint32_t cnt = (uint32_t)(rest ? __ffs(rest) : n - lane);
-                    constexpr int LG = (HB == 8) ? 2 : 1;
-                    const int sh = (idx & ((1 << LG) - 1)) * HB;
-                    const uint32_t old = atomicAdd(&V.hist[idx >> LG], cnt << sh);
-                    const uint32_t now = ((old >> sh) & ((1u << HB) - 1u)) + cnt;
-                    const uint32_t key = 2u * (uint32_t)(a > idx ? a - idx : idx - a) + (idx > a ? 1u : 0u);
-                    if (now > lbest) { lbest = now; lkey = key; }
-                    else if (now == lbest) lkey = min(lkey, key);
-                }
+                vote_hits_chunk<HB>(V, list + done, n, a, lbest, lkey);
                 done += n;
             }
             if (done) {                                           // carry the remainder (< 32 entries) to the front
@@ -380,43 +449,7 @@ __device__ __forceinline__ int vote_band_warp(const DevParams& P, WarpView& V, c
     __syncwarp();
 
     // 3. bin_bands + select_band (alignment.c:130-181) and zeroing of the histogram
-    int idx;
-    constexpr int PER = 32 / HB;                                  // counters per word
-    if (g == 0) {
-        const uint32_t cmax = __reduce_max_sync(0xFFFFFFFFu, lbest);
-        if (cmax == 0u) {                                         // no vote at all: the index nearest to a
-            idx = a < 0 ? 0 : (a > numdiag - 1 ? numdiag - 1 : a);
-        } else {
-            const uint32_t bestkey = __reduce_min_sync(0xFFFFFFFFu, lbest == cmax ? lkey : 0xFFFFFFFFu);
-            idx = (bestkey & 1u) ? a + (int)(bestkey >> 1) : a - (int)(bestkey >> 1);
-            const int nq = ((numdiag + PER - 1) / PER + 3) / 4;   // uint4 chunks
-            uint4* h4 = reinterpret_cast<uint4*>(V.hist);
-            #pragma unroll 1
-            for (int q = lane; q < nq; q += 32) h4[q] = make_uint4(0u, 0u, 0u, 0u);
-        }
-    } else {
-        unsigned long long best = 0;
-        #pragma unroll 1
-        for (int i = lane; i < numdiag; i += 32) {
-            uint32_t b = 0;
-            if (i < numdiag - g)
-                #pragma unroll 1
-                for (int j = 0; j <= g; j++) {
-                    const int t = i + j;
-                    b += (HB == 8) ? ((V.hist[t >> 2] >> ((t & 3) * 8)) & 0xFFu) : ((V.hist[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu);
-                }
-            const uint32_t dist = (uint32_t)(a > i ? a - i : i - a);
-            const unsigned long long key = ((unsigned long long)b << 42) |
-                                           ((unsigned long long)(0x1FFFFFu - dist) << 21) |
-                                           (unsigned long long)(0x1FFFFFu - (uint32_t)i);
-            best = key > best ? key : best;
-        }
-        best = warp_max_u64(best);
-        __syncwarp();
-        #pragma unroll 1
-        for (int s = lane; s < (numdiag + PER - 1) / PER + 1 && s < V.L.hist_words; s += 32) V.hist[s] = 0;
-        idx = (int)(0x1FFFFFu - (uint32_t)(best & 0x1FFFFFu));
-    }
+    const int idx = select_band_warp<HB>(V, numdiag, g, a, lbest, lkey);
 
     // 4. leave the table clean for the next vote
     if (DIRECT) {

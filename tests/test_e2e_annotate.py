@@ -64,3 +64,8 @@ def test_annotated_vcf_identical(pair, flags):
     assert batched == ref_vcf
     auto, _ = annotate("indelminer_gpu_annot", pair, flags, dict(INDELGPU_MODE="auto"))
     assert auto == ref_vcf
+    # one pass, no fork: realignment prefetched per block, the support check batched per known variant (two-pass loop)
+    inline, log = annotate("indelminer_gpu_annot", pair, flags, dict(INDELGPU_MODE="inline"))
+    assert inline == ref_vcf
+    m = re.search(r"(\d+) known variants checked, (\d+) \(variant, read\) pairs scored in (\d+) batches", log)
+    assert m and int(m.group(2)) > 100

@@ -95,3 +95,42 @@ def test_auto_mode_single_run_batched(flags, golden):
     assert "697 candidate reads realigned in batches" in r.stderr
     with open(os.path.join(GOLD, golden)) as f:
         assert r.stdout == f.read()
+
+
+@pytest.mark.parametrize("args,golden", [(["-i", "indelminer.config"], "testdata_refrun.vcf"),
+                                         ([], "testdata_refrun_noconfig.vcf"),
+                                         (["-g", "4", "-i", "indelminer.config"], "testdata_refrun_g4.vcf"),
+                                         (["-g", "16", "-i", "indelminer.config"], "testdata_refrun_g16.vcf")])
+def test_inline_mode_one_pass_batched(args, golden):
+    """INDELGPU_MODE=inline (host/indelgpu_inline.c): one pass over the BAM, no fork; a
+    prefetching thread realigns each block of records in one indelgpu_realign_batch while fetch_func -- unchanged --
+    consumes the previous block.  The second case is BASELINE config 1 as written (no -i: insert ranges and coverage
+    are estimated from the BAM first, bamoperations.c:62-147)."""
+    import re
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if not os.path.exists(PROG):
+        pytest.skip("oracle/_ref/indelminer_gpu not built")
+    from indelminer_b200 import build
+    build.build()
+    cmd = [PROG] + args + ["testdata_reference.fa", "sample=alignments.bam"]
+    r = subprocess.run(cmd, cwd=GOLD, capture_output=True, text=True, timeout=600, env=dict(os.environ, INDELGPU_MODE="inline"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    with open(os.path.join(GOLD, golden)) as f:
+        assert r.stdout == f.read()
+    m = re.search(r"(\d+) calls answered from (\d+) prefetched batches \((\d+) reads realigned in them\), (\d+) computed per read", r.stderr)
+    assert m and int(m.group(1)) + int(m.group(4)) == 697 and int(m.group(1)) > 400
+
+
+def test_config1_without_config_file_per_read():
+    """BASELINE config 1 through the per-read path as well"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if not os.path.exists(PROG):
+        pytest.skip("oracle/_ref/indelminer_gpu not built")
+    r = subprocess.run([PROG, "testdata_reference.fa", "sample=alignments.bam"], cwd=GOLD, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    with open(os.path.join(GOLD, "testdata_refrun_noconfig.vcf")) as f:
+        assert r.stdout == f.read()

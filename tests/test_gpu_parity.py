@@ -427,3 +427,47 @@ def test_synthetic_cfg3_batch_exact_vs_oracle(gpu, oracle):
         hist[o.status] = hist.get(o.status, 0) + 1
     assert hist.get(6, 0) > 5000 and hist.get(1, 0) > 200
     R.close()
+
+
+def test_chunked_host_path_with_pinned_buffers(gpu, monkeypatch):
+    """With pinned host buffers every copy of the chunked path is asynchronous: kernel ch+1 runs while chunk
+    ch's results are copied back, and keeps allocating segment words.  The per-chunk segment count must be the
+    one snapshot between the two kernels (capi.cu), or words allocated but not yet written reach the host.
+    Many small chunks, repeated, segment words compared one by one with the unchunked pageable run."""
+    import ctypes as C
+    from indelminer_b200 import lib as _lib, synth
+    L = _lib.load()
+    ref = synth.make_reference(400_000, seed=31)
+    n = 30000
+    w = synth.make_candidates(ref, n, seed=32)
+    R = gpu.Realigner()
+    R.set_reference([ref.tobytes()])
+    a = R.attempt_pe_alignment_batch(None, w["tid"], w["position"], w["range1"], packed=(w["read_bases"], w["read_off"]))
+    want = [list(a.words(i)) for i in range(n)]
+
+    def pinned(arr):
+        p = L.indelgpu_host_alloc(arr.nbytes)
+        out = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(arr.nbytes,)).view(arr.dtype).reshape(arr.shape)
+        out[...] = arr
+        return out, p
+
+    cap = int(L.indelgpu_seg_bound(n, int(w["read_off"][-1])))
+    bufs = {k: pinned(w[k]) for k in ("read_bases", "read_off", "tid", "position", "range1")}
+    outs = {"status": pinned(np.zeros(n, np.int32)), "nseg": pinned(np.zeros(n, np.int32)), "rstart": pinned(np.zeros(n, np.int32)),
+            "seg_off": pinned(np.zeros(n, np.int64)), "segs": pinned(np.zeros(cap, np.uint32))}
+    hb = _lib.Batch(n, *[bufs[k][0].ctypes.data for k in ("read_bases", "read_off", "tid", "position", "range1")])
+    hr = _lib.Result(outs["status"][0].ctypes.data, outs["nseg"][0].ctypes.data, outs["rstart"][0].ctypes.data,
+                     outs["seg_off"][0].ctypes.data, outs["segs"][0].ctypes.data, cap, 0, None, None, None, 0)
+    monkeypatch.setenv("INDELGPU_CHUNK_READS", "512")
+    for rep in range(6):
+        outs["segs"][0][...] = 0xFFFFFFFF
+        assert L.indelgpu_realign_batch(R._ctx, C.byref(hb), C.byref(hr)) == 0, _lib.last_error()
+        assert L.indelgpu_last_launch_count(R._ctx) > 50
+        assert int(hr.seg_count) == a.seg_count
+        assert np.array_equal(outs["status"][0], a.status) and np.array_equal(outs["nseg"][0], a.nseg)
+        so, ns, sg = outs["seg_off"][0], outs["nseg"][0], outs["segs"][0]
+        for i in range(n):
+            assert list(sg[so[i]:so[i] + ns[i]]) == want[i], (rep, i)
+    for v, p in list(bufs.values()) + list(outs.values()):
+        L.indelgpu_host_free(p)
+    R.close()
