@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--tasks", type=int, default=1 << 17, help="alignments / pairs for --workload band / support (SURVEY D1 size: 1048576)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the band sweep, the support check and the VCF wall time")
+    ap.add_argument("--sweep-tasks", type=int, default=1 << 20, help="alignments per band of extra.band_sweep (SURVEY D1: 2^20)")
+    ap.add_argument("--vcf-mb", type=int, default=4, help="contig size of the end-to-end VCF wall-time run")
     return ap.parse_args()
 
 
@@ -182,6 +185,26 @@ def calibrate_cpu_sample(ref, w, cores, target_s=12.0):
     return int(max(probe, min(len(w["position"]), rate * cores * target_s)))
 
 
+def bench_config(a):
+    """the same `config` object for both arms (the driver compares them key by key)"""
+    return {"workload": "cfg3: 64 Mb synthetic contig, planted 1-50 bp indels, 2x150 bp candidates, -g %d -k 6" % a.numgaps,
+            "reads_per_gpu_per_step": a.reads, "ref_mb": a.ref_mb, "read_len": 150, "max_range": 700,
+            "sharding": "contig region per rank, no data-path collective",
+            "l2": "256 MB flush write between timed iterations (outside the event pairs)"}
+
+
+def csrc_sha():
+    """hash of the CUDA sources: ties a committed ncu number to the build it was measured on"""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "indelminer_b200", "csrc")
+    for fn in sorted(os.listdir(d)):
+        if fn.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, fn), "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 # --------------------------------------------------------------------------- main arms
 def run_reference(a, rank, world):
     if rank != 0:
@@ -202,12 +225,12 @@ def run_reference(a, rank, world):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "cfg3: 64 Mb synthetic contig, planted 1-50 bp indels, 2x150 bp candidates, -g 0 -k 6",
-                   "reads_per_step": nsample, "ref_mb": a.ref_mb},
+        "config": bench_config(a),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": used, "kind": kind,
-                         "sample": f"first {nsample} of {a.reads} candidate reads per step, function level "
+                         "sample": f"each step = the first {nsample} of the {a.reads} candidate reads of the config's batch, function level "
                                    "(attempt_diagonal_alignments with windows precomputed; the as-shipped per-read "
-                                   "strlen(contig) of alignment.c:771 is excluded), one process per core"},
+                                   "strlen(contig) of alignment.c:771 is excluded), one forked process per core; the reference "
+                                   "leaks its evidence records (oracle/ref_shim.c), harmless per forked step"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -240,9 +263,9 @@ def run_ours(a, rank, world, local_rank):
     R.set_reference([ref.tobytes()])
 
     if a.workload == "band":
-        return run_band(a, R, L, torch, dev, peak, peak_src)
+        return run_band(a, R, L, torch, dev, peak, peak_src, local_rank)
     if a.workload == "support":
-        return run_support(a, R, L, torch)
+        return run_support(a, R, L, torch, local_rank)
 
     # region sharding: rank r owns the r-th slice of the contig (weak scaling: same count per GPU)
     Lr = len(ref)
@@ -356,11 +379,8 @@ def run_ours(a, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "cfg3: 64 Mb synthetic contig, planted 1-50 bp indels, 2x150 bp candidates, -g %d -k 6" % a.numgaps,
-                   "reads_per_gpu_per_step": n, "ref_mb": a.ref_mb, "read_len": M, "max_range": max_range,
-                   "sharding": "contig region per rank, no data-path collective",
-                   "l2": "256 MB flush write between timed iterations (outside the event pairs)",
-                   "split_reads_per_step": nsplit},
+        "config": bench_config(a),
+        "split_reads_per_step": nsplit,
         "gcups": cells / kernel_s / 1e9,
         "cells_per_step": {"forward": cf, "reverse": cr, "align": cg},
         "clocks": clocks,
@@ -372,23 +392,24 @@ def run_ours(a, rank, world, local_rank):
                                else "pipe_vote / pipe_dp / pipe_combine (5 launches per step; time = whole step)",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_s * 1e3, "peak_source": peak_src},
     }
-    if a.numgaps == 0 and clocks.get("sm_mhz"):
-        # why the HBM fraction is small: the kernel is bound by instruction issue (k-mer vote), not by bytes.
-        # Executed warp instructions per read come from the committed ncu capture; the rate is measured here.
-        sms = R.sm_count
-        peak_issue = sms * 4 * clocks["sm_mhz"] * 1e6                     # 4 schedulers per SM, 1 warp instruction / clk each
-        line["roofline"]["issue"] = {
-            "warp_instr_per_read": NCU_WARP_INSTR_PER_READ, "source": "profiles/r01_v11_realign_kernel_ncu_full.csv (ncu)",
-            "achieved_gwarp_instr_s": NCU_WARP_INSTR_PER_READ * (n / kernel_s) / 1e9,
-            "peak_gwarp_instr_s": peak_issue / 1e9,
-            "frac": NCU_WARP_INSTR_PER_READ * (n / kernel_s) / peak_issue}
+    assert M == 150 and max_range == 700, "bench_config() states the generator's read length and range"
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof) and a.numgaps == 0 and a.reads == 1 << 20:
+        # DRAM bytes of one launch from the committed `ncu --set full` capture -- only if it was taken on THIS build
         try:
             with open(prof) as f:
-                line["roofline"]["traffic"] = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            if tj.get("csrc_sha") == csrc_sha():
+                line["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
+                line["roofline"]["traffic_source"] = tj.get("source")
         except Exception:
             pass
+    err_flag = L.indelgpu_last_error_flag(R._ctx)
+    assert err_flag == 0, f"device error flag {err_flag} after the timed region"
+    if rank == 0:
+        # the timed batch itself, spot-checked against the oracle after the timed region (never inside it)
+        line["oracle_spot_check"] = spot_check(R, w, d_status.cpu().numpy(), d_nseg.cpu().numpy(), d_rstart.cpu().numpy(),
+                                               d_segoff.cpu().numpy(), d_segs.cpu().numpy(), ref, 4096)
     if rank == 0 and world == 1 and not a.no_cpu:
         cores = os.cpu_count() or 1
         nsample = a.cpu_sample or calibrate_cpu_sample(ref, w, cores)
@@ -402,13 +423,88 @@ def run_ours(a, rank, world, local_rank):
             "as_shipped_1core": srate,
             "as_shipped_note": f"attempt_pe_alignment incl. its per-read strlen(contig) (alignment.c:771), {shipped_n} reads, 1 core",
         }
+    if rank == 0 and world == 1 and not a.no_extra:
+        # the other parts of BASELINE.json's metric, measured in the same process and clock-stamped:
+        # banded-DP GCUPS against the INT32 issue rate (D1 sweep), the support check (row f1), end-to-end VCF wall time
+        line["extra"] = {}
+        try:
+            line["extra"]["band_sweep"] = band_sweep(a, R, L, torch, local_rank)
+        except Exception as e:                                   # noqa: BLE001  (the headline must survive)
+            line["extra"]["band_sweep"] = {"error": repr(e)}
+        try:
+            line["extra"]["support"] = support_line(a, R, L, torch, local_rank, tasks=1 << 17, steps=100, warmup=2, cpu=False)
+        except Exception as e:                                   # noqa: BLE001
+            line["extra"]["support"] = {"error": repr(e)}
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import e2e_inline
+            if e2e_inline.have_programs():
+                line["vcf_wall_time"] = e2e_inline.vcf_wall_time(length=a.vcf_mb * 1_000_000, depth=30, modes=("inline",))
+            else:
+                line["vcf_wall_time"] = {"unavailable": "oracle/_ref programs not built (they need /root/reference at build time)"}
+        except Exception as e:                                   # noqa: BLE001
+            line["vcf_wall_time"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
-def run_band(a, R, L, torch, dev, peak, peak_src):
+def spot_check(R, w, status, nseg, rstart, seg_off, segs, ref, count):
+    """`count` reads spread over the timed batch, realigned by the oracle and compared (status, start, segment words)"""
+    from oracle import oracle as O
+    from indelminer_b200.api import walk_segments
+    p = O.default_params()
+    cs = ref.tobytes()
+    M = w["read_len"]
+    n = len(status)
+    bad = 0
+    idx = np.linspace(0, n - 1, count).astype(np.int64)
+    for i in idx:
+        o = O.realign_read(p, cs, int(w["position"][i]), int(w["range1"][i]), w["read_bases"][i * M:(i + 1) * M].tobytes())
+        words = segs[seg_off[i]:seg_off[i] + nseg[i]].view(np.uint32)
+        got = walk_segments(int(rstart[i]), words) if nseg[i] else []
+        if int(status[i]) != o.status or got != o.segments():
+            bad += 1
+    return {"reads": int(count), "mismatches": int(bad), "checker": "oracle/indel_oracle.c orc_realign_read"}
+
+
+def band_sweep(a, R, L, torch, dev_index):
+    """D1: bands 1..129 at 2^20 alignments, every band with its own clocks record"""
+    from indelminer_b200 import synth
+    gops = C.c_double(0)
+    if L.indelgpu_int32_peak(R._ctx, C.byref(gops)) != 0:
+        raise RuntimeError(_liberr())
+    out = {"tasks": a.sweep_tasks, "shape": "M=150, N=1410, 1 % substitutions, half of the reads with one 1-50 bp indel",
+           "int32_peak_gops": gops.value, "int_ops_per_cell": INT_OPS_PER_CELL,
+           "peak_source": "measured in this process: indelgpu_int32_peak (independent add + max chains)", "bands": []}
+    t = synth.make_band_tasks(a.sweep_tasks, 0)
+    packed = (t["reads"], t["read_off"], t["wins"], t["win_off"])
+    for band in (1, 5, 9, 17, 33, 65, 129):
+        low = (t["true_off"] - band // 2).astype(np.int32)
+        up = (low + band - 1).astype(np.int32)
+        R.band_align_batch(None, None, low, up, packed=packed, want_cigar=False)          # warm-up
+        sampler = ClockSampler(dev_index)
+        sampler.start()
+        kms, launches = [], 0
+        for _ in range(3):
+            res = R.band_align_batch(None, None, low, up, packed=packed, want_cigar=False)
+            kms.append(L.indelgpu_last_kernel_ms(R._ctx))
+            launches += 1
+        clocks = sampler.stop()
+        cells = int(res["cells"].sum())
+        executed = cells - res["shortcut_cells"]
+        k_s = float(np.mean(kms)) / 1e3
+        gc = cells / k_s / 1e9
+        out["bands"].append({"band": band, "kernel_ms": k_s * 1e3, "gcups": gc, "gcups_executed_cells": executed / k_s / 1e9,
+                             "cells": {"forward": int(res["cells"][0]), "reverse": int(res["cells"][1]), "align": int(res["cells"][2]),
+                                       "align_not_swept_shortcut": int(res["shortcut_cells"])},
+                             "frac_of_int32_peak": gc * INT_OPS_PER_CELL / gops.value if gops.value else None,
+                             "gpu_launches": launches, "clocks": clocks})
+    return out
+
+
+def run_band(a, R, L, torch, dev, peak, peak_src, dev_index=0):
     """D1: banded local_align + ALIGN + fetch_cigar on independent tasks; GCUPS of the
     kernel (CUDA events around the launch, inside the library) against the INT32 issue rate measured on
     this GPU by indelgpu_int32_peak, at INT_OPS_PER_CELL integer operations per DP cell."""
@@ -421,12 +517,15 @@ def run_band(a, R, L, torch, dev, peak, peak_src):
     for _ in range(a.warmup):
         out = R.band_align_batch(None, None, t["low"], t["up"], packed=packed)
     torch.cuda.synchronize()
+    sampler = ClockSampler(dev_index)
+    sampler.start()
     kms, wall = [], []
     for _ in range(a.steps):
         t0 = time.perf_counter()
         out = R.band_align_batch(None, None, t["low"], t["up"], packed=packed)
         wall.append(time.perf_counter() - t0)
         kms.append(L.indelgpu_last_kernel_ms(R._ctx))
+    clocks = sampler.stop()
     cells = int(out["cells"].sum())
     k_s = float(np.mean(kms)) / 1e3
     gcups = cells / k_s / 1e9
@@ -434,7 +533,10 @@ def run_band(a, R, L, torch, dev, peak, peak_src):
             "warmup": a.warmup, "ms_per_step": k_s * 1e3, "higher_is_better": True, "dtype": "int32", "data": "synthetic",
             "config": {"workload": f"D1 band sweep: {a.tasks} alignments, M=150, N=1410, band={a.band}",
                        "timing": "CUDA events around the kernel on the library's stream"},
-            "cells_per_step": {"forward": int(out["cells"][0]), "reverse": int(out["cells"][1]), "align": int(out["cells"][2])},
+            "cells_per_step": {"forward": int(out["cells"][0]), "reverse": int(out["cells"][1]), "align": int(out["cells"][2]),
+                               "align_not_swept_shortcut": int(out["shortcut_cells"])},
+            "gcups_executed_cells": (cells - out["shortcut_cells"]) / k_s / 1e9,
+            "gpu_launches": a.steps, "clocks": clocks,
             "e2e": {"value": cells / float(np.mean(wall)) / 1e9, "unit": "GCUPS", "note": "host buffers in and out, copies included"},
             "roofline": {"bound": "int32", "achieved": gcups * INT_OPS_PER_CELL, "peak": gops.value, "unit": "Gop/s",
                          "frac": gcups * INT_OPS_PER_CELL / gops.value if gops.value else None,
@@ -443,62 +545,66 @@ def run_band(a, R, L, torch, dev, peak, peak_src):
     print(json.dumps(line), flush=True)
 
 
-NCU_WARP_INSTR_PER_READ = 4710  # realign_kernel: 4 938 399 073 executed warp instructions / 1 048 576 reads (ncu, r01 v11)
 SUPPORT_OPS_PER_CELL = 26      # integer instructions per DP cell of the wavefront kernel (SASS count)
 
 
-def run_support(a, R, L, torch):
+def support_line(a, R, L, torch, dev_index, tasks, steps, warmup, cpu):
     """Row f1: the known-indel support check, realign_with_indel (variant.c:1246-1424), on
-    --tasks (target, query) pairs; GCUPS of the kernel (CUDA events inside the library) against the INT32
+    `tasks` (target, query) pairs; GCUPS of the kernel (CUDA events inside the library) against the INT32
     issue rate measured here, and the oracle's C port timed on a sample of the same pairs."""
     from indelminer_b200 import synth
-    t = synth.make_support_tasks(a.tasks)
+    t = synth.make_support_tasks(tasks)
     pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()      # noqa: E731  (host buffers, pinned)
     packed = (pin(t["targets"]), pin(t["target_off"]), pin(t["queries"]), pin(t["query_off"]))
-    outbuf = tuple(pin(np.zeros(a.tasks, dtype=np.int32)) for _ in range(3))
+    outbuf = tuple(pin(np.zeros(tasks, dtype=np.int32)) for _ in range(3))
     gops = C.c_double(0)
     if L.indelgpu_int32_peak(R._ctx, C.byref(gops)) != 0:
         raise RuntimeError(_liberr())
-    for _ in range(a.warmup):
+    for _ in range(warmup):
         out = R.indel_support_batch(None, None, packed=packed, out=outbuf)
     torch.cuda.synchronize()
-    kms, wall = [], []
-    for _ in range(a.steps):
+    sampler = ClockSampler(dev_index)
+    sampler.start()
+    kms, wall, launches = [], [], 0
+    for _ in range(steps):
         t0 = time.perf_counter()
         out = R.indel_support_batch(None, None, packed=packed, out=outbuf)
         wall.append(time.perf_counter() - t0)
         kms.append(L.indelgpu_last_kernel_ms(R._ctx))
+        launches += int(L.indelgpu_last_launch_count(R._ctx))
+    clocks = sampler.stop()
     cells = int(out["cells"])
     k_s = float(np.mean(kms)) / 1e3
     gcups = cells / k_s / 1e9
-    cpu = None
-    if not a.no_cpu:
-        from oracle import oracle as O          # the checker, timed as the CPU baseline (one core)
-        ns = min(a.tasks, 4096)
-        t0 = time.perf_counter()
-        cc = [0]
-        for k in range(ns):
-            tt = t["targets"][t["target_off"][k]:t["target_off"][k + 1]].tobytes()
-            q = t["queries"][t["query_off"][k]:t["query_off"][k + 1]].tobytes()
-            r = O.indel_support_dp(tt, q, cells=cc)
-            assert r == (int(out["subs"][k]), int(out["indels"][k]), int(out["aligned"][k])), k
-        dt = time.perf_counter() - t0
-        cpu = {"value": cc[0] / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port",
-               "sample": f"first {ns} pairs through oracle/indel_oracle.c orc_indel_support_dp (results compared)"}
-    line = {"metric": "indel_support_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": 1, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": k_s * 1e3, "higher_is_better": True, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"f1 known-indel support: {a.tasks} pairs, 150 bp reads, 1-50 bp indels, target ~{int(t['target_off'][-1] / a.tasks)} bp",
-                       "timing": "CUDA events around the kernel on the library's stream"},
-            "pairs_per_s": a.tasks / k_s, "gpu_launches": int(L.indelgpu_last_launch_count(R._ctx)),
-            "e2e": {"value": cells / float(np.mean(wall)) / 1e9, "unit": "GCUPS", "pairs_per_s": a.tasks / float(np.mean(wall)),
+    from oracle import oracle as O          # the checker: a sample of the timed batch compared; timed as the CPU baseline when asked
+    ns = min(tasks, 4096 if cpu else 512)
+    t0 = time.perf_counter()
+    cc = [0]
+    for k in range(ns):
+        tt = t["targets"][t["target_off"][k]:t["target_off"][k + 1]].tobytes()
+        q = t["queries"][t["query_off"][k]:t["query_off"][k + 1]].tobytes()
+        r = O.indel_support_dp(tt, q, cells=cc)
+        assert r == (int(out["subs"][k]), int(out["indels"][k]), int(out["aligned"][k])), k
+    dt = time.perf_counter() - t0
+    cpu_obj = {"value": cc[0] / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port",
+               "sample": f"first {ns} pairs through oracle/indel_oracle.c orc_indel_support_dp (results compared)"} if cpu else None
+    return {"metric": "indel_support_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": 1, "steps": steps,
+            "warmup": warmup, "ms_per_step": k_s * 1e3, "higher_is_better": True, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"f1 known-indel support: {tasks} pairs, 150 bp reads, 1-50 bp indels, target ~{int(t['target_off'][-1] / tasks)} bp",
+                       "timing": "CUDA events around the kernels on the library's stream"},
+            "pairs_per_s": tasks / k_s, "gpu_launches": launches, "clocks": clocks, "oracle_checked_pairs": ns,
+            "e2e": {"value": cells / float(np.mean(wall)) / 1e9, "unit": "GCUPS", "pairs_per_s": tasks / float(np.mean(wall)),
                     "note": "host buffers in and out, copies included"},
             "roofline": {"bound": "int32", "achieved": gcups * SUPPORT_OPS_PER_CELL, "peak": gops.value, "unit": "Gop/s",
                          "frac": gcups * SUPPORT_OPS_PER_CELL / gops.value if gops.value else None,
                          "int_ops_per_cell": SUPPORT_OPS_PER_CELL,
                          "frac_at_10_ops_per_cell": gcups * INT_OPS_PER_CELL / gops.value if gops.value else None,
                          "peak_source": "measured here: indelgpu_int32_peak (independent add + max chains)"},
-            "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+            "cpu_baseline": cpu_obj}
+
+
+def run_support(a, R, L, torch, dev_index=0):
+    print(json.dumps(support_line(a, R, L, torch, dev_index, a.tasks, a.steps, a.warmup, not a.no_cpu)), flush=True)
 
 
 def _liberr():

@@ -70,8 +70,17 @@ static void gpu_die(const char* what)
     fatalf("libindelgpu: %s: %s", what, indelgpu_last_error());
 }
 
+#include <time.h>
+static double now_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+}
+
 static indelgpu_ctx* make_ctx(void)
 {
+    const double t0 = now_ms();
     indelgpu_params p;
     indelgpu_default_params(&p);
     p.klength = (int32_t)klength;
@@ -81,6 +90,7 @@ static indelgpu_ctx* make_ctx(void)
     const char* dev = getenv("INDELGPU_DEVICE");
     indelgpu_ctx* c = indelgpu_create(dev ? atoi(dev) : 0, &p);
     if (c == NULL) gpu_die("indelgpu_create");
+    if (getenv("INDELGPU_VERBOSE")) fprintf(stderr, "libindelgpu: context created in %.0f ms\n", now_ms() - t0);
     return c;
 }
 
@@ -108,7 +118,9 @@ static indelgpu_ctx* ctx_for_contig(char** const sequences, const int32_t tid, i
         const char* seq = sequences[tid];
         const int64_t len = (int64_t)strlen(seq);        /* once per contig, not per read (alignment.c:771) */
         g_slots[tid].ctx = make_ctx();
+        const double t0 = now_ms();
         if (indelgpu_set_reference(g_slots[tid].ctx, 1, &seq, &len) != 0) gpu_die("indelgpu_set_reference");
+        if (getenv("INDELGPU_VERBOSE")) fprintf(stderr, "libindelgpu: contig %d (%lld bases) uploaded in %.0f ms\n", tid, (long long)len, now_ms() - t0);
     }
     *ptid = 0;
     return g_slots[tid].ctx;

@@ -82,6 +82,8 @@ static pf_block g_blk[2];
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static pthread_cond_t g_cv = PTHREAD_COND_INITIALIZER;
 
+static int g_consumed = 0;                 /* blocks of the current region fetch_func has finished */
+
 static const pf_block* g_cur_blk = NULL;   /* the record fetch_func is looking at right now */
 static int g_cur_idx = -1;
 static int g_in_fetch = 0;
@@ -226,6 +228,21 @@ static void* producer_main(void* arg)
         pf_block* k = &g_blk[serial & 1];
         pthread_mutex_lock(&g_mu);
         while (k->full) pthread_cond_wait(&g_cv, &g_mu);
+        /* Until a call has taught this file the contig's context and a read group's range nothing can be
+         * prefetched: do not run ahead of fetch_func then, or the blocks filled in the meantime are all misses */
+        while (g_consumed < serial) {
+            int32_t dtid;
+            pthread_mutex_unlock(&g_mu);
+            pthread_mutex_lock(&indelgpu_glue_gpu_mu);
+            const int ready = indelgpu_glue_ctx_peek(pa->tid, &dtid) != NULL;
+            pthread_mutex_unlock(&indelgpu_glue_gpu_mu);
+            pthread_mutex_lock(&g_rg_mu);
+            const int known = g_nrg > 0;
+            pthread_mutex_unlock(&g_rg_mu);
+            pthread_mutex_lock(&g_mu);
+            if (ready && known) break;
+            if (g_consumed < serial) pthread_cond_wait(&g_cv, &g_mu);
+        }
         pthread_mutex_unlock(&g_mu);
         fill_block(k, pa, serial);
         const int last = k->last;
@@ -253,6 +270,7 @@ int indelgpu_bam_fetch(bamFile fp, const bam_index_t* idx, int tid, int beg, int
     pa.fp = fp; pa.tid = tid;
     pa.iter = bam_iter_query(idx, tid, beg, end);
     g_blk[0].full = g_blk[1].full = 0;
+    g_consumed = 0;
     pthread_t thr;
     if (pthread_create(&thr, NULL, producer_main, &pa) != 0) fatalf("libindelgpu: inline mode: cannot start the prefetching thread");
     int ret = 0;
@@ -272,6 +290,7 @@ int indelgpu_bam_fetch(bamFile fp, const bam_index_t* idx, int tid, int beg, int
         ret = k->ret;
         pthread_mutex_lock(&g_mu);
         k->full = 0;
+        g_consumed = serial + 1;
         pthread_cond_broadcast(&g_cv);
         pthread_mutex_unlock(&g_mu);
         if (last) break;

@@ -162,6 +162,11 @@ int indelgpu_realign_batch_device(indelgpu_ctx* ctx, const indelgpu_batch* d_in,
  *   out[3]     algorithmic bytes: sum over alignments of N + M + 4 * (6 + ncigar) */
 int indelgpu_last_counters(indelgpu_ctx* ctx, int64_t out[4]);
 
+/* ALIGN cells of the last indelgpu_band_align_batch that the cell counters include (they count what the
+ * reference sweeps) but that were not swept on the GPU: the unique-diagonal shortcut.  Executed cells =
+ * forward + reverse + align - *out. */
+int indelgpu_last_shortcut_cells(indelgpu_ctx* ctx, int64_t* out);
+
 /* Error flag the kernels of the last batch left on the device (waits for them): 0 none; 1 at least one
  * read was rejected (status INDELGPU_ST_ASSERT); 2 the segment buffer overflowed -- nseg / seg_off are
  * set but the words were not written, compare *d_seg_count with seg_capacity; 3 a TMA bulk copy never

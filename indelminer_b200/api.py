@@ -127,9 +127,10 @@ class Realigner:
     # ------------------------------------------------------------------ reference
     def set_reference(self, sequences):
         """`char** sequences` of attempt_pe_alignment: one upper-cased string per contig."""
-        bs = [_as_bytes(s) for s in sequences]
+        # numpy uint8 arrays are passed by address (a 3.1 Gb genome is not copied into bytes objects first)
+        bs = [s if isinstance(s, np.ndarray) else _as_bytes(s) for s in sequences]
         n = len(bs)
-        ptrs = (C.c_char_p * n)(*bs)
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data if isinstance(b, np.ndarray) else C.cast(C.c_char_p(b), C.c_void_p).value for b in bs])
         lens = (C.c_int64 * n)(*[len(b) for b in bs])
         _check(self._L.indelgpu_set_reference(self._ctx, n, ptrs, lens))
         self.contig_lengths = [len(b) for b in bs]
@@ -198,9 +199,11 @@ class Realigner:
                                             [_as_bytes(refseq)[zstart1:end1]], a)
         return int(low[0]), int(up[0])
 
-    def band_align_batch(self, reads, windows, low, up, want_script=False, packed=None):
+    def band_align_batch(self, reads, windows, low, up, want_script=False, packed=None, want_cigar=True):
         """local_align (+ALIGN) + fetch_cigar on independent tasks.
-        Returns dict(score, ends[n,4] = (si, sj, ei, ej), ncigar, cigar[n,stride], script, cells)."""
+        Returns dict(score, ends[n,4] = (si, sj, ei, ej), ncigar, cigar[n,stride], script, cells, shortcut_cells).
+        want_cigar=False leaves the CIGAR words on the device (band-sweep micro-bench: scores, end points and
+        CIGAR lengths still come back)."""
         if packed is not None:
             rd, roff, wd, woff = packed
         else:
@@ -216,15 +219,17 @@ class Realigner:
         score = np.zeros(n, dtype=np.int32)
         ends = np.zeros((n, 4), dtype=np.int32)
         ncig = np.zeros(n, dtype=np.int32)
-        cig = np.zeros((n, cstride), dtype=np.uint32)
+        cig = np.zeros((n, cstride), dtype=np.uint32) if want_cigar else None
         script = np.zeros((n, sstride), dtype=np.int32) if want_script else None
         cells = np.zeros(3, dtype=np.int64)
         _check(self._L.indelgpu_band_align_batch(
             self._ctx, n, rd.ctypes.data, roff.ctypes.data, wd.ctypes.data, woff.ctypes.data,
             low.ctypes.data, up.ctypes.data, score.ctypes.data, ends.ctypes.data, ncig.ctypes.data,
-            cig.ctypes.data, cstride, script.ctypes.data if want_script else None, sstride,
+            cig.ctypes.data if want_cigar else None, cstride if want_cigar else 0, script.ctypes.data if want_script else None, sstride,
             cells.ctypes.data))
-        return dict(score=score, ends=ends, ncigar=ncig, cigar=cig, script=script, cells=cells)
+        skipped = C.c_int64(0)
+        _check(self._L.indelgpu_last_shortcut_cells(self._ctx, C.byref(skipped)))
+        return dict(score=score, ends=ends, ncigar=ncig, cigar=cig, script=script, cells=cells, shortcut_cells=int(skipped.value))
 
     def indel_support_batch(self, targets, queries, packed=None, out=None):
         """Batched realign_with_indel (variant.c:1246-1424) on already built targets (the reference interval

@@ -103,7 +103,7 @@ struct indelgpu_ctx {
     DevBuf in_reads, in_off, in_tid, in_pos, in_rng;
     DevBuf out_status, out_nseg, out_rstart, out_segoff, out_segs, out_detail, out_cig1, out_cig2;
     DevBuf chunk_counts;     // chunked host path: segment count after each chunk's kernel, snapshot in stream order
-    DevBuf counters;         // bytes: 0 work counter (int) | 8 seg count (u64) | 16 cells (3 x u64) | 40 error flag (int) | 48 algorithmic bytes (u64)
+    DevBuf counters;         // bytes: 0 work counter (int) | 8 seg count (u64) | 16 cells (3 x u64) | 40 error flag (int) | 48 algorithmic bytes (u64) | 56 ALIGN cells not swept (u64, band tasks)
     DevBuf scratch;
     DevBuf s_tgt, s_toff, s_qry, s_qoff, s_out, s_ord, s_idx, s_V, s_I, s_F;
     int32_t* h_order = nullptr; size_t h_order_cap = 0;            // pinned work list of the support check   // known-indel support check (indel_support.cuh)
@@ -517,6 +517,19 @@ extern "C" int indelgpu_last_counters(indelgpu_ctx* c, int64_t out[4])
     CU(cudaMemcpy(c->pinned_small, c->counters.p, 64, cudaMemcpyDeviceToHost));
     memcpy(out, (char*)c->pinned_small + 16, 24);
     memcpy(out + 3, (char*)c->pinned_small + 48, 8);
+    return 0;
+}
+
+// ALIGN cells of the last indelgpu_band_align_batch that were counted (SURVEY.md 8d defines Gc by what the reference
+// sweeps) but NOT swept here, because the unique-diagonal shortcut proved the all-REP script optimal (band_dp.cuh).
+// executed cells = forward + reverse + align - this.
+extern "C" int indelgpu_last_shortcut_cells(indelgpu_ctx* c, int64_t* out)
+{
+    if (!c || !out) return fail(INDELGPU_EINVAL, "last_shortcut_cells: NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(c->pinned_small, c->counters.p, 64, cudaMemcpyDeviceToHost));
+    memcpy(out, (char*)c->pinned_small + 56, 8);
     return 0;
 }
 

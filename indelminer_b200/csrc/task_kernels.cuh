@@ -156,7 +156,7 @@ band_tasks_kernel(const __grid_constant__ TaskArgs a)
     const IArr<32> gbase{a.scratch.base + (long long)gwarp * 32 * a.scratch.stride + lane};
     const IArr<32> bands = gbase;            // L1-resident; shared memory measured slower (it costs resident warps)
     const IArr<32> rowsb = gbase + wb4;
-    unsigned long long cf = 0, cr = 0, cg = 0;
+    unsigned long long cf = 0, cr = 0, cg = 0, cskip = 0;          // cskip: ALIGN cells counted but not swept (unique-diagonal shortcut)
     DcFrame st[kDcFrames];
 
     auto geometry = [&](int idx, const uint8_t** read, int* M, const uint8_t** win, int* N, int* lo, int* hi) {
@@ -202,7 +202,7 @@ band_tasks_kernel(const __grid_constant__ TaskArgs a)
         bool need = false;
         if (!L.none) {
             if (band_unique_diagonal(a.P, read, M, win, lo, hi, L, a.cigar + (int64_t)idx * a.cigar_stride, &n, &cells)) {
-                cg += (unsigned long long)cells;
+                cg += (unsigned long long)cells; cskip += (unsigned long long)cells;
                 if (a.script) {
                     int32_t* so = a.script + (int64_t)idx * a.script_stride;
                     const int len = L.endi - L.starti + 1;
@@ -242,10 +242,12 @@ band_tasks_kernel(const __grid_constant__ TaskArgs a)
     cf = warp_sum_u64(cf);
     cr = warp_sum_u64(cr);
     cg = warp_sum_u64(cg);
+    cskip = warp_sum_u64(cskip);
     if (lane == 0 && (cf | cr | cg)) {
         atomicAdd(a.cell_totals + 0, cf);
         atomicAdd(a.cell_totals + 1, cr);
         atomicAdd(a.cell_totals + 2, cg);
+        atomicAdd(a.cell_totals + 5, cskip);          // counters byte 56
     }
 }
 

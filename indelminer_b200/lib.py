@@ -15,7 +15,7 @@ EXPORTS = [
     "indelgpu_create", "indelgpu_destroy", "indelgpu_device", "indelgpu_sm_count",
     "indelgpu_host_alloc", "indelgpu_host_free", "indelgpu_set_reference",
     "indelgpu_seg_bound", "indelgpu_realign_batch", "indelgpu_realign_batch_device",
-    "indelgpu_last_counters", "indelgpu_last_error_flag", "indelgpu_last_launch_count", "indelgpu_last_kernel_ms", "indelgpu_int32_peak",
+    "indelgpu_last_counters", "indelgpu_last_error_flag", "indelgpu_last_shortcut_cells", "indelgpu_last_launch_count", "indelgpu_last_kernel_ms", "indelgpu_int32_peak",
     "indelgpu_find_best_band_batch", "indelgpu_band_align_batch", "indelgpu_indel_support_batch", "indelgpu_device_count",
     "local_align", "ALIGN", "DISPLAY", "fetch_cigar",
 ]
@@ -78,6 +78,7 @@ def load():
     L.indelgpu_last_counters.argtypes = [C.c_void_p, C.c_void_p]
     L.indelgpu_last_launch_count.argtypes = [C.c_void_p]
     L.indelgpu_last_error_flag.argtypes = [C.c_void_p]
+    L.indelgpu_last_shortcut_cells.argtypes = [C.c_void_p, C.c_void_p]
     L.indelgpu_last_kernel_ms.restype = C.c_double
     L.indelgpu_last_kernel_ms.argtypes = [C.c_void_p]
     L.indelgpu_int32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]

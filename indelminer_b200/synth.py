@@ -94,27 +94,34 @@ def make_band_tasks(n, band, seed=20261018, read_len=150, win_len=1410, ref_seed
     L = 1 << 22
     ref = make_reference(L, seed=ref_seed, n_frac=0.001)
     M, N = read_len, win_len
-    wstart = rng.integers(0, L - N - 200, size=n)
-    off = rng.integers(0, N - M - 60, size=n)         # true offset of the read in its window
-    cols = np.arange(M, dtype=np.int64)[None, :]
+    wstart = rng.integers(0, L - N - 200, size=n).astype(np.int32)
+    off = rng.integers(0, N - M - 60, size=n).astype(np.int32)         # true offset of the read in its window
     has = rng.random(n) < 0.5
     isdel = rng.random(n) < 0.5
-    sl = rng.integers(1, 51, size=n)
-    cut = rng.integers(12, M - 12, size=n)
-    idx = (wstart + off)[:, None] + cols
-    after = cols >= cut[:, None]
-    idx = np.where((has & isdel)[:, None] & after, idx + sl[:, None], idx)
-    insz = (has & ~isdel)[:, None] & after & (cols < (cut + sl)[:, None])
-    idx = np.where((has & ~isdel)[:, None] & (cols >= (cut + sl)[:, None]), idx - sl[:, None], idx)
-    reads = ref[np.clip(idx, 0, L - 1)]
-    reads = np.where(insz, ACGT[rng.integers(0, 4, size=(n, M), dtype=np.uint8)], reads)
-    reads = np.where(rng.random((n, M)) < 0.01, ACGT[rng.integers(0, 4, size=(n, M), dtype=np.uint8)], reads)
-    wins = ref[wstart[:, None] + np.arange(N, dtype=np.int64)[None, :]]
+    sl = rng.integers(1, 51, size=n).astype(np.int32)
+    cut = rng.integers(12, M - 12, size=n).astype(np.int32)
+    reads = np.empty((n, M), dtype=np.uint8)
+    wins = np.empty((n, N), dtype=np.uint8)
+    cols = np.arange(M, dtype=np.int32)[None, :]
+    wcols = np.arange(N, dtype=np.int32)[None, :]
+    for c0 in range(0, n, 1 << 15):                                     # chunks keep the index arrays small at n = 2^20
+        c = slice(c0, min(n, c0 + (1 << 15)))
+        m = c.stop - c.start
+        idx = (wstart[c] + off[c])[:, None] + cols
+        after = cols >= cut[c][:, None]
+        idx = np.where((has[c] & isdel[c])[:, None] & after, idx + sl[c][:, None], idx)
+        insz = (has[c] & ~isdel[c])[:, None] & after & (cols < (cut[c] + sl[c])[:, None])
+        idx = np.where((has[c] & ~isdel[c])[:, None] & (cols >= (cut[c] + sl[c])[:, None]), idx - sl[c][:, None], idx)
+        blk = ref[np.clip(idx, 0, L - 1)]
+        blk = np.where(insz, ACGT[rng.integers(0, 4, size=(m, M), dtype=np.uint8)], blk)
+        blk = np.where(rng.random((m, M), dtype=np.float32) < 0.01, ACGT[rng.integers(0, 4, size=(m, M), dtype=np.uint8)], blk)
+        reads[c] = blk
+        wins[c] = ref[wstart[c][:, None] + wcols]
     low = (off - band // 2).astype(np.int32)
     up = (low + band - 1).astype(np.int32)
     return dict(reads=np.ascontiguousarray(reads.reshape(-1)), read_off=np.arange(n + 1, dtype=np.int64) * M,
                 wins=np.ascontiguousarray(wins.reshape(-1)), win_off=np.arange(n + 1, dtype=np.int64) * N,
-                low=low, up=up)
+                low=low, up=up, true_off=off)
 
 
 def make_support_tasks(n, seed=20261018, read_len=150, max_indel=50, ref_len=1 << 22, sub_rate=0.01):

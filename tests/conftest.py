@@ -17,3 +17,14 @@ def oracle():
     from oracle import oracle as O
     O.build(ref=True)
     return O
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from indelminer_b200 import build
+    build.build()
+    import indelminer_b200
+    return indelminer_b200
