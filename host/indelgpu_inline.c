@@ -89,6 +89,15 @@ static int g_cur_idx = -1;
 static int g_in_fetch = 0;
 
 static long long g_hits = 0, g_direct = 0, g_prefetched = 0, g_batches = 0, g_records = 0;
+static double g_t_read = 0, g_t_gpu = 0, g_t_prod_wait = 0, g_t_cons_wait = 0, g_t_func = 0;     /* seconds, INDELGPU_VERBOSE */
+
+#include <time.h>
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
 static int g_stats_registered = 0;
 
 static void print_stats(void)
@@ -96,6 +105,10 @@ static void print_stats(void)
     fprintf(stderr, "libindelgpu: inline mode: %lld BAM records, %lld calls answered from %lld prefetched batches "
                     "(%lld reads realigned in them), %lld computed per read\n",
             g_records, g_hits, g_batches, g_prefetched, g_direct);
+    if (getenv("INDELGPU_VERBOSE"))
+        fprintf(stderr, "libindelgpu: inline mode: prefetch thread %.2f s reading + classifying, %.2f s in indelgpu_realign_batch, %.2f s waiting for "
+                        "fetch_func; main thread %.2f s in fetch_func, %.2f s waiting for the prefetch thread\n",
+                g_t_read, g_t_gpu, g_t_prod_wait, g_t_func, g_t_cons_wait);
 }
 
 static int block_records(int serial)
@@ -195,6 +208,7 @@ static void fill_block(pf_block* k, const producer_arg* pa, int serial)
     indelgpu_ctx* ctx = indelgpu_glue_ctx_peek(pa->tid, &dtid);
     pthread_mutex_unlock(&indelgpu_glue_gpu_mu);
     char read[1024];
+    const double t_r0 = now_s();
     while (k->nrec < want) {
         bam1_t* b = &k->recs[k->nrec];
         const int ret = bam_iter_read(pa->fp, pa->iter, b);
@@ -209,10 +223,13 @@ static void fill_block(pf_block* k, const producer_arg* pa, int serial)
         }
         k->cand[k->nrec++] = slot;
     }
+    const double t_r1 = now_s();
+    g_t_read += t_r1 - t_r0;
     if (k->batch->n > 0) {
         pthread_mutex_lock(&indelgpu_glue_gpu_mu);
         const int rc = igb_run(k->batch, ctx);
         pthread_mutex_unlock(&indelgpu_glue_gpu_mu);
+        g_t_gpu += now_s() - t_r1;
         /* a batch that fails (e.g. it holds a read on which the reference itself would abort, status 7) is
          * dropped: its reads go through the per-read path, which reports the error for the call that is
          * actually made -- a foreseen call that never happens must not stop the run */
@@ -226,6 +243,7 @@ static void* producer_main(void* arg)
     const producer_arg* pa = arg;
     for (int serial = 0;; serial++) {
         pf_block* k = &g_blk[serial & 1];
+        const double t_w0 = now_s();
         pthread_mutex_lock(&g_mu);
         while (k->full) pthread_cond_wait(&g_cv, &g_mu);
         /* Until a call has taught this file the contig's context and a read group's range nothing can be
@@ -244,6 +262,7 @@ static void* producer_main(void* arg)
             if (g_consumed < serial) pthread_cond_wait(&g_cv, &g_mu);
         }
         pthread_mutex_unlock(&g_mu);
+        g_t_prod_wait += now_s() - t_w0;
         fill_block(k, pa, serial);
         const int last = k->last;
         pthread_mutex_lock(&g_mu);
@@ -276,15 +295,19 @@ int indelgpu_bam_fetch(bamFile fp, const bam_index_t* idx, int tid, int beg, int
     int ret = 0;
     for (int serial = 0;; serial++) {
         pf_block* k = &g_blk[serial & 1];
+        const double t_c0 = now_s();
         pthread_mutex_lock(&g_mu);
         while (!k->full) pthread_cond_wait(&g_cv, &g_mu);
         pthread_mutex_unlock(&g_mu);
+        const double t_c1 = now_s();
+        g_t_cons_wait += t_c1 - t_c0;
         g_cur_blk = k;
         for (int i = 0; i < k->nrec; i++) {
             g_cur_idx = i;
             func(&k->recs[i], data);                                        /* bam_index.c:722 */
         }
         g_records += k->nrec;
+        g_t_func += now_s() - t_c1;
         g_cur_blk = NULL; g_cur_idx = -1;
         const int last = k->last;
         ret = k->ret;

@@ -148,6 +148,23 @@ int64_t indelgpu_seg_bound(int32_t n, int64_t total_read_bases);
  * host threads, one thread per context at a time. */
 int indelgpu_realign_batch(indelgpu_ctx* ctx, const indelgpu_batch* h_in, indelgpu_result* h_out);
 
+/* The same with the reads as the BAM holds them (bam1_seq: 4 bits per base, high nibble first, every read starting
+ * on a byte): the host copies the record's bytes instead of expanding them with bit2char (readaln.c:4-17) and
+ * reversing them (indelminer.c:404-409, 479-484) -- both happen on the device -- and the batch is 0.6 bytes per
+ * base on the wire instead of 1.  Codes other than 1, 2, 4, 8, 15 (A C G T N) are inputs the reference stops on:
+ * the call returns INDELGPU_ELIMIT.  Debug outputs (detail, cigar1, cigar2) are not available here. */
+typedef struct indelgpu_batch4 {
+    int32_t        n;
+    const uint8_t* seq4;          /* concatenated 4-bit reads                               */
+    const int64_t* byte_off;      /* n + 1 byte offsets into seq4; read i fills (len[i] + 1) / 2 bytes */
+    const int32_t* len;           /* n   read lengths in bases (core.l_qseq)                */
+    const uint8_t* flags;         /* n   bit 0: reverse-complement the read before aligning */
+    const int32_t* tid;
+    const int32_t* position;
+    const int32_t* range1;
+} indelgpu_batch4;
+int indelgpu_realign_batch4(indelgpu_ctx* ctx, const indelgpu_batch4* h_in, indelgpu_result* h_out);
+
 /* Device buffers in and out (all pointers in *d_in / *d_out are device pointers, the structs
  * themselves live on the host).  d_in->read_bases must be 16-byte aligned and readable up to the next
  * 16-byte boundary past its last base (the kernels stage reads with TMA bulk copies; any cudaMalloc'ed

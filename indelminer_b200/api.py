@@ -44,6 +44,46 @@ def pack_sequences(seqs):
     return np.ascontiguousarray(data), off
 
 
+_NT16 = np.zeros(256, dtype=np.uint8)            # bam_nt16_table restricted to what bit2char accepts (readaln.c:4-17)
+for _ch, _code in ((b"A", 1), (b"C", 2), (b"G", 4), (b"T", 8), (b"N", 15)):
+    _NT16[_ch[0]] = _code
+_COMP = np.arange(256, dtype=np.uint8)
+for _a, _b in ((b"A", b"T"), (b"C", b"G"), (b"G", b"C"), (b"T", b"A")):
+    _COMP[_a[0]] = _b[0]
+
+
+def pack4(read_bases, read_off, revcomp=None):
+    """ASCII reads -> the BAM's 4-bit form (seq4, byte_off, len, flags) for attempt_pe_alignment_batch4.  With
+    `revcomp` (bool per read) a read is stored as the BAM would hold its reverse complement and flagged, so that the
+    device undoes it: the alignment input is the same ASCII read either way.  Equal-length reads are vectorised."""
+    n = len(read_off) - 1
+    lens = (read_off[1:] - read_off[:-1]).astype(np.int32)
+    nb = (lens.astype(np.int64) + 1) // 2
+    byte_off = np.zeros(n + 1, dtype=np.int64)
+    byte_off[1:] = np.cumsum(nb)
+    flags = np.zeros(n, dtype=np.uint8) if revcomp is None else np.ascontiguousarray(revcomp, dtype=np.uint8)
+    seq4 = np.zeros(int(byte_off[-1]), dtype=np.uint8)
+    if n and (lens == lens[0]).all() and int(read_off[0]) == 0:
+        M = int(lens[0])
+        mat = read_bases[:n * M].reshape(n, M)
+        if revcomp is not None:
+            mat = np.where(flags[:, None].astype(bool), _COMP[mat[:, ::-1]], mat)
+        codes = _NT16[mat]
+        if M % 2:
+            codes = np.concatenate([codes, np.zeros((n, 1), dtype=np.uint8)], axis=1)
+        seq4[:] = ((codes[:, 0::2] << 4) | codes[:, 1::2]).reshape(-1)
+    else:
+        for i in range(n):
+            r = read_bases[read_off[i]:read_off[i + 1]]
+            if flags[i]:
+                r = _COMP[r[::-1]]
+            codes = _NT16[r]
+            if len(codes) % 2:
+                codes = np.concatenate([codes, np.zeros(1, dtype=np.uint8)])
+            seq4[byte_off[i]:byte_off[i + 1]] = (codes[0::2] << 4) | codes[1::2]
+    return seq4, byte_off, lens, flags
+
+
 def walk_segments(rstart, words):
     """new_readseg's coordinate bookkeeping (readaln.c:24-99): words -> [(op, len, start, end)]."""
     out = []
@@ -157,6 +197,29 @@ class Realigner:
                         res.cigar1.ctypes.data if stride else None,
                         res.cigar2.ctypes.data if stride else None, stride)
         _check(self._L.indelgpu_realign_batch(self._ctx, C.byref(b), C.byref(r)))
+        res.seg_count = int(r.seg_count)
+        res.launches = self._L.indelgpu_last_launch_count(self._ctx)
+        res.cells, res.alg_bytes = self.last_counters()
+        return res
+
+    def attempt_pe_alignment_batch4(self, seq4, byte_off, length, flags, tid, position, range1):
+        """The same batch with the reads as the BAM holds them (indelgpu_realign_batch4): 4 bits per base, high
+        nibble first, every read on a byte boundary; flags bit 0 = reverse-complement on the device."""
+        n = len(byte_off) - 1
+        seq4 = np.ascontiguousarray(seq4, dtype=np.uint8)
+        byte_off = np.ascontiguousarray(byte_off, dtype=np.int64)
+        length = np.ascontiguousarray(length, dtype=np.int32)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        tid = np.ascontiguousarray(tid, dtype=np.int32)
+        position = np.ascontiguousarray(position, dtype=np.int32)
+        range1 = np.ascontiguousarray(range1, dtype=np.int32)
+        cap = int(self._L.indelgpu_seg_bound(n, 2 * int(byte_off[-1])))
+        res = BatchResult(n, cap, False, 0)
+        b = _lib.Batch4(n, seq4.ctypes.data, byte_off.ctypes.data, length.ctypes.data, flags.ctypes.data,
+                        tid.ctypes.data, position.ctypes.data, range1.ctypes.data)
+        r = _lib.Result(res.status.ctypes.data, res.nseg.ctypes.data, res.rstart.ctypes.data,
+                        res.seg_off.ctypes.data, res.segs.ctypes.data, cap, 0, None, None, None, 0)
+        _check(self._L.indelgpu_realign_batch4(self._ctx, C.byref(b), C.byref(r)))
         res.seg_count = int(r.seg_count)
         res.launches = self._L.indelgpu_last_launch_count(self._ctx)
         res.cells, res.alg_bytes = self.last_counters()

@@ -101,6 +101,7 @@ struct indelgpu_ctx {
     int64_t ref_bases = 0;
     // batch staging
     DevBuf in_reads, in_off, in_tid, in_pos, in_rng;
+    DevBuf in_seq4, in_boff, in_len, in_flags;        // 4-bit packed batches (indelgpu_realign_batch4), unpacked on the device
     DevBuf out_status, out_nseg, out_rstart, out_segoff, out_segs, out_detail, out_cig1, out_cig2;
     DevBuf chunk_counts;     // chunked host path: segment count after each chunk's kernel, snapshot in stream order
     DevBuf counters;         // bytes: 0 work counter (int) | 8 seg count (u64) | 16 cells (3 x u64) | 40 error flag (int) | 48 algorithmic bytes (u64) | 56 ALIGN cells not swept (u64, band tasks)
@@ -181,7 +182,7 @@ extern "C" void indelgpu_destroy(indelgpu_ctx* c)
     for (cudaEvent_t e : c->ev_out) cudaEventDestroy(e);
     if (c->pinned_counts) cudaFreeHost(c->pinned_counts);
     if (c->h_order) cudaFreeHost(c->h_order);
-    DevBuf* all[] = {&c->ref_raw, &c->ref_packed, &c->ref_off, &c->ref_len, &c->idx_off, &c->idx_pos, &c->in_reads, &c->in_off, &c->in_tid,
+    DevBuf* all[] = {&c->ref_raw, &c->ref_packed, &c->ref_off, &c->ref_len, &c->idx_off, &c->idx_pos, &c->in_reads, &c->in_off, &c->in_tid, &c->in_seq4, &c->in_boff, &c->in_len, &c->in_flags,
                      &c->in_pos, &c->in_rng, &c->out_status, &c->out_nseg, &c->out_rstart, &c->out_segoff,
                      &c->out_segs, &c->out_detail, &c->out_cig1, &c->out_cig2, &c->counters, &c->chunk_counts, &c->scratch,
                      &c->p_low, &c->p_aln, &c->p_cig, &c->p_plan, &c->p_flags,
@@ -329,9 +330,15 @@ static int plan_warps(indelgpu_ctx* c, Kern kern, int bytes_per_warp, int* warps
     return 0;
 }
 
+// a batch in the BAM's 4-bit form, on the device (fused -g 0 kernel only; banded runs unpack it first)
+struct Packed4Dev { const uint8_t* seq4; const int64_t* byte_off; const uint8_t* flags; };
+
 static void fill_realign_args(indelgpu_ctx* c, RealignArgs& a, const indelgpu_batch* d_in, indelgpu_result* d_out,
-                              unsigned long long* d_seg_count, int max_read, int max_numdiag, const WarpLayout& L)
+                              unsigned long long* d_seg_count, int max_read, int max_numdiag, const WarpLayout& L,
+                              const int32_t* d_read_len = nullptr, const Packed4Dev* p4 = nullptr)
 {
+    a.read_len = d_read_len;
+    a.seq4 = p4 ? p4->seq4 : nullptr; a.byte_off = p4 ? p4->byte_off : nullptr; a.rflags = p4 ? p4->flags : nullptr;
     a.P = c->P;
     a.ref.raw = c->ref_raw.as<uint8_t>(); a.ref.packed = c->ref_packed.as<uint32_t>();
     a.ref.contig_off = c->ref_off.as<int64_t>(); a.ref.contig_len = c->ref_len.as<int64_t>(); a.ref.ncontigs = c->ncontigs;
@@ -348,7 +355,8 @@ static void fill_realign_args(indelgpu_ctx* c, RealignArgs& a, const indelgpu_ba
 
 // -g N > 0: vote / DP / vote / DP / combine (realign_pipeline.cuh)
 static int launch_pipeline(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_read, int max_numdiag, const WarpLayout& L,
-                           indelgpu_result* d_out, unsigned long long* d_seg_count, cudaStream_t st, bool keep_totals)
+                           indelgpu_result* d_out, unsigned long long* d_seg_count, cudaStream_t st, bool keep_totals,
+                           const int32_t* d_read_len)
 {
     const int n = d_in->n;
     const int max_band = c->P.g + 1;
@@ -360,7 +368,7 @@ static int launch_pipeline(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_
     p.plan = c->p_plan.as<Plan>(); p.flags = c->p_flags.as<int32_t>();
 
     RealignArgs a;
-    fill_realign_args(c, a, d_in, d_out, d_seg_count, max_read, max_numdiag, L);
+    fill_realign_args(c, a, d_in, d_out, d_seg_count, max_read, max_numdiag, L, d_read_len);
 
     void (*vk)(RealignArgs, PipeBufs, int);
     if (L.hist_bits == 8) vk = L.direct ? pipe_vote_kernel<true, 8> : pipe_vote_kernel<false, 8>;
@@ -411,7 +419,7 @@ static int launch_pipeline(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_
 // counter, the cell totals and the error flag keep accumulating
 static int launch_realign(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_read, int max_range1,
                           indelgpu_result* d_out, unsigned long long* d_seg_count, cudaStream_t st,
-                          bool keep_totals = false)
+                          bool keep_totals = false, const int32_t* d_read_len = nullptr, const Packed4Dev* p4 = nullptr)
 {
     if (c->ncontigs <= 0) return fail(INDELGPU_EINVAL, "realign: no reference uploaded (indelgpu_set_reference)");
     if (max_read <= 0 || max_read > 65000) return fail(INDELGPU_ELIMIT, "read length %d outside 1..65000", max_read);
@@ -421,12 +429,16 @@ static int launch_realign(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_r
     const bool banded = c->P.g > 0;
     // the banded pipeline only votes with this layout (its CIGARs live in HBM), so it takes the compact form too
     const long long vd = std::max(2LL * max_range1, (long long)max_range1 + c->P.maxdel) + max_read + 2;
+    if (p4 && (c->P.k > 6 || c->idx_blocks > 0)) return fail(INDELGPU_EINVAL, "internal: only the direct-table window-scan kernel expands 4-bit reads");
     const bool indexed = !banded && c->idx_blocks > 0;            // -g 0, k <= 6: the fused kernel votes through the resident index
-    const WarpLayout L = make_warp_layout(c->P, max_read, max_numdiag, (int)vd, 0, indexed ? 1 : 0);
+    if (p4 && banded) return fail(INDELGPU_EINVAL, "internal: 4-bit batches reach the banded pipeline unpacked");
+    const WarpLayout L = make_warp_layout(c->P, max_read, max_numdiag, (int)vd, 0, indexed ? 1 : 0, p4 ? 1 : 0);
+    if (p4 && ((uintptr_t)p4->seq4 & 15) != 0) return fail(INDELGPU_EINVAL, "seq4 must be 16-byte aligned on the device (TMA bulk copies)");
     if (((uintptr_t)d_in->read_bases & 15) != 0) return fail(INDELGPU_EINVAL, "read_bases must be 16-byte aligned on the device (TMA bulk copies)");
-    if (banded) return launch_pipeline(c, d_in, max_read, max_numdiag, L, d_out, d_seg_count, st, keep_totals);
+    if (banded) return launch_pipeline(c, d_in, max_read, max_numdiag, L, d_out, d_seg_count, st, keep_totals, d_read_len);
     void (*kern)(RealignArgs);
-    if (L.indexed)        kern = L.hist_bits == 8 ? realign_kernel<true, 8, true> : realign_kernel<true, 16, true>;
+    if (p4)               kern = L.hist_bits == 8 ? realign_kernel<true, 8, false, true> : realign_kernel<true, 16, false, true>;
+    else if (L.indexed)   kern = L.hist_bits == 8 ? realign_kernel<true, 8, true> : realign_kernel<true, 16, true>;
     else if (L.hist_bits == 8) kern = L.direct ? realign_kernel<true, 8, false> : realign_kernel<false, 8, false>;
     else                  kern = L.direct ? realign_kernel<true, 16, false> : realign_kernel<false, 16, false>;
     int wpc = 0, occ = 0;
@@ -434,7 +446,7 @@ static int launch_realign(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_r
     const int blocks = (int)std::min<long long>((long long)c->sms * occ, std::max(1, (d_in->n + wpc - 1) / wpc));
 
     RealignArgs a;
-    fill_realign_args(c, a, d_in, d_out, d_seg_count, max_read, max_numdiag, L);
+    fill_realign_args(c, a, d_in, d_out, d_seg_count, max_read, max_numdiag, L, d_read_len, p4);
 
     if (keep_totals) CU(cudaMemsetAsync(c->counters.p, 0, 4, st));
     else {
@@ -547,25 +559,91 @@ extern "C" int indelgpu_last_error_flag(indelgpu_ctx* c)
     return err;
 }
 
-extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, indelgpu_result* o)
+// BAM 4-bit bases -> ASCII on the device (bit2char, readaln.c:4-17: 1 A, 2 C, 4 G, 8 T, 15 N; anything else is an
+// input the reference stops on: error flag 1), reverse-complemented when the read's flag asks for it
+// (reverse_complement_string, sequences.c:204-220, on A C G T N).  One warp per read; read i lands at 2 * byte_off[i].
+__global__ void unpack_reads4_kernel(int n, const uint8_t* __restrict__ seq4, const int64_t* __restrict__ byte_off,
+                                     const int32_t* __restrict__ len, const uint8_t* __restrict__ flags,
+                                     uint8_t* __restrict__ out, int64_t* __restrict__ out_off, int* error_flag)
 {
-    if (!c || !h || !o) return fail(INDELGPU_EINVAL, "realign_batch: NULL argument");
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    #pragma unroll 1
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
+        const int64_t b0 = byte_off[i];
+        const int L = len[i];
+        const bool rc = (flags[i] & 1u) != 0u;
+        uint8_t* dst = out + 2 * b0;
+        if (lane == 0) { out_off[i] = 2 * b0; if (i == n - 1) out_off[n] = 2 * byte_off[n]; }
+        #pragma unroll 1
+        for (int j = lane; 2 * j < L; j += 32) {
+            const uint32_t byte = seq4[b0 + j];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int t = 2 * j + h;
+                if (t >= L) break;
+                const uint32_t code = h == 0 ? (byte >> 4) : (byte & 15u);      // bam1_seqi: high nibble first
+                uint8_t fwd, rev;
+                switch (code) {
+                    case 1: fwd = 'A'; rev = 'T'; break;
+                    case 2: fwd = 'C'; rev = 'G'; break;
+                    case 4: fwd = 'G'; rev = 'C'; break;
+                    case 8: fwd = 'T'; rev = 'A'; break;
+                    case 15: fwd = 'N'; rev = 'N'; break;
+                    default: fwd = 'N'; rev = 'N'; atomicExch(error_flag, 1); break;
+                }
+                if (rc) dst[L - 1 - t] = rev; else dst[t] = fwd;
+            }
+        }
+    }
+}
+
+// host view of a batch in either input form
+struct HostBatch {
+    int n;
+    const uint8_t* bases; const int64_t* off;                    // ASCII: read i = bases[off[i] .. off[i+1])
+    const int32_t* len; const uint8_t* flags; bool packed4;      // 4-bit: bases = BAM nibbles, off = byte offsets
+    const int32_t* tid; const int32_t* position; const int32_t* range1;
+};
+
+static int realign_batch_impl(indelgpu_ctx* c, const HostBatch* h, indelgpu_result* o);
+
+extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* b, indelgpu_result* o)
+{
+    if (!c || !b || !o) return fail(INDELGPU_EINVAL, "realign_batch: NULL argument");
+    if (b->n > 0 && (!b->read_bases || !b->read_off || !b->tid || !b->position || !b->range1)) return fail(INDELGPU_EINVAL, "realign_batch: NULL buffer");
+    const HostBatch h = {b->n, b->read_bases, b->read_off, nullptr, nullptr, false, b->tid, b->position, b->range1};
+    return realign_batch_impl(c, &h, o);
+}
+
+extern "C" int indelgpu_realign_batch4(indelgpu_ctx* c, const indelgpu_batch4* b, indelgpu_result* o)
+{
+    if (!c || !b || !o) return fail(INDELGPU_EINVAL, "realign_batch4: NULL argument");
+    if (b->n > 0 && (!b->seq4 || !b->byte_off || !b->len || !b->flags || !b->tid || !b->position || !b->range1)) return fail(INDELGPU_EINVAL, "realign_batch4: NULL buffer");
+    if (o->detail || o->cigar1 || o->cigar2) return fail(INDELGPU_EINVAL, "realign_batch4: debug outputs are only available through indelgpu_realign_batch");
+    const HostBatch h = {b->n, b->seq4, b->byte_off, b->len, b->flags, true, b->tid, b->position, b->range1};
+    return realign_batch_impl(c, &h, o);
+}
+
+static int realign_batch_impl(indelgpu_ctx* c, const HostBatch* h, indelgpu_result* o)
+{
     const int n = h->n;
     if (n < 0) return fail(INDELGPU_EINVAL, "negative batch size");
     o->seg_count = 0;
     c->launches = 0;
     if (n == 0) return 0;
-    if (!h->read_bases || !h->read_off || !h->tid || !h->position || !h->range1 ||
-        !o->status || !o->nseg || !o->rstart || !o->seg_off || !o->segs)
+    if (!o->status || !o->nseg || !o->rstart || !o->seg_off || !o->segs)
         return fail(INDELGPU_EINVAL, "realign_batch: NULL buffer");
+    const bool p4 = h->packed4;
     CU(cudaSetDevice(c->device));
     // sizes are validated (and the kernel limits derived) chunk by chunk, right before a chunk is enqueued,
     // so that the first copies do not wait for a pass over the whole batch
     auto scan_range = [&](int lo, int hi, int* mr, int* mg) -> int {
         int max_read = 0, max_range = 0;
         for (int i = lo; i < hi; i++) {
-            const int64_t len = h->read_off[i + 1] - h->read_off[i];
+            const int64_t len = p4 ? (int64_t)h->len[i] : h->off[i + 1] - h->off[i];
             if (len <= 0 || len > 65000) return fail(INDELGPU_ELIMIT, "read %d has length %lld (must be 1..65000)", i, (long long)len);
+            if (p4 && h->off[i + 1] - h->off[i] != (len + 1) / 2) return fail(INDELGPU_EINVAL, "read %d: %lld bases do not fill %lld bytes", i, (long long)len, (long long)(h->off[i + 1] - h->off[i]));
             max_read = std::max(max_read, (int)len);
             if (h->range1[i] < 0) return fail(INDELGPU_EINVAL, "read %d: negative range", i);
             max_range = std::max(max_range, h->range1[i]);
@@ -573,8 +651,10 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
         *mr = max_read; *mg = max_range;
         return 0;
     };
-    const int64_t nbases = h->read_off[n] - h->read_off[0];
-    if (h->read_off[0] != 0) return fail(INDELGPU_EINVAL, "read_off[0] must be 0");
+    // device ASCII bytes: a 4-bit read of L bases occupies 2 * ceil(L / 2) of them
+    const int64_t nbytes_in = h->off[n] - h->off[0];
+    const int64_t nbases = p4 ? 2 * nbytes_in : nbytes_in;
+    if (h->off[0] != 0) return fail(INDELGPU_EINVAL, "the first read offset must be 0");
     const int64_t segcap = std::min<int64_t>(o->seg_capacity, indelgpu_seg_bound(n, nbases));
     cudaStream_t st = c->stream;
     if (c->in_reads.ensure((size_t)nbases + 16) || c->in_off.ensure(8 * (size_t)(n + 1)) || c->in_tid.ensure(4 * (size_t)n) ||
@@ -582,12 +662,15 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
         c->out_nseg.ensure(4 * (size_t)n) || c->out_rstart.ensure(4 * (size_t)n) || c->out_segoff.ensure(8 * (size_t)n) ||
         c->out_segs.ensure(4 * (size_t)std::max<int64_t>(segcap, 1)))
         return INDELGPU_ENOMEM;
+    if (p4 && (c->in_seq4.ensure((size_t)nbytes_in + 16) || c->in_boff.ensure(8 * (size_t)(n + 1)) || c->in_len.ensure(4 * (size_t)n) ||
+               c->in_flags.ensure((size_t)n + 16))) return INDELGPU_ENOMEM;
     if (o->detail && c->out_detail.ensure(sizeof(indelgpu_detail) * (size_t)n)) return INDELGPU_ENOMEM;
     const size_t cigbytes = 4 * (size_t)n * (size_t)std::max(o->cigar_stride, 0);
     if (o->cigar1 && c->out_cig1.ensure(cigbytes + 4)) return INDELGPU_ENOMEM;
     if (o->cigar2 && c->out_cig2.ensure(cigbytes + 4)) return INDELGPU_ENOMEM;
 
-    indelgpu_batch din = *h;
+    indelgpu_batch din;
+    din.n = n;
     din.read_bases = c->in_reads.as<uint8_t>(); din.read_off = c->in_off.as<int64_t>();
     din.tid = c->in_tid.as<int32_t>(); din.position = c->in_pos.as<int32_t>(); din.range1 = c->in_rng.as<int32_t>();
     indelgpu_result dout = *o;
@@ -596,6 +679,40 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
     dout.detail = o->detail ? c->out_detail.as<indelgpu_detail>() : nullptr;
     dout.cigar1 = o->cigar1 ? c->out_cig1.as<uint32_t>() : nullptr;
     dout.cigar2 = o->cigar2 ? c->out_cig2.as<uint32_t>() : nullptr;
+
+    // host -> device copies of reads [c0, c1) on stream `si`; 4-bit batches are unpacked on `sk` once `ev` says they landed
+    auto enqueue_inputs = [&](int c0, int c1, cudaStream_t si) -> int {
+        const int m = c1 - c0;
+        const int64_t b0 = h->off[c0], b1 = h->off[c1];
+        if (!p4) {
+            CU(cudaMemcpyAsync(c->in_off.as<int64_t>() + c0, h->off + c0, 8 * (size_t)(m + 1), cudaMemcpyHostToDevice, si));
+            CU(cudaMemcpyAsync(c->in_reads.as<uint8_t>() + b0, h->bases + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, si));
+        } else {
+            CU(cudaMemcpyAsync(c->in_boff.as<int64_t>() + c0, h->off + c0, 8 * (size_t)(m + 1), cudaMemcpyHostToDevice, si));
+            CU(cudaMemcpyAsync(c->in_seq4.as<uint8_t>() + b0, h->bases + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, si));
+            CU(cudaMemcpyAsync(c->in_len.as<int32_t>() + c0, h->len + c0, 4 * (size_t)m, cudaMemcpyHostToDevice, si));
+            CU(cudaMemcpyAsync(c->in_flags.as<uint8_t>() + c0, h->flags + c0, (size_t)m, cudaMemcpyHostToDevice, si));
+        }
+        CU(cudaMemcpyAsync(c->in_tid.as<int32_t>() + c0, h->tid + c0, 4 * (size_t)m, cudaMemcpyHostToDevice, si));
+        CU(cudaMemcpyAsync(c->in_pos.as<int32_t>() + c0, h->position + c0, 4 * (size_t)m, cudaMemcpyHostToDevice, si));
+        CU(cudaMemcpyAsync(c->in_rng.as<int32_t>() + c0, h->range1 + c0, 4 * (size_t)m, cudaMemcpyHostToDevice, si));
+        return 0;
+    };
+    // -g 0: the fused kernel expands the 4-bit reads itself; the banded pipeline reads ASCII, so the batch is unpacked first
+    const bool fused4 = p4 && c->P.g == 0 && c->P.k <= 6 && c->idx_blocks == 0;
+    auto enqueue_unpack = [&](int c0, int c1, cudaStream_t sk) -> int {
+        if (!p4 || fused4) return 0;
+        const int m = c1 - c0;
+        const int blocks = (int)std::min<long long>((long long)c->sms * 8, (m + 7) / 8);
+        unpack_reads4_kernel<<<blocks, 256, 0, sk>>>(m, c->in_seq4.as<uint8_t>(), c->in_boff.as<int64_t>() + c0, c->in_len.as<int32_t>() + c0,
+                                                      c->in_flags.as<uint8_t>() + c0, c->in_reads.as<uint8_t>(), c->in_off.as<int64_t>() + c0,
+                                                      ctr_err(c));
+        c->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    };
+    const int32_t* d_len = p4 ? c->in_len.as<int32_t>() : nullptr;
+    Packed4Dev dev4 = {c->in_seq4.as<uint8_t>(), c->in_boff.as<int64_t>(), c->in_flags.as<uint8_t>()};
 
     // Large batches without debug outputs are cut into chunks so that the H2D copy of chunk i+1 and
     // the D2H copy of chunk i-1 overlap the kernel of chunk i (three streams, two events per chunk).
@@ -637,19 +754,18 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
             const int c0 = cuts[ch], c1 = cuts[ch + 1], m = c1 - c0;
             int max_read = 0, max_range = 0;
             if (int rcs = scan_range(c0, c1, &max_read, &max_range)) { cudaDeviceSynchronize(); return rcs; }
-            const int64_t b0 = h->read_off[c0], b1 = h->read_off[c1];
-            CU(cudaMemcpyAsync(c->in_off.as<int64_t>() + c0, h->read_off + c0, 8 * (size_t)(m + 1), cudaMemcpyHostToDevice, c->st_in));
-            CU(cudaMemcpyAsync(c->in_reads.as<uint8_t>() + b0, h->read_bases + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->st_in));
-            CU(cudaMemcpyAsync(c->in_tid.as<int32_t>() + c0, h->tid + c0, 4 * (size_t)m, cudaMemcpyHostToDevice, c->st_in));
-            CU(cudaMemcpyAsync(c->in_pos.as<int32_t>() + c0, h->position + c0, 4 * (size_t)m, cudaMemcpyHostToDevice, c->st_in));
-            CU(cudaMemcpyAsync(c->in_rng.as<int32_t>() + c0, h->range1 + c0, 4 * (size_t)m, cudaMemcpyHostToDevice, c->st_in));
+            if (int rci = enqueue_inputs(c0, c1, c->st_in)) { cudaDeviceSynchronize(); return rci; }
             CU(cudaEventRecord(c->ev_in[ch], c->st_in));
             CU(cudaStreamWaitEvent(st, c->ev_in[ch], 0));
+            // (the unpack kernel's error flag write must not be wiped by the first chunk's counter reset: reset first)
+            if (ch == 0) CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
+            if (int rcu = enqueue_unpack(c0, c1, st)) { cudaDeviceSynchronize(); return rcu; }
             indelgpu_batch dc = din; dc.n = m;
             dc.read_off = din.read_off + c0; dc.tid = din.tid + c0; dc.position = din.position + c0; dc.range1 = din.range1 + c0;
             indelgpu_result rc2 = dout;
             rc2.status = dout.status + c0; rc2.nseg = dout.nseg + c0; rc2.rstart = dout.rstart + c0; rc2.seg_off = dout.seg_off + c0;
-            int rcl = launch_realign(c, &dc, max_read, max_range, &rc2, ctr_segs(c), st, ch > 0);
+            Packed4Dev dc4 = {dev4.seq4, dev4.byte_off + c0, dev4.flags + c0};
+            int rcl = launch_realign(c, &dc, max_read, max_range, &rc2, ctr_segs(c), st, true, d_len ? d_len + c0 : nullptr, fused4 ? &dc4 : nullptr);
             if (rcl) { cudaDeviceSynchronize(); return rcl; }
             // The segment allocator keeps counting while chunk ch+1 runs, and the words of a read are written
             // one read later than they are allocated (realign_kernel's pend_* flush).  The count that bounds
@@ -680,14 +796,12 @@ extern "C" int indelgpu_realign_batch(indelgpu_ctx* c, const indelgpu_batch* h, 
     } else {
         int max_read = 0, max_range = 0;
         if (int rcs = scan_range(0, n, &max_read, &max_range)) return rcs;
-        CU(cudaMemcpyAsync(c->in_reads.p, h->read_bases, (size_t)nbases, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(c->in_off.p, h->read_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(c->in_tid.p, h->tid, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(c->in_pos.p, h->position, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(c->in_rng.p, h->range1, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        if (int rci = enqueue_inputs(0, n, st)) return rci;
+        CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
+        if (int rcu = enqueue_unpack(0, n, st)) return rcu;
         if (o->cigar1) CU(cudaMemsetAsync(c->out_cig1.p, 0, cigbytes, st));
         if (o->cigar2) CU(cudaMemsetAsync(c->out_cig2.p, 0, cigbytes, st));
-        int rc = launch_realign(c, &din, max_read, max_range, &dout, ctr_segs(c), st);
+        int rc = launch_realign(c, &din, max_read, max_range, &dout, ctr_segs(c), st, true, d_len, fused4 ? &dev4 : nullptr);
         if (rc) return rc;
         CU(cudaMemcpyAsync(o->status, dout.status, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(o->nseg, dout.nseg, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));

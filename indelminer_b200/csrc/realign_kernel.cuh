@@ -25,6 +25,8 @@ struct RealignArgs {
     KmerIndex idx;                     // resident k-mer index of the reference (used when L.indexed)
     int n;
     const uint8_t* reads; const int64_t* read_off;
+    const int32_t* read_len;           // optional: lengths when the reads are not back to back (4-bit batches)
+    const uint8_t* seq4; const int64_t* byte_off; const uint8_t* rflags;    // optional: the batch in the BAM's 4-bit form (fused kernel)
     const int32_t* tid; const int32_t* position; const int32_t* range1;
     int32_t* status; int32_t* nseg; int32_t* rstart; int64_t* seg_off;
     uint32_t* segs; int64_t seg_capacity; unsigned long long* seg_count;
@@ -189,14 +191,16 @@ struct ReadCtx {
     int64_t roff; int readlen;
     int64_t cbase;
     int32_t position, left1, right1, left2, right2;
-    bool bad;
+    bool bad, rc;
 };
 
+template <bool PACKED = false>
 __device__ __forceinline__ ReadCtx load_read_ctx(const RealignArgs& a, int idx)
 {
     ReadCtx c;
-    c.roff = a.read_off[idx];
-    c.readlen = (int)(a.read_off[idx + 1] - c.roff);
+    c.rc = false;
+    if (PACKED) { c.roff = a.byte_off[idx]; c.readlen = a.read_len[idx]; c.rc = (a.rflags[idx] & 1u) != 0u; }
+    else { c.roff = a.read_off[idx]; c.readlen = a.read_len ? a.read_len[idx] : (int)(a.read_off[idx + 1] - c.roff); }
     const int32_t ctg = a.tid[idx];
     c.position = a.position[idx];
     const int32_t range1 = a.range1[idx];
@@ -222,21 +226,24 @@ __device__ __forceinline__ ReadCtx load_read_ctx(const RealignArgs& a, int idx)
 }
 
 // lane 0: register the expected bytes and issue the two bulk copies of one batch entry
+template <bool PACKED = false>
 __device__ __forceinline__ void stage_read(const RealignArgs& a, WarpView& V, const ReadCtx& c, int buf)
 {
     uint64_t* bar = V.bar + buf;
     if (c.bad) { mbar_arrive(bar); return; }
     const int64_t r0 = c.roff & ~(int64_t)15;
-    const uint32_t rbytes = (uint32_t)(((c.roff + c.readlen - r0) + 15) / 16 * 16);
+    const uint8_t* rsrc = PACKED ? a.seq4 : a.reads;
+    const int nstage = PACKED ? (c.readlen + 1) / 2 : c.readlen;
+    const uint32_t rbytes = (uint32_t)(((c.roff + nstage - r0) + 15) / 16 * 16);
     int64_t sw0;
     const uint32_t wbytes = window_span_bytes(c.cbase + c.left2, c.cbase + c.right2, &sw0);
     if (a.L.indexed) {                                           // the vote reads the resident index: only the read is staged
         mbar_arrive_expect_tx(bar, rbytes);
-        bulk_g2s(read_buf(V, buf), a.reads + r0, rbytes, bar);
+        bulk_g2s(read_buf(V, buf), rsrc + r0, rbytes, bar);
         return;
     }
     mbar_arrive_expect_tx(bar, rbytes + wbytes);
-    bulk_g2s(read_buf(V, buf), a.reads + r0, rbytes, bar);
+    bulk_g2s(read_buf(V, buf), rsrc + r0, rbytes, bar);
     bulk_g2s(win_buf(V, buf), a.ref.packed + sw0, wbytes, bar);
 }
 
@@ -253,7 +260,8 @@ constexpr int kWorkChunk = 2;     // batch entries a warp takes per atomic: larg
 // table entry (8 when a slice has at most 255 k-mers).
 // The two rounds are ONE loop body so that the vote and the alignment exist once in the instruction
 // stream: warps of a CTA are in different phases and the kernel has to stay instruction-cache friendly.
-template <bool DIRECT, int HB, bool INDEXED>
+// PACKED: the batch holds the reads as the BAM does (4 bits per base); they are expanded -- and reversed where flagged -- here.
+template <bool DIRECT, int HB, bool INDEXED, bool PACKED = false>
 __global__ void __launch_bounds__(256, INDEXED ? REALIGN_MIN_BLOCKS_INDEXED : REALIGN_MIN_BLOCKS)
 realign_kernel(const __grid_constant__ RealignArgs a)
 {
@@ -290,8 +298,8 @@ realign_kernel(const __grid_constant__ RealignArgs a)
         ReadCtx cn;
         cn.bad = true;
         if (nxt < a.n) {
-            cn = load_read_ctx(a, nxt);
-            if (lane == 0) stage_read(a, V, cn, (it + 1) & 1);
+            cn = load_read_ctx<PACKED>(a, nxt);
+            if (lane == 0) stage_read<PACKED>(a, V, cn, (it + 1) & 1);
         }
         if (cur >= 0) {
             const int idx = cur, buf = it & 1;
@@ -308,6 +316,10 @@ realign_kernel(const __grid_constant__ RealignArgs a)
                 const int32_t anchor = c.position, left2 = c.left2, right2 = c.right2;
                 const int64_t cbase = c.cbase;
                 S.read = read_buf(V, buf) + (int)(c.roff & 15);
+                if (PACKED) {                                        // the batch holds the read as the BAM does: expand it here
+                    if (!expand_read4_warp(V.ascii, S.read, readlen, c.rc) && lane == 0) atomicExch(a.error_flag, 1);
+                    S.read = V.ascii;
+                }
                 const uint32_t* swin = win_buf(V, buf);
                 const int64_t sw0 = ((cbase + left2) & ~(int64_t)63) >> 4;
                 pack_read_warp(V, S.read, readlen);

@@ -21,10 +21,11 @@ struct WarpLayout {
     int hist_cap;        // diagonals the histogram can hold
     int win_bytes;       // bytes of one staged packed window (multiple of 16)
     int read_bytes;      // bytes of one staged read (multiple of 16, includes 16 bytes of misalignment)
+    int ascii_bytes;     // 4-bit batches: the read expanded to ASCII (0 when the batch is ASCII already)
     int pk_words;        // packed read words
     int ops_cap;         // words per CIGAR buffer
     int off_tab, off_hist, off_win0, off_win1, off_read0, off_read1, off_pk, off_psum, off_bits,
-        off_cig1, off_cig2, off_segs, off_bar, off_misc, off_list;
+        off_cig1, off_cig2, off_segs, off_bar, off_misc, off_list, off_ascii;
     int total;           // bytes per warp (multiple of 128)
 };
 
@@ -44,7 +45,7 @@ __host__ __device__ inline int cigar_cap(const DevParams& P, int max_read, int b
 // the diagonals one vote can address.  The two differ: round 1 votes on window 1 (2 * range1 bases) and
 // every round-2 window lies on one side of the anchor (alignment.c:606-706: at most range1 + maxdelsize).
 __host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int max_read, int max_numdiag, int max_votediag, int banded,
-                                                       int indexed = 0)
+                                                       int indexed = 0, int packed4 = 0)
 {
     WarpLayout L;
     L.indexed = indexed && P.k <= 6;
@@ -60,6 +61,7 @@ __host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int m
     L.hist_words = round_up((max_votediag + 4) * (L.hist_bits / 8), 16) / 4;
     L.win_bytes = L.indexed ? 0 : round_up(max_numdiag / 4 + 64, 16);   // window <= max_numdiag bases, 64-base aligned start, hi word
     L.read_bytes = round_up(max_read + 32, 16);
+    L.ascii_bytes = packed4 ? round_up(max_read + 16, 16) : 0;
     L.pk_words = max_read / 16 + 3;
     L.ops_cap = cigar_cap(P, max_read, banded);
     int o = 0;
@@ -69,6 +71,7 @@ __host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int m
     L.off_win1 = o;  o += L.win_bytes;
     L.off_read0 = o; o += L.read_bytes;
     L.off_read1 = o; o += L.read_bytes;
+    L.off_ascii = o; o += L.ascii_bytes;
     L.off_pk = o;    o += round_up(L.pk_words * 4, 16);
     L.off_cig1 = o;  o += round_up(L.ops_cap * 4, 16);
     L.off_cig2 = o;  o += round_up(L.ops_cap * 4, 16);
@@ -141,6 +144,7 @@ struct WarpView {
     WarpLayout L;
     uint16_t* tab16; uint32_t* keys; uint32_t* vals;
     uint32_t* hist;
+    uint8_t* ascii;                      // 4-bit batches: the current read as ASCII
     uint32_t* win0; uint8_t* rbuf0;      // double buffers: buffer b at win0 + b * win_bytes / rbuf0 + b * read_bytes
     uint32_t* pk;
     uint64_t* bar;        // [2]
@@ -161,6 +165,7 @@ __device__ __forceinline__ void bind_warp(WarpView& V, unsigned char* base, cons
     V.hist = reinterpret_cast<uint32_t*>(base + L.off_hist);
     V.win0 = reinterpret_cast<uint32_t*>(base + L.off_win0);
     V.rbuf0 = base + L.off_read0;
+    V.ascii = base + L.off_ascii;
     V.pk = reinterpret_cast<uint32_t*>(base + L.off_pk);
     V.bar = reinterpret_cast<uint64_t*>(base + L.off_bar);
     V.misc = reinterpret_cast<int*>(base + L.off_misc);
@@ -205,6 +210,35 @@ __device__ __forceinline__ void pack_read_warp(WarpView& V, const uint8_t* read,
     }
     if (lane == 0) { V.pk[2 * chunks] = 0; V.pk[2 * chunks + 1] = 0; }
     __syncwarp();
+}
+
+// BAM 4-bit bases (bam1_seqi: high nibble first) -> ASCII as bit2char does (readaln.c:4-17: 1 A, 2 C, 4 G, 8 T, 15 N),
+// written back to front and complemented when the batch entry asks for the reverse complement
+// (reverse_complement_string, sequences.c:204-220, on A C G T N).  Returns false on a code bit2char stops the program on.
+__device__ __forceinline__ bool expand_read4_warp(uint8_t* out, const uint8_t* nib, int L, bool rc)
+{
+    const int lane = threadIdx.x & 31;
+    // byte c of the table = the base of code c (0 = invalid)
+    const unsigned long long f_lo = 0x0000004700434100ULL, f_hi = 0x4E00000000000054ULL;     // . A C . G . . .   T . . . . . . N
+    const unsigned long long r_lo = 0x0000004300475400ULL, r_hi = 0x4E00000000000041ULL;     // . T G . C . . .   A . . . . . . N
+    bool ok = true;
+    #pragma unroll 1
+    for (int j = lane; 2 * j < L; j += 32) {
+        const uint32_t byte = nib[j];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int t = 2 * j + h;
+            const uint32_t code = h == 0 ? (byte >> 4) : (byte & 15u);
+            const unsigned long long tab = rc ? (code < 8u ? r_lo : r_hi) : (code < 8u ? f_lo : f_hi);
+            uint32_t ch = (uint32_t)(tab >> (8 * (code & 7u))) & 0xFFu;
+            if (t < L) {
+                if (ch == 0u) { ok = false; ch = 'N'; }
+                out[rc ? L - 1 - t : t] = (uint8_t)ch;
+            }
+        }
+    }
+    __syncwarp();
+    return __all_sync(0xFFFFFFFFu, ok);
 }
 
 __device__ __forceinline__ uint32_t kmer_at(const uint32_t* pk, int i, uint32_t kmask)

@@ -14,7 +14,7 @@ EXPORTS = [
     "indelgpu_version", "indelgpu_default_params", "indelgpu_last_error",
     "indelgpu_create", "indelgpu_destroy", "indelgpu_device", "indelgpu_sm_count",
     "indelgpu_host_alloc", "indelgpu_host_free", "indelgpu_set_reference",
-    "indelgpu_seg_bound", "indelgpu_realign_batch", "indelgpu_realign_batch_device",
+    "indelgpu_seg_bound", "indelgpu_realign_batch", "indelgpu_realign_batch4", "indelgpu_realign_batch_device",
     "indelgpu_last_counters", "indelgpu_last_error_flag", "indelgpu_last_shortcut_cells", "indelgpu_last_launch_count", "indelgpu_last_kernel_ms", "indelgpu_int32_peak",
     "indelgpu_find_best_band_batch", "indelgpu_band_align_batch", "indelgpu_indel_support_batch", "indelgpu_device_count",
     "local_align", "ALIGN", "DISPLAY", "fetch_cigar",
@@ -37,6 +37,12 @@ class Detail(C.Structure):
 
 class Batch(C.Structure):
     _fields_ = [("n", C.c_int32), ("read_bases", C.c_void_p), ("read_off", C.c_void_p),
+                ("tid", C.c_void_p), ("position", C.c_void_p), ("range1", C.c_void_p)]
+
+
+class Batch4(C.Structure):
+    """indelgpu_batch4: reads in the BAM's own 4-bit form"""
+    _fields_ = [("n", C.c_int32), ("seq4", C.c_void_p), ("byte_off", C.c_void_p), ("len", C.c_void_p), ("flags", C.c_void_p),
                 ("tid", C.c_void_p), ("position", C.c_void_p), ("range1", C.c_void_p)]
 
 
@@ -73,6 +79,7 @@ def load():
     L.indelgpu_seg_bound.restype = C.c_int64
     L.indelgpu_seg_bound.argtypes = [C.c_int32, C.c_int64]
     L.indelgpu_realign_batch.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Result)]
+    L.indelgpu_realign_batch4.argtypes = [C.c_void_p, C.POINTER(Batch4), C.POINTER(Result)]
     L.indelgpu_realign_batch_device.argtypes = [C.c_void_p, C.POINTER(Batch), C.c_int32, C.c_int32,
                                                 C.POINTER(Result), C.c_void_p, C.c_void_p]
     L.indelgpu_last_counters.argtypes = [C.c_void_p, C.c_void_p]

@@ -471,3 +471,99 @@ def test_chunked_host_path_with_pinned_buffers(gpu, monkeypatch):
     for v, p in list(bufs.values()) + list(outs.values()):
         L.indelgpu_host_free(p)
     R.close()
+
+
+def test_packed_4bit_batches_equal_ascii_batches(gpu, monkeypatch):
+    """indelgpu_realign_batch4: reads in the BAM's own 4-bit form (0.6 bytes per base on the wire), unpacked -- and,
+    where flagged, reverse-complemented -- on the device.  Same answers as the ASCII batch, word for word: equal-length
+    reads, ragged reads with odd lengths, N bases, flagged reads, one launch and the chunked host path."""
+    from indelminer_b200 import api, synth
+    ref = synth.make_reference(500_000, seed=41, n_frac=0.002)
+    w = synth.make_candidates(ref, 9000, seed=42)
+    R = gpu.Realigner()
+    R.set_reference([ref.tobytes()])
+    a = R.attempt_pe_alignment_batch(None, w["tid"], w["position"], w["range1"], packed=(w["read_bases"], w["read_off"]))
+    rng = np.random.default_rng(43)
+    rc = rng.random(9000) < 0.5
+    for flags in (None, rc):
+        seq4, boff, lens, fl = api.pack4(w["read_bases"], w["read_off"], flags)
+        assert len(seq4) == 9000 * 75
+        b = R.attempt_pe_alignment_batch4(seq4, boff, lens, fl, w["tid"], w["position"], w["range1"])
+        assert np.array_equal(a.status, b.status) and np.array_equal(a.nseg, b.nseg) and np.array_equal(a.rstart, b.rstart)
+        assert a.seg_count == b.seg_count and a.cells == b.cells
+        for i in range(9000):
+            assert list(a.words(i)) == list(b.words(i)), i
+    monkeypatch.setenv("INDELGPU_CHUNK_READS", "1000")
+    seq4, boff, lens, fl = api.pack4(w["read_bases"], w["read_off"], rc)
+    b = R.attempt_pe_alignment_batch4(seq4, boff, lens, fl, w["tid"], w["position"], w["range1"])
+    assert b.launches > 10 and np.array_equal(a.status, b.status)
+    for i in range(9000):
+        assert list(a.words(i)) == list(b.words(i)), i
+    monkeypatch.delenv("INDELGPU_CHUNK_READS")
+    # ragged: odd lengths, reads cut at random
+    M = w["read_len"]
+    keep = rng.integers(31, M + 1, size=3000)
+    reads = [w["read_bases"][i * M:i * M + keep[i]].tobytes() for i in range(3000)]
+    data, off = api.pack_sequences(reads)
+    a2 = R.attempt_pe_alignment_batch(None, w["tid"][:3000], w["position"][:3000], w["range1"][:3000], packed=(data, off))
+    seq4, boff, lens, fl = api.pack4(data, off, rc[:3000])
+    b2 = R.attempt_pe_alignment_batch4(seq4, boff, lens, fl, w["tid"][:3000], w["position"][:3000], w["range1"][:3000])
+    assert np.array_equal(a2.status, b2.status)
+    for i in range(3000):
+        assert list(a2.words(i)) == list(b2.words(i)), i
+    # a code bit2char stops the program on (readaln.c:13-15) is an error, not an N
+    bad = seq4.copy()
+    bad[boff[5]] = 0x31                     # M (3) A (1)
+    with pytest.raises(gpu.IndelGpuError):
+        R.attempt_pe_alignment_batch4(bad, boff, lens, fl, w["tid"][:3000], w["position"][:3000], w["range1"][:3000])
+    R.close()
+
+
+def test_gpu_against_the_reference_objects_directly(gpu, oracle):
+    """No oracle in between: the GPU against the reference's own object code (oracle/_ref/libref_dp.so,
+    libref_align.so -- they travel to the GPU box as built files).  (1) local_align + ALIGN at bands 33 ... 160 on
+    windows up to 1 500 bases: score, end points, divide-and-conquer script.  (2) attempt_diagonal_alignments +
+    update_readsegs for wide -g (16, 32, 47): the final segment lists."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = make_rng(321)
+    reads, wins, lows, ups = [], [], [], []
+    for _ in range(260):
+        alpha = rng.choice(["ACGT", "ACGT", "ACGTN", "AC"])
+        N = rng.randrange(300, 1500)
+        ref = rseq(rng, N, alpha)
+        M = rng.randrange(40, 151)
+        off = rng.randrange(0, N - M - 60)
+        read = mutate(rng, ref[off:off + M + 55], alpha, sub=0.01, nindel=rng.randrange(0, 3), maxindel=50)[:M]
+        w = rng.choice([33, 41, 65, 129, 160])
+        low = off - w // 2 + rng.randrange(-4, 5)
+        if max(-len(read), low) > min(N, low + w - 1):
+            continue
+        reads.append(read); wins.append(ref); lows.append(low); ups.append(low + w - 1)
+    R = gpu.Realigner()
+    out = R.band_align_batch(reads, wins, lows, ups, want_script=True)
+    npos = 0
+    for i in range(len(reads)):
+        score, ends, script = oracle.ref_local_align(reads[i], wins[i], lows[i], ups[i])
+        ctx = (i, lows[i], ups[i], len(reads[i]), len(wins[i]))
+        assert int(out["score"][i]) == score, ctx
+        if score > 0:
+            npos += 1
+            assert tuple(int(x) for x in out["ends"][i]) == ends, ctx
+            assert list(out["script"][i][:len(script)]) == script, ctx
+    assert npos > 200
+    R.close()
+    for g in (16, 32, 47):
+        oracle.ref_set_params(6, g, 1000, 10)
+        cases = [split_read_case(rng) for _ in range(120)]
+        Rg = gpu.Realigner(numgaps=g)
+        seen = set()
+        for ref, position, range1, read in cases:          # one contig per case: one context each would be slow, so batch per reference
+            Rg.set_reference([ref])
+            res = Rg.attempt_pe_alignment_batch([read], [0], [position], [range1])
+            want_segs, want_nev = oracle.ref_realign(ref, position, range1, read)
+            assert res.segments(0) == want_segs, (g, position, range1, read)
+            seen.add(int(res.status[0]))
+        assert 6 in seen
+        Rg.close()
+    oracle.ref_set_params()

@@ -43,6 +43,32 @@ def test_local_align_small(O):
     assert pos > n // 2
 
 
+def test_local_align_at_the_sizes_the_gpu_is_tested_on(O):
+    """local_align's forward / reverse sweeps at the shapes of the D1 band sweep and of the GPU parity tests: bands
+    65, 129, 160 (the warp max-scan rewrite, local_sweeps_warp) and 33 / 41 (the register sweeps' upper end), windows
+    up to 1 500 bases, reads up to 150 -- score, end points AND the script ALIGN returns for the sub-rectangle"""
+    rng = make_rng(21)
+    p = O.default_params()
+    pos = 0
+    for it in range(700):
+        alpha = rng.choice(["ACGT", "ACGT", "ACGTN", "AC"])
+        N = rng.randrange(300, 1500)
+        ref = rseq(rng, N, alpha)
+        M = rng.randrange(40, 151)
+        off = rng.randrange(0, N - M - 60)
+        read = mutate(rng, ref[off:off + M + 55], alpha, sub=0.01, nindel=rng.randrange(0, 3), maxindel=50)[:M]
+        w = rng.choice([33, 41, 65, 129, 160])
+        low = off - w // 2 + rng.randrange(-4, 5)
+        up = low + w - 1
+        if max(-len(read), low) > min(N, up):
+            continue
+        a = O.local_align(p, read, ref, low, up)
+        b = O.ref_local_align(read, ref, low, up)
+        assert a == b, (it, w, read, off, low, up)
+        pos += a[0] > 0
+    assert pos > 500
+
+
 def test_global_align_dc_script(O):
     """ALIGN incl. the divide-and-conquer traceback: scores AND scripts (tie-heavy alphabets)."""
     rng = make_rng(7)
@@ -86,7 +112,7 @@ def test_find_best_band(O, k, g):
     O.ref_set_params()
 
 
-@pytest.mark.parametrize("k,g", [(6, 0), (6, 3), (8, 0), (5, 8)])
+@pytest.mark.parametrize("k,g", [(6, 0), (6, 3), (8, 0), (5, 8), (6, 16), (6, 32), (6, 47)])
 def test_realign_two_rounds(O, k, g):
     """attempt_diagonal_alignments + update_readsegs: final segment lists and evidence counts."""
     rng = make_rng(11 + k + 31 * g)

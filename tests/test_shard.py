@@ -104,3 +104,26 @@ def test_two_rank_gloo_matches_single_rank(tmp_path):
         assert list(segs[seg_off[i]:seg_off[i] + nseg[i]]) == [(ln << 4) | op for op, ln, _s, _e in segs_i]
         if segs_i:
             assert rstart[i] == segs_i[0][2]
+
+
+def test_pack4_round_trip():
+    """api.pack4 (ASCII -> the BAM's 4-bit form, optionally stored reverse-complemented and flagged) decoded the way
+    unpack_reads4_kernel does (high nibble first, bit2char's table, complement + reversal when flagged) gives the
+    reads back: equal-length fast path and ragged path"""
+    import numpy as np
+    from indelminer_b200 import api
+    rng = np.random.default_rng(3)
+    dec = {1: "A", 2: "C", 4: "G", 8: "T", 15: "N"}
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    for lens in ([151] * 40, list(rng.integers(1, 90, size=60))):
+        reads = ["".join(rng.choice(list("ACGTN"), p=[.24, .24, .24, .24, .04]) for _ in range(L)) for L in lens]
+        data, off = api.pack_sequences(reads)
+        flags = rng.random(len(reads)) < 0.5
+        seq4, boff, ln, fl = api.pack4(data, off, flags)
+        assert list(ln) == list(lens) and boff[-1] == sum((L + 1) // 2 for L in lens)
+        for i, r in enumerate(reads):
+            b = seq4[boff[i]:boff[i + 1]]
+            s = "".join(dec[(b[t // 2] >> 4) if t % 2 == 0 else (b[t // 2] & 15)] for t in range(lens[i]))
+            if fl[i]:
+                s = "".join(comp[ch] for ch in reversed(s))
+            assert s == r, i
