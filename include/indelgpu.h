@@ -142,7 +142,8 @@ int64_t indelgpu_seg_bound(int32_t n, int64_t total_read_bases);
 
 /* Host buffers in, host buffers out: H2D copies, kernels, D2H copies, synchronised on return.
  * Batches of >= 2^18 reads are processed in chunks of 2^18 reads (the first three are 1/8, 1/4 and 1/2 of
- * that, so that the first kernel starts after a short copy) whose copies overlap the kernels of
+ * that, so that the first kernel starts after a short copy, and the last three shrink the same way so that
+ * little is left to copy back after the last kernel) whose copies overlap the kernels of
  * the neighbouring chunks (pinned buffers from indelgpu_host_alloc make the copies asynchronous);
  * results do not depend on the chunking.  Contexts are independent and may be driven from different
  * host threads, one thread per context at a time. */

@@ -725,8 +725,20 @@ static int realign_batch_impl(indelgpu_ctx* c, const HostBatch* h, indelgpu_resu
     // after a short copy instead of a full chunk's; then full chunks
     std::vector<int> cuts(1, 0);
     if (!(debug_out || n < kChunkReads)) {
-        for (int div = 8; div >= 2 && cuts.back() < n; div >>= 1) cuts.push_back(std::min(n, cuts.back() + std::max(64, kChunkReads / div)));
-        while (cuts.back() < n) cuts.push_back(std::min(n, cuts.back() + kChunkReads));
+        // chunk boundaries: the first chunks are small (1/8, 1/4, 1/2 of a chunk) so that the first kernel starts after a
+        // short copy instead of a full chunk's; the last ones shrink the same way (1/2, 1/4, 1/8) so that little is left
+        // to copy back after the last kernel; equal chunks of at most kChunkReads in between
+        const int k8 = std::max(64, kChunkReads / 8), k4 = std::max(64, kChunkReads / 4), k2 = std::max(64, kChunkReads / 2);
+        const bool down = n >= 2 * (k8 + k4 + k2) + kChunkReads / 2;
+        const int tail = down ? k8 + k4 + k2 : 0;
+        for (int step : {k8, k4, k2}) if (cuts.back() < n - tail) cuts.push_back(std::min(n - tail, cuts.back() + step));
+        const int mid = n - tail - cuts.back();
+        if (mid > 0) {
+            const int pieces = (mid + kChunkReads - 1) / kChunkReads;
+            const int a0 = cuts.back();
+            for (int q = 1; q <= pieces; q++) cuts.push_back(a0 + (int)((long long)mid * q / pieces));
+        }
+        if (down) { cuts.push_back(n - k4 - k8); cuts.push_back(n - k8); cuts.push_back(n); }
     } else cuts.push_back(n);
     const int nchunks = (int)cuts.size() - 1;
     if (nchunks > 1) {

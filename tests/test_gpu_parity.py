@@ -353,7 +353,7 @@ def test_chunked_host_path_equals_single_launch(gpu, monkeypatch):
     a = R.attempt_pe_alignment_batch(*args, packed=(w["read_bases"], w["read_off"]))
     monkeypatch.setenv("INDELGPU_CHUNK_READS", "1000")
     b = R.attempt_pe_alignment_batch(*args, packed=(w["read_bases"], w["read_off"]))
-    assert b.launches == 9 and a.launches == 1          # 125 + 250 + 500 reads (ramp-up), then six chunks of up to 1000
+    assert b.launches == 11 and a.launches == 1         # 125 + 250 + 500 reads (ramp-up), five chunks of 850, then 500 + 250 + 125
     assert np.array_equal(a.status, b.status) and np.array_equal(a.nseg, b.nseg) and np.array_equal(a.rstart, b.rstart)
     assert a.seg_count == b.seg_count == int(a.nseg.sum())
     assert a.cells == b.cells and a.alg_bytes == b.alg_bytes
@@ -558,12 +558,20 @@ def test_gpu_against_the_reference_objects_directly(gpu, oracle):
         cases = [split_read_case(rng) for _ in range(120)]
         Rg = gpu.Realigner(numgaps=g)
         seen = set()
-        for ref, position, range1, read in cases:          # one contig per case: one context each would be slow, so batch per reference
+        aborts = 0
+        for ref, position, range1, read in cases:          # one contig per case
             Rg.set_reference([ref])
-            res = Rg.attempt_pe_alignment_batch([read], [0], [position], [range1])
+            try:
+                res = Rg.attempt_pe_alignment_batch([read], [0], [position], [range1])
+            except gpu.IndelGpuError as e:
+                # numdiagonals <= numgaps in round 2 (short slice, wide -g): the reference's forceassert (alignment.c:405)
+                # would stop THIS process, so it cannot be asked; the library reports the read as rejected (status 7)
+                assert "rejected" in str(e), e
+                aborts += 1
+                continue
             want_segs, want_nev = oracle.ref_realign(ref, position, range1, read)
             assert res.segments(0) == want_segs, (g, position, range1, read)
             seen.add(int(res.status[0]))
-        assert 6 in seen
+        assert 6 in seen and aborts <= 12, (g, aborts)
         Rg.close()
     oracle.ref_set_params()
