@@ -509,7 +509,12 @@ IG_HD inline int script_to_cigar(const uint8_t* A, const uint8_t* B, int M, int 
 // special case of the serial code is the general recurrence.
 // Same results and cell counts as the memory-resident sweeps below (tests/test_host_harness.py).
 // ---------------------------------------------------------------------------------------
-template <int W>
+// WMIN = the narrowest band routed to this instantiation: diagonals t < WMIN lie inside every band it sees.
+// Rows whose band is not cut by the window (the great majority) take a branch-free body: no per-cell validity
+// selects, and the position of the row's first maximum rides in the low bits of one max() per cell
+// (key = score * 64 + 63 - t: the largest key is the largest score at the smallest t) instead of a compare and
+// three selects per cell; rows at the window's edges keep the general body.
+template <int W, int WMIN>
 IG_HD inline void local_sweeps_reg(const DevParams& P, const uint8_t* read, int M, const uint8_t* win, int N,
                                    int low, int up, int& best_o, int& endi_o, int& endj_o,
                                    int& starti_o, int& startj_o, bool& found_o, int& cf_o, int& cr_o)
@@ -542,18 +547,39 @@ IG_HD inline void local_sweeps_reg(const DevParams& P, const uint8_t* read, int 
         const int xn = i + low + W - 1;                             // new top byte for row i + 1, fetched now, merged below
         const uint32_t wnew = (xn >= 0 && xn < N) ? (uint32_t)win[xn] : 0u;
         int e = kNeg, left = kNeg;
+        if (tlo == 0 && thi == band - 1) {
+            // the band lies inside the window on this row
+            int key = -1;
 #pragma unroll
-        for (int t = 0; t < W; t++) {
-            const int hup = (t + 1 < W) ? Hr[t + 1] : kNeg, dup = (t + 1 < W) ? Dr[t + 1] : kNeg;
-            const int d = ig_max(hup - m, dup - Hh);
-            const bool eq = ((wr[t >> 2] >> (8 * (t & 3))) & 0xFFu) == ai;
-            e = ig_max(left - m, e - Hh);
-            int c = ig_max(ig_max(Hr[t] + (eq ? P.match : P.mismatch), e), ig_max(d, 0));
-            const bool v = t >= tlo && t <= thi;
-            if (v) {
-                Hr[t] = c; Dr[t] = d; left = c;
-                if (c > best) { best = c; endi = i; endt = t; }
-            } else { left = kNeg; e = kNeg; }
+            for (int t = 0; t < W; t++) {
+                const int hup = (t + 1 < W) ? Hr[t + 1] : kNeg, dup = (t + 1 < W) ? Dr[t + 1] : kNeg;
+                const int d = ig_max(hup - m, dup - Hh);
+                const bool eq = ((wr[t >> 2] >> (8 * (t & 3))) & 0xFFu) == ai;
+                e = ig_max(left - m, e - Hh);
+                const int c = ig_max(ig_max(Hr[t] + (eq ? P.match : P.mismatch), e), ig_max(d, 0));
+                if (t < WMIN) {
+                    Hr[t] = c; Dr[t] = d; left = c;
+                    key = ig_max(key, c * 64 + (63 - t));
+                } else if (t < band) {
+                    Hr[t] = c; Dr[t] = d; left = c;
+                    key = ig_max(key, c * 64 + (63 - t));
+                } else { left = kNeg; e = kNeg; }
+            }
+            if ((key >> 6) > best) { best = key >> 6; endi = i; endt = 63 - (key & 63); }
+        } else {
+#pragma unroll
+            for (int t = 0; t < W; t++) {
+                const int hup = (t + 1 < W) ? Hr[t + 1] : kNeg, dup = (t + 1 < W) ? Dr[t + 1] : kNeg;
+                const int d = ig_max(hup - m, dup - Hh);
+                const bool eq = ((wr[t >> 2] >> (8 * (t & 3))) & 0xFFu) == ai;
+                e = ig_max(left - m, e - Hh);
+                int c = ig_max(ig_max(Hr[t] + (eq ? P.match : P.mismatch), e), ig_max(d, 0));
+                const bool v = t >= tlo && t <= thi;
+                if (v) {
+                    Hr[t] = c; Dr[t] = d; left = c;
+                    if (c > best) { best = c; endi = i; endt = t; }
+                } else { left = kNeg; e = kNeg; }
+            }
         }
         cf += thi - tlo + 1;
 #pragma unroll
@@ -594,20 +620,39 @@ IG_HD inline void local_sweeps_reg(const DevParams& P, const uint8_t* read, int 
         const int xn = i + low - 2;                                 // new bottom byte for row i - 1, fetched now, merged below
         const uint32_t wnew = (xn >= 0 && xn < N) ? (uint32_t)win[xn] : 0u;
         int e = kNeg, right = kNeg;
+        if (tlo == 0 && thi == band - 1) {
+            // the band lies inside the window on this row: every cell is computed, and the first cell in sweep order
+            // (largest t) that reaches the optimum is picked afterwards -- what the sweep writes behind it is never read
+            int tfound = -1;
 #pragma unroll
-        for (int t = W - 1; t >= 0; t--) {
-            const int hdn = (t > 0) ? Hr[t - 1] : kNeg, ddn = (t > 0) ? Dr[t - 1] : kNeg;
-            const int d = ig_max(hdn - m, ddn - Hh);
-            const bool eq = ((wr[t >> 2] >> (8 * (t & 3))) & 0xFFu) == ai;
-            e = ig_max(right - m, e - Hh);
-            const int c = ig_max(ig_max(Hr[t] + (eq ? P.match : P.mismatch), e), d);
-            const bool v = t >= tlo && t <= thi && !found;
-            if (v) {
-                Hr[t] = c; Dr[t] = d; right = c;
-                if (c == best) { found = true; starti = i; startt = t; cr += thi - t + 1; }
-            } else {
-                right = kNeg; e = kNeg;
-                if (t < tlo) { Hr[t] = kNeg; Dr[t] = kNeg; }          // left the window: stale values must not be read
+            for (int t = W - 1; t >= 0; t--) {
+                const int hdn = (t > 0) ? Hr[t - 1] : kNeg, ddn = (t > 0) ? Dr[t - 1] : kNeg;
+                const int d = ig_max(hdn - m, ddn - Hh);
+                const bool eq = ((wr[t >> 2] >> (8 * (t & 3))) & 0xFFu) == ai;
+                e = ig_max(right - m, e - Hh);
+                const int c = ig_max(ig_max(Hr[t] + (eq ? P.match : P.mismatch), e), d);
+                if (t < WMIN || t < band) {
+                    Hr[t] = c; Dr[t] = d; right = c;
+                    tfound = ig_max(tfound, c == best ? t : -1);
+                } else { right = kNeg; e = kNeg; }
+            }
+            if (tfound >= 0) { found = true; starti = i; startt = tfound; cr += thi - tfound + 1; }
+        } else {
+#pragma unroll
+            for (int t = W - 1; t >= 0; t--) {
+                const int hdn = (t > 0) ? Hr[t - 1] : kNeg, ddn = (t > 0) ? Dr[t - 1] : kNeg;
+                const int d = ig_max(hdn - m, ddn - Hh);
+                const bool eq = ((wr[t >> 2] >> (8 * (t & 3))) & 0xFFu) == ai;
+                e = ig_max(right - m, e - Hh);
+                const int c = ig_max(ig_max(Hr[t] + (eq ? P.match : P.mismatch), e), d);
+                const bool v = t >= tlo && t <= thi && !found;
+                if (v) {
+                    Hr[t] = c; Dr[t] = d; right = c;
+                    if (c == best) { found = true; starti = i; startt = t; cr += thi - t + 1; }
+                } else {
+                    right = kNeg; e = kNeg;
+                    if (t < tlo) { Hr[t] = kNeg; Dr[t] = kNeg; }          // left the window: stale values must not be read
+                }
             }
         }
         if (!found) cr += ig_max(0, thi - tlo + 1);
@@ -648,15 +693,15 @@ IG_HD inline BandLocal band_local(const DevParams& P, IArr<STRIDE> bands, int ma
     IArr<STRIDE> Hp = bands, Dp = bands + wb, Hn = bands + 2 * wb, Dn = bands + 3 * wb;
     int best = 0, endi = 0, endj = 0, cf = 0, cr = 0, starti = 0, startj = 0; bool found = false;
     // the unrolled sweeps compute W diagonals whatever the band: pick the tightest instantiation
-#define IG_SWEEP(W) local_sweeps_reg<W>(P, read, M, win, N, low, up, best, endi, endj, starti, startj, found, cf, cr)
-    if (band <= 6)       IG_SWEEP(6);
-    else if (band <= 8)  IG_SWEEP(8);
-    else if (band <= 12) IG_SWEEP(12);
-    else if (band <= 16) IG_SWEEP(16);
-    else if (band <= 20) IG_SWEEP(20);
-    else if (band <= 24) IG_SWEEP(24);
-    else if (band <= 32) IG_SWEEP(32);
-    else if (band <= 40) IG_SWEEP(40);
+#define IG_SWEEP(W, WMIN) local_sweeps_reg<W, WMIN>(P, read, M, win, N, low, up, best, endi, endj, starti, startj, found, cf, cr)
+    if (band <= 6)       IG_SWEEP(6, 1);
+    else if (band <= 8)  IG_SWEEP(8, 7);
+    else if (band <= 12) IG_SWEEP(12, 9);
+    else if (band <= 16) IG_SWEEP(16, 13);
+    else if (band <= 20) IG_SWEEP(20, 17);
+    else if (band <= 24) IG_SWEEP(24, 21);
+    else if (band <= 32) IG_SWEEP(32, 25);
+    else if (band <= 40) IG_SWEEP(40, 33);
 #undef IG_SWEEP
     else {
 #define AT(arr, t) ((arr)[(t) + 1])

@@ -99,3 +99,17 @@ def test_inline_annotate_mode_two_pass_support(pair):
     assert m and int(m.group(2)) > 100 and int(m.group(3)) <= int(m.group(1))
     direct, _ = run("indelminer_fakegpu_annot", args, pair)
     assert direct == want
+
+
+def test_stable_sort_flavour_is_libc_independent_and_agrees_here(pair):
+    """row f4: slsort bound to a stable merge sort (host/indelgpu_stablesort.c, -Dqsort=... on the unchanged slinklist.c).
+    On this C library its VCFs equal the default build's -- test_data (incl. the BF token that differs from upstream's
+    golden file) and a synthetic set with many equal-position evidence records"""
+    need("indelminer_fakegpu_stable")
+    out, _ = run("indelminer_fakegpu_stable", ["-i", "indelminer.config", "testdata_reference.fa", "sample=alignments.bam"], GOLD,
+                 dict(INDELGPU_MODE="inline"))
+    with open(os.path.join(GOLD, "testdata_refrun.vcf")) as f:
+        assert out == f.read()
+    want, _ = run("indelminer_ref", ["-i", "tumor.config", "tumor.fa", "tumor=tumor.bam"], pair)
+    out, _ = run("indelminer_fakegpu_stable", ["-i", "tumor.config", "tumor.fa", "tumor=tumor.bam"], pair, dict(INDELGPU_MODE="inline"))
+    assert out == want
