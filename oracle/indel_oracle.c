@@ -68,6 +68,14 @@ static uint32_t kmer_at(const char* s, int k)
     return c;
 }
 
+/* 1 when find_best_band's forceassert(numdiagonals > numgaps) (alignment.c:403-405, unsigned arithmetic kept) fires */
+int orc_would_assert(const orc_params* p, uint32_t N, uint32_t M)
+{
+    const uint32_t k = (uint32_t)p->klength, g = (uint32_t)p->numgaps;
+    const uint32_t numdiag = (N - (k - 1)) + (M - (k - 1));
+    return !(numdiag > g);
+}
+
 void orc_find_best_band(const orc_params* p,
                         const char* refseq, uint32_t zstart1, uint32_t end1, uint32_t anchor,
                         const char* readseq, uint32_t zstart2, uint32_t end2,
@@ -77,6 +85,8 @@ void orc_find_best_band(const orc_params* p,
     const uint32_t N = end1 - zstart1, M = end2 - zstart2;
     /* alignment.c:403-405 (unsigned arithmetic kept) */
     const uint32_t numdiag = (N - (k - 1)) + (M - (k - 1));
+    /* the reference stops the program here (forceassert, alignment.c:405).  The oracle must survive to say so: the
+     * stand-alone entry point still exits, orc_realign_read reports ORC_ST_ASSERT (see orc_would_assert) */
     if (!(numdiag > g)) { fprintf(stderr, "oracle: numdiagonals <= numgaps\n"); exit(1); }
     if (M < k) {                                   /* alignment.c:408-412 */
         *plow = (int)(numdiag - 1); *pup = (int)(numdiag - 1);
@@ -672,6 +682,7 @@ void orc_realign_read(const orc_params* p, const char* refseq, int reflength,
     (void)right1;
 
     /* round 1 (alignment.c:555-566) */
+    if (orc_would_assert(p, (uint32_t)right1 - (uint32_t)left1, readlength)) { o->status = ORC_ST_ASSERT; return; }
     orc_find_best_band(p, refseq, (uint32_t)left1, (uint32_t)right1, (uint32_t)anchor,
                        read, 0, readlength, &o->low1, &o->up1);
     int r1, r2, q1, q2;
@@ -726,6 +737,7 @@ void orc_realign_read(const orc_params* p, const char* refseq, int reflength,
         } else { o->status = ORC_ST_NOBRANCH; return; }
     } else { o->status = ORC_ST_NOBRANCH; return; }
 
+    if (orc_would_assert(p, e1 - zs1, e2 - zs2)) { o->status = ORC_ST_ASSERT; o->nseg = 0; return; }
     orc_find_best_band(p, refseq, zs1, e1, anc, read, zs2, e2, &o->low2, &o->up2);
     int r3, r4, q3, q4;
     o->n2 = orc_attempt_band_alignment(p, refseq, zs1, e1, read, zs2, e2, o->low2, o->up2,

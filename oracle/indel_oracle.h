@@ -102,8 +102,11 @@ enum {
     ORC_ST_R2FAIL = 3,        /* round 2 did not reach the read end  :623,645,679,701 */
     ORC_ST_NOBRANCH = 4,      /* neither q1==0 nor q2==L / r2>=anchor / r1==anchor  :651,657,707,712 */
     ORC_ST_NOCOMBINE = 5,     /* segments neither overlap nor abut :750 */
-    ORC_ST_SPLIT = 6          /* two segments combined            :724-749 */
+    ORC_ST_SPLIT = 6,         /* two segments combined            :724-749 */
+    ORC_ST_ASSERT = 7         /* the reference stops the program: forceassert(numdiagonals > numgaps), alignment.c:405 */
 };
+
+int orc_would_assert(const orc_params* p, uint32_t N, uint32_t M);
 
 void orc_realign_read(const orc_params* p, const char* refseq, int reflength,
                       int position, int range1, const char* read, int readlength,

@@ -565,10 +565,13 @@ def test_gpu_against_the_reference_objects_directly(gpu, oracle):
                 res = Rg.attempt_pe_alignment_batch([read], [0], [position], [range1])
             except gpu.IndelGpuError as e:
                 # numdiagonals <= numgaps in round 2 (short slice, wide -g): the reference's forceassert (alignment.c:405)
-                # would stop THIS process, so it cannot be asked; the library reports the read as rejected (status 7)
+                # would stop THIS process, so it cannot be asked; the library reports the read as rejected (status 7),
+                # and the oracle names exactly these reads (ORC_ST_ASSERT)
                 assert "rejected" in str(e), e
+                assert oracle.realign_read(oracle.default_params(6, g), ref, position, range1, read).status == 7
                 aborts += 1
                 continue
+            assert oracle.realign_read(oracle.default_params(6, g), ref, position, range1, read).status != 7
             want_segs, want_nev = oracle.ref_realign(ref, position, range1, read)
             assert res.segments(0) == want_segs, (g, position, range1, read)
             seen.add(int(res.status[0]))

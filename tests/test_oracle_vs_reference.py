@@ -119,13 +119,17 @@ def test_realign_two_rounds(O, k, g):
     O.ref_set_params(k, g, 1000, 10)
     p = O.default_params(k, g)
     seen = set()
+    stops = 0
     for _ in range(500):
         ref, position, range1, read = split_read_case(rng)
         a = O.realign_read(p, ref, position, range1, read)
+        if a.status == 7:           # numdiagonals <= numgaps in round 2 (short slice, wide -g): the reference's forceassert
+            stops += 1              # (alignment.c:405) would end THIS process, so it cannot be asked
+            continue
         b = O.ref_realign(ref, position, range1, read)
         assert (a.segments(), a.nevidence) == b, (k, g, position, range1, read)
         seen.add(a.status)
-    assert {1, 2, 3, 4, 5, 6} <= seen
+    assert {1, 2, 3, 4, 5, 6} <= seen and stops <= 40, stops
     O.ref_set_params()
 
 
