@@ -1,6 +1,8 @@
 """The JSON line bench.py prints is a contract with the driver: check the committed line of the final
-build (profiles/r01_v11_bench.json, produced by `python bench.py` on the GPU box) for every key the
-contract names, and the reference arm's line for its own."""
+build (profiles/r02_bench.json, produced by `python bench.py` on the GPU box) for every key the
+contract names, the reference arm's line for its own, and the round-2 additions: the two arms'
+`config` objects are equal, the band sweep and the support check are part of the default line with their own
+clocks records, the end-to-end VCF wall time is in the line."""
 import json
 import os
 
@@ -13,7 +15,7 @@ def load(name):
 
 
 def test_default_line_has_every_contract_key():
-    d = load("r01_v11_bench.json")
+    d = load("r02_bench.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in d, k
@@ -38,7 +40,27 @@ def test_default_line_has_every_contract_key():
 
 
 def test_reference_arm_line():
-    d = load("r01_v5_bench_reference_arm.json")
+    d = load("r02_bench_reference_arm.json")
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["config"] == load("r02_bench.json")["config"]          # the driver compares the arms' configs key by key
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
+
+
+def test_round2_additions_of_the_default_line():
+    d = load("r02_bench.json")
+    assert d["oracle_spot_check"]["reads"] >= 4096 and d["oracle_spot_check"]["mismatches"] == 0
+    bands = d["extra"]["band_sweep"]["bands"]
+    assert [b["band"] for b in bands] == [1, 5, 9, 17, 33, 65, 129] and d["extra"]["band_sweep"]["tasks"] == 1 << 20
+    for b in bands:
+        for k in ("kernel_ms", "gcups", "gcups_executed_cells", "cells", "frac_of_int32_peak", "gpu_launches", "clocks"):
+            assert k in b, (b["band"], k)
+        assert b["clocks"]["sm_mhz"] and not b["clocks"]["reasons"] and b["gpu_launches"] > 0
+        c = b["cells"]
+        executed = c["forward"] + c["reverse"] + c["align"] - c["align_not_swept_shortcut"]
+        assert 0 < b["gcups_executed_cells"] <= b["gcups"] and executed > 0
+    s = d["extra"]["support"]
+    assert s["clocks"]["sm_mhz"] and s["gpu_launches"] > 0 and s["oracle_checked_pairs"] >= 512 and s["roofline"]["frac"] > 0.5
+    v = d["vcf_wall_time"]
+    assert v["identical"] is True and v["records"] > 1000 and 0 < v["gpu_s"] < v["reference_s"]
+    assert "indelgpu_realign_batch4" in d["e2e"]["entry_point"]
