@@ -331,8 +331,12 @@ realign_kernel(const __grid_constant__ RealignArgs a)
                 // had a whole read's worth of time to arrive.  Write them out before anything stitches again.
                 if (pend_idx >= 0) {
                     const long long poff = __shfl_sync(0xFFFFFFFFu, pend_off, 0);
-                    if (poff + pend_ns <= a.seg_capacity) for (int t = lane; t < pend_ns; t += 32) a.segs[poff + t] = S.segs[t];
-                    else if (lane == 0) atomicExch(a.error_flag, 2);
+                    if (poff + pend_ns <= a.seg_capacity) {
+                        uint32_t* dst = a.segs + poff;               // nearly always fewer than 32 words: one predicated store
+                        if (lane < pend_ns) dst[lane] = S.segs[lane];
+                        #pragma unroll 1
+                        for (int t = lane + 32; t < pend_ns; t += 32) dst[t] = S.segs[t];
+                    } else if (lane == 0) atomicExch(a.error_flag, 2);
                     if (lane == 0) a.seg_off[pend_idx] = poff;
                     pend_idx = -1;
                     __syncwarp();

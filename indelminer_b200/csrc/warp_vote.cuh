@@ -75,17 +75,21 @@ __host__ __device__ inline WarpLayout make_warp_layout(const DevParams& P, int m
     L.off_pk = o;    o += round_up(L.pk_words * 4, 16);
     L.off_cig1 = o;  o += round_up(L.ops_cap * 4, 16);
     L.off_cig2 = o;  o += round_up(L.ops_cap * 4, 16);
-    L.off_segs = o;  o += round_up((2 * L.ops_cap + 4) * 4, 16);
     L.off_bar = o;   o += 16;                                      // two mbarriers
     L.off_misc = o;  o += 256;                                     // Aln x 2, Plan, scalars
     // the vote's hit list and the alignment's prefix sums / match bits are never live together: one region
     {
         // kHitListCap entries (window scan) or kIdxListHits entries (kmer_index.cuh)
-        const int list_bytes = round_up((L.indexed ? 160 : 32 + 512 + 32) * (L.hist_bits == 8 ? 2 : 4), 16);
+        const int list_bytes = round_up((L.indexed ? 160 : 32 + 256 + 32) * (L.hist_bits == 8 ? 2 : 4), 16);
         const int psum_bytes = round_up((max_read + 2) * 4, 16);
         const int bits_bytes = round_up(((max_read + 127) / 128 * 4 + 4) * 4, 16);
-        L.off_list = o; L.off_psum = o; L.off_bits = o + psum_bytes;
-        o += list_bytes > psum_bytes + bits_bytes ? list_bytes : psum_bytes + bits_bytes;
+        // ... and the stitched segment words are written after the last alignment and flushed before the next read's
+        // first vote (realign_kernel's pend_* block): the same region again
+        const int segs_bytes = round_up((2 * L.ops_cap + 4) * 4, 16);
+        L.off_list = o; L.off_psum = o; L.off_bits = o + psum_bytes; L.off_segs = o;
+        int region = list_bytes > psum_bytes + bits_bytes ? list_bytes : psum_bytes + bits_bytes;
+        if (segs_bytes > region) region = segs_bytes;
+        o += region;
     }
     L.total = round_up(o, 128);
     return L;
@@ -250,7 +254,7 @@ __device__ __forceinline__ uint32_t kmer_at(const uint32_t* pk, int i, uint32_t 
 // element type of the per-warp hit list: diagonal indices fit 16 bits whenever HB == 8 (make_warp_layout)
 template <int HB> struct HitIdx { typedef uint32_t type; };
 template <> struct HitIdx<8> { typedef uint16_t type; };
-constexpr int kHitListCap = 32 + 512 + 32;     // carried remainder + one step of 32 lanes x 16 positions
+constexpr int kHitListCap = 32 + 256 + 32;     // carried remainder + at most 256 hits appended at a time (a step with more is split in two)
 
 // table entry: offset + 1 of the read k-mer if it occurs exactly once in the slice, else 0.
 // Direct tables hold one entry per possible k-mer, HB/8 bytes wide (HB == 8 iff the slice has at most
@@ -446,21 +450,43 @@ __device__ __forceinline__ int vote_band_warp(const DevParams& P, WarpView& V, c
                     const int phi = (wi == w1) ? (lr - (wi << 4)) : 15;
                     hits &= (0xFFFFu << plo) & (0xFFFFu >> (15 - phi));
                 }
-                const int mine = __popc(hits);
-                int pre = mine;                                   // inclusive scan of the lanes' hit counts
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, pre, o); if (lane >= o) pre += t; }
-                const int total = __shfl_sync(0xFFFFFFFFu, pre, 31);
-                int slot = fill + pre - mine;
+                // pass B, then pass C on the full chunks.  A step with more than 256 hits (repeat-rich windows only) is
+                // appended in two halves -- positions 0-7 of every lane, then 8-15 -- so that the list never holds more
+                // than 31 + 256 entries
+                uint32_t rest = hits; bool low_half = false;
 #pragma unroll 1
-                while (hits) {
-                    const int p = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    const uint32_t off = kmer_lookup<DIRECT, HB>(V, __funnelshift_r(lo, hi, 2 * p) & kmask);
-                    list[slot++] = (hit_t)(rel0 + p - (int)(off - 1u) + shiftM);
-                }
-                fill += total;
-                __syncwarp();
+                do {
+                    const uint32_t take = low_half ? (rest & 0x00FFu) : rest;
+                    const int mine = __popc(take);
+                    int pre = mine;                               // inclusive scan of the lanes' hit counts
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, pre, o); if (lane >= o) pre += t; }
+                    const int total = __shfl_sync(0xFFFFFFFFu, pre, 31);
+                    if (total > 256) { low_half = true; continue; }
+                    int slot = fill + pre - mine;
+                    uint32_t h = take;
+#pragma unroll 1
+                    while (h) {
+                        const int p = __ffs(h) - 1;
+                        h &= h - 1;
+                        const uint32_t off = kmer_lookup<DIRECT, HB>(V, __funnelshift_r(lo, hi, 2 * p) & kmask);
+                        list[slot++] = (hit_t)(rel0 + p - (int)(off - 1u) + shiftM);
+                    }
+                    fill += total;
+                    rest &= ~take; low_half = false;
+                    __syncwarp();
+                    if (__any_sync(0xFFFFFFFFu, rest != 0u)) {       // more to come: make room first
+                        int dn = 0;
+#pragma unroll 1
+                        for (; fill - dn >= 32; dn += 32) vote_hits_chunk<HB>(V, list + dn, 32, a, lbest, lkey);
+                        const int rem = fill - dn;
+                        const hit_t v = (lane < rem) ? list[dn + lane] : (hit_t)0;
+                        __syncwarp();
+                        if (lane < rem) list[lane] = v;
+                        fill = rem;
+                        __syncwarp();
+                    }
+                } while (__any_sync(0xFFFFFFFFu, rest != 0u));
             }
             // pass C: full chunks of 32; the last, partial chunk once the window is exhausted
             int done = 0;
