@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -760,6 +761,9 @@ static int realign_batch_impl(indelgpu_ctx* c, const HostBatch* h, indelgpu_resu
             c->ev_out.push_back(e);
         }
         unsigned long long* counts = reinterpret_cast<unsigned long long*>(c->pinned_counts);
+        const bool verbose = getenv("INDELGPU_VERBOSE") != nullptr;
+        const auto t_begin = std::chrono::steady_clock::now();
+        if (verbose) CU(cudaEventRecord(c->ev_t0, st));
         if (c->chunk_counts.ensure(8 * (size_t)(nchunks + 8))) return INDELGPU_ENOMEM;
         unsigned long long* d_counts = c->chunk_counts.as<unsigned long long>();
         for (int ch = 0; ch < nchunks; ch++) {
@@ -793,6 +797,8 @@ static int realign_batch_impl(indelgpu_ctx* c, const HostBatch* h, indelgpu_resu
             CU(cudaMemcpyAsync(o->rstart + c0, dout.rstart + c0, 4 * (size_t)m, cudaMemcpyDeviceToHost, c->st_out));
             CU(cudaMemcpyAsync(o->seg_off + c0, dout.seg_off + c0, 8 * (size_t)m, cudaMemcpyDeviceToHost, c->st_out));
         }
+        const auto t_enq = std::chrono::steady_clock::now();
+        if (verbose) CU(cudaEventRecord(c->ev_t1, st));
         // segment words: the allocator is monotonic and the chunks' kernels run in order, so the words of
         // chunk ch are [count after ch-1, count after ch); copy each range as soon as its count is known,
         // while the later chunks are still being realigned
@@ -805,6 +811,16 @@ static int realign_batch_impl(indelgpu_ctx* c, const HostBatch* h, indelgpu_resu
         }
         segs_copied = (int64_t)prev;
         CU(cudaStreamSynchronize(c->st_out));
+        if (verbose) {
+            const auto t_end = std::chrono::steady_clock::now();
+            float kms = 0;
+            cudaEventSynchronize(c->ev_t1);
+            cudaEventElapsedTime(&kms, c->ev_t0, c->ev_t1);
+            fprintf(stderr, "libindelgpu: realign_batch: %d chunks; host enqueued everything after %.2f ms; kernel stream busy from its first to its last "
+                            "command %.2f ms; results on the host after %.2f ms\n", nchunks,
+                    std::chrono::duration<double, std::milli>(t_enq - t_begin).count(), (double)kms,
+                    std::chrono::duration<double, std::milli>(t_end - t_begin).count());
+        }
     } else {
         int max_read = 0, max_range = 0;
         if (int rcs = scan_range(0, n, &max_read, &max_range)) return rcs;
