@@ -422,7 +422,7 @@ def run_ours(a, rank, world, local_rank):
     if rank == 0:
         # the timed batch itself, spot-checked against the oracle after the timed region (never inside it)
         line["oracle_spot_check"] = spot_check(R, w, d_status.cpu().numpy(), d_nseg.cpu().numpy(), d_rstart.cpu().numpy(),
-                                               d_segoff.cpu().numpy(), d_segs.cpu().numpy(), ref, 4096)
+                                               d_segoff.cpu().numpy(), d_segs.cpu().numpy(), ref, 4096, a.numgaps)
     if rank == 0 and world == 1 and not a.no_cpu:
         cores = os.cpu_count() or 1
         nsample = a.cpu_sample or calibrate_cpu_sample(ref, w, cores)
@@ -463,11 +463,11 @@ def run_ours(a, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def spot_check(R, w, status, nseg, rstart, seg_off, segs, ref, count):
+def spot_check(R, w, status, nseg, rstart, seg_off, segs, ref, count, numgaps=0):
     """`count` reads spread over the timed batch, realigned by the oracle and compared (status, start, segment words)"""
     from oracle import oracle as O
     from indelminer_b200.api import walk_segments
-    p = O.default_params()
+    p = O.default_params(6, numgaps)
     cs = ref.tobytes()
     M = w["read_len"]
     n = len(status)
