@@ -17,7 +17,9 @@
  * with a GPU run in the other (tests/golden/cfg3_reference.json).
  *
  *   synth_bam PREFIX --contigs N --length L [--lengths l1,l2,...] --depth D --readlen M --insert MEAN,SD
- *             --spacing S --maxindel K --subrate R --seed X [--keep F] [--readseed Y] [--level Z]
+ *             --spacing S --maxindel K --subrate R --seed X [--keep F] [--readseed Y] [--level Z] [--rg N]
+ * --rg N (default 0 = no RG tag) deals the pairs to N read groups rg0 .. rgN-1 (RG:Z tag, @RG header lines) and gives
+ * every group its own IL line in the config (the maximum grows by 10 per group): exercises the per-read-group range.
  * writes PREFIX.fa, PREFIX.bam, PREFIX.bam.bai, PREFIX.config and prints one JSON line of counts.
  */
 #include <stdint.h>
@@ -149,6 +151,8 @@ static int key_cmp(const void* x, const void* y)
 
 static int op_code(char c) { return c == 'M' ? BAM_CMATCH : c == 'I' ? BAM_CINS : c == 'D' ? BAM_CDEL : BAM_CSOFT_CLIP; }
 
+static int g_nrg = 0;
+
 static void write_record(bamFile out, int tid, uint64_t pair, const end_t* e, const end_t* mate, int is_first, int M)
 {
     static uint8_t data[4096];
@@ -179,10 +183,15 @@ static void write_record(bamFile out, int tid, uint64_t pair, const end_t* e, co
     p += (M + 1) / 2;
     memset(p, 40, (size_t)M); p += M;                                  /* quality 'I' */
     p[0] = 'M'; p[1] = 'Q'; p[2] = 'C'; p[3] = 60; p += 4;
+    int l_aux = 4;
+    if (g_nrg > 0) {
+        const int n = snprintf((char*)p, 16, "RGZrg%d", (int)(pair % (uint64_t)g_nrg)) + 1;      /* tag, type, NUL-terminated name */
+        p += n; l_aux += n;
+    }
     b.core.tid = tid; b.core.pos = (int32_t)pos; b.core.bin = bam_reg2bin((uint32_t)pos, (uint32_t)end);
     b.core.qual = e->unmapped ? 0 : 60; b.core.l_qname = (uint8_t)lq; b.core.flag = flag; b.core.n_cigar = (uint16_t)nc;
     b.core.l_qseq = M; b.core.mtid = tid; b.core.mpos = (int32_t)pnext; b.core.isize = (int32_t)tlen;
-    b.data = data; b.data_len = (int)(p - data); b.m_data = (int)sizeof(data); b.l_aux = 4;
+    b.data = data; b.data_len = (int)(p - data); b.m_data = (int)sizeof(data); b.l_aux = l_aux;
     bam_write1(out, &b);
 }
 
@@ -208,6 +217,7 @@ int main(int argc, char** argv)
         else if (!strcmp(o, "--keep")) keep = atof(v);
         else if (!strcmp(o, "--readseed")) { readseed = strtoull(v, NULL, 10); have_readseed = 1; }
         else if (!strcmp(o, "--level")) level = atoi(v);
+        else if (!strcmp(o, "--rg")) g_nrg = atoi(v);
         else { fprintf(stderr, "synth_bam: unknown option %s\n", o); return 2; }
     }
     if (M > 1000 || M < 20 || ncontigs < 1 || ncontigs > 512) return 2;
@@ -221,19 +231,21 @@ int main(int argc, char** argv)
     snprintf(path, sizeof(path), "%s.config", prefix);
     FILE* cfg = fopen(path, "w");
     if (!fa || !cfg) { fprintf(stderr, "synth_bam: cannot write %s.*\n", prefix); return 1; }
-    fprintf(cfg, "IL generic %d %d\n", imean - 6 * isd, imean + 4 * isd);
+    if (g_nrg <= 0) fprintf(cfg, "IL generic %d %d\n", imean - 6 * isd, imean + 4 * isd);
+    for (int r = 0; r < g_nrg; r++) fprintf(cfg, "IL rg%d %d %d\n", r, imean - 6 * isd, imean + 4 * isd + 10 * r);
 
     bam_header_t* h = bam_header_init();
     h->n_targets = ncontigs;
     h->target_name = calloc((size_t)ncontigs, sizeof(char*));
     h->target_len = calloc((size_t)ncontigs, sizeof(uint32_t));
-    char* text = malloc(64 + 64 * (size_t)ncontigs);
+    char* text = malloc(64 + 64 * (size_t)ncontigs + 32 * (size_t)(g_nrg > 0 ? g_nrg : 0));
     int tl = sprintf(text, "@HD\tVN:1.0\tSO:coordinate\n");
     for (int c = 0; c < ncontigs; c++) {
         char nm[32]; snprintf(nm, sizeof(nm), "chr%d", c + 1);
         h->target_name[c] = strdup(nm); h->target_len[c] = (uint32_t)clen[c];
         tl += sprintf(text + tl, "@SQ\tSN:%s\tLN:%lld\n", nm, (long long)clen[c]);
     }
+    for (int r = 0; r < g_nrg; r++) tl += sprintf(text + tl, "@RG\tID:rg%d\tSM:s\n", r);
     h->text = text; h->l_text = (uint32_t)tl;
     snprintf(path, sizeof(path), "%s.bam", prefix);
     snprintf(mode, sizeof(mode), "w%d", level);

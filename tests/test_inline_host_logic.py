@@ -113,3 +113,21 @@ def test_stable_sort_flavour_is_libc_independent_and_agrees_here(pair):
     want, _ = run("indelminer_ref", ["-i", "tumor.config", "tumor.fa", "tumor=tumor.bam"], pair)
     out, _ = run("indelminer_fakegpu_stable", ["-i", "tumor.config", "tumor.fa", "tumor=tumor.bam"], pair, dict(INDELGPU_MODE="inline"))
     assert out == want
+
+
+def test_inline_mode_learns_the_range_of_every_read_group(tmp_path):
+    """three read groups with different insert ranges (RG:Z tags, one IL line each): range[1] lives in a hashtable
+    private to indelminer.c, so the prefetcher learns it per group from the first call that passes it; after that the
+    calls of all three groups are answered from the prefetched batches"""
+    need("indelminer_ref", "indelminer_fakegpu", "synth_bam")
+    d = str(tmp_path)
+    subprocess.check_call([os.path.join(REFDIR, "synth_bam"), "c", "--length", "300000", "--depth", "20", "--seed", "12", "--rg", "3"],
+                          cwd=d, stdout=subprocess.DEVNULL)
+    with open(os.path.join(d, "c.config")) as f:
+        assert sum(ln.startswith("IL rg") for ln in f) == 3
+    want, _ = run("indelminer_ref", ["-i", "c.config", "c.fa", "s=c.bam"], d)
+    out, err = run("indelminer_fakegpu", ["-i", "c.config", "c.fa", "s=c.bam"], d, dict(INDELGPU_MODE="inline"))
+    assert out == want
+    m = re.search(r"(\d+) calls answered from (\d+) prefetched batches \((\d+) reads realigned in them\), (\d+) computed per read", err)
+    hits, _b, prefetched, direct = map(int, m.groups())
+    assert hits > 10 * direct and prefetched == hits
