@@ -47,6 +47,9 @@ void indelgpu_inline_learn(int32_t range1);
  * -Dbam_index_load=indelgpu_bam_index_load -Dbam_index_destroy=indelgpu_bam_index_destroy: the
  * open / load-index / fetch / close / destroy sequence calculate_cov_params (shared.c:178-212) and
  * is_indel_supported (variant.c:1561-1572) run once per printed variant reuses one handle and one index. */
+/* shared.c only: -Dbam_fetch=indelgpu_bam_fetch_cov (host/indelgpu_inline.c): the per-variant coverage fetch of
+ * calculate_cov_params, answered from the records the inline driver still holds when they cover the region */
+int indelgpu_bam_fetch_cov(bamFile fp, const bam_index_t* idx, int tid, int beg, int end, void* data, bam_fetch_f func);
 BGZF* indelgpu_bgzf_open(const char* path, const char* mode);
 int indelgpu_bgzf_close(BGZF* fp);
 bam_index_t* indelgpu_bam_index_load(const char* fn);

@@ -71,14 +71,23 @@ static int32_t rg_range1(const char* name)
 typedef struct {
     bam1_t* recs; int nrec, caprec;
     int32_t* cand;                 /* per record: index in `batch`, or -1 */
-    igb_batch* batch;
+    igb_batch* batch;              /* one of the two pinned batches (serial & 1): only the records are kept for long */
     int answered;                  /* the batch results are valid */
-    int full;                      /* 0 = the producer may fill it, 1 = the consumer may read it */
+    int serial;                    /* which block of the current region this is */
     int last;                      /* the region ends with this block */
     int ret;                       /* bam_iter_read's last return value */
+    int32_t maxspan;               /* the longest reference span (bam_calend - pos) of any record up to and including this block */
 } pf_block;
 
-static pf_block g_blk[2];
+/* A ring of blocks: the consumer is at block c, the producer may fill c + 1, and blocks c - 3 .. c stay readable for
+ * indelgpu_bam_fetch_cov (the per-variant coverage fetch looks back about one READCHUNK of records). */
+enum { NBLK = 6, KEEP = 3 };
+static pf_block g_blk[NBLK];
+static igb_batch* g_batch[2];
+static int g_produced = 0;                 /* blocks of the current region the producer has finished */
+static int g_fetch_tid = -1, g_fetch_beg = 0, g_fetch_end = 0, g_cur_serial = -1;
+static int g_last_serial = -1;             /* after the region's last block: the ring stays valid until the next region starts */
+static long long g_cov_served = 0, g_cov_fallback = 0;
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static pthread_cond_t g_cv = PTHREAD_COND_INITIALIZER;
 
@@ -105,6 +114,8 @@ static void print_stats(void)
     fprintf(stderr, "libindelgpu: inline mode: %lld BAM records, %lld calls answered from %lld prefetched batches "
                     "(%lld reads realigned in them), %lld computed per read\n",
             g_records, g_hits, g_batches, g_prefetched, g_direct);
+    fprintf(stderr, "libindelgpu: inline mode: %lld per-variant region fetches served from the retained records, %lld from the BAM\n",
+            g_cov_served, g_cov_fallback);
     if (getenv("INDELGPU_VERBOSE"))
         fprintf(stderr, "libindelgpu: inline mode: prefetch thread %.2f s reading + classifying, %.2f s in indelgpu_realign_batch, %.2f s waiting for "
                         "fetch_func; main thread %.2f s in fetch_func, %.2f s waiting for the prefetch thread\n",
@@ -194,15 +205,17 @@ static void fill_block(pf_block* k, const producer_arg* pa, int serial)
         k->cand = ckrealloc(k->cand, sizeof(int32_t) * (size_t)want);
         k->caprec = want;
     }
-    if (k->batch == NULL) {
+    if (g_batch[serial & 1] == NULL) {
         /* candidates are a small share of the records; a batch that fills up just leaves the rest of the
          * block to the per-read path */
         const int cap = block_records(1 << 20) / 4 + 256;
-        k->batch = igb_create(cap, (int64_t)cap * 256);
-        if (k->batch == NULL) fatalf("libindelgpu: inline mode: cannot allocate the pinned batch (%s)", indelgpu_last_error());
+        g_batch[serial & 1] = igb_create(cap, (int64_t)cap * 256);
+        if (g_batch[serial & 1] == NULL) fatalf("libindelgpu: inline mode: cannot allocate the pinned batch (%s)", indelgpu_last_error());
     }
+    k->batch = g_batch[serial & 1];
     igb_clear(k->batch);
-    k->nrec = 0; k->answered = 0; k->last = 0; k->ret = 0;
+    k->nrec = 0; k->answered = 0; k->last = 0; k->ret = 0; k->serial = serial;
+    int32_t maxspan = serial > 0 ? g_blk[(serial - 1) % NBLK].maxspan : 1;
     int32_t dtid = 0;
     pthread_mutex_lock(&indelgpu_glue_gpu_mu);
     indelgpu_ctx* ctx = indelgpu_glue_ctx_peek(pa->tid, &dtid);
@@ -213,6 +226,7 @@ static void fill_block(pf_block* k, const producer_arg* pa, int serial)
         bam1_t* b = &k->recs[k->nrec];
         const int ret = bam_iter_read(pa->fp, pa->iter, b);
         if (ret < 0) { k->last = 1; k->ret = ret; break; }
+        if (b->core.n_cigar) { const int32_t span = (int32_t)bam_calend(&b->core, bam1_cigar(b)) - b->core.pos; if (span > maxspan) maxspan = span; }
         int32_t slot = -1;
         if (ctx != NULL && b->core.mtid == pa->tid) {
             const int len = foresee_call(b, read, (int)sizeof(read));
@@ -223,6 +237,7 @@ static void fill_block(pf_block* k, const producer_arg* pa, int serial)
         }
         k->cand[k->nrec++] = slot;
     }
+    k->maxspan = maxspan;
     const double t_r1 = now_s();
     g_t_read += t_r1 - t_r0;
     if (k->batch->n > 0) {
@@ -242,10 +257,10 @@ static void* producer_main(void* arg)
 {
     const producer_arg* pa = arg;
     for (int serial = 0;; serial++) {
-        pf_block* k = &g_blk[serial & 1];
+        pf_block* k = &g_blk[serial % NBLK];
         const double t_w0 = now_s();
         pthread_mutex_lock(&g_mu);
-        while (k->full) pthread_cond_wait(&g_cv, &g_mu);
+        while (serial > g_consumed + 1) pthread_cond_wait(&g_cv, &g_mu);      /* at most one block ahead of fetch_func */
         /* Until a call has taught this file the contig's context and a read group's range nothing can be
          * prefetched: do not run ahead of fetch_func then, or the blocks filled in the meantime are all misses */
         while (g_consumed < serial) {
@@ -266,7 +281,7 @@ static void* producer_main(void* arg)
         fill_block(k, pa, serial);
         const int last = k->last;
         pthread_mutex_lock(&g_mu);
-        k->full = 1;
+        g_produced = serial + 1;
         pthread_cond_broadcast(&g_cv);
         pthread_mutex_unlock(&g_mu);
         if (last) break;
@@ -288,31 +303,31 @@ int indelgpu_bam_fetch(bamFile fp, const bam_index_t* idx, int tid, int beg, int
     producer_arg pa;
     pa.fp = fp; pa.tid = tid;
     pa.iter = bam_iter_query(idx, tid, beg, end);
-    g_blk[0].full = g_blk[1].full = 0;
-    g_consumed = 0;
+    g_consumed = 0; g_produced = 0; g_last_serial = -1;
+    g_fetch_tid = tid; g_fetch_beg = beg; g_fetch_end = end;
     pthread_t thr;
     if (pthread_create(&thr, NULL, producer_main, &pa) != 0) fatalf("libindelgpu: inline mode: cannot start the prefetching thread");
     int ret = 0;
     for (int serial = 0;; serial++) {
-        pf_block* k = &g_blk[serial & 1];
+        pf_block* k = &g_blk[serial % NBLK];
         const double t_c0 = now_s();
         pthread_mutex_lock(&g_mu);
-        while (!k->full) pthread_cond_wait(&g_cv, &g_mu);
+        while (g_produced <= serial) pthread_cond_wait(&g_cv, &g_mu);
         pthread_mutex_unlock(&g_mu);
         const double t_c1 = now_s();
         g_t_cons_wait += t_c1 - t_c0;
-        g_cur_blk = k;
+        g_cur_blk = k; g_cur_serial = serial;
         for (int i = 0; i < k->nrec; i++) {
             g_cur_idx = i;
             func(&k->recs[i], data);                                        /* bam_index.c:722 */
         }
         g_records += k->nrec;
         g_t_func += now_s() - t_c1;
-        g_cur_blk = NULL; g_cur_idx = -1;
+        g_cur_blk = NULL; g_cur_idx = -1; g_cur_serial = -1;
         const int last = k->last;
+        if (last) g_last_serial = serial;
         ret = k->ret;
         pthread_mutex_lock(&g_mu);
-        k->full = 0;
         g_consumed = serial + 1;
         pthread_cond_broadcast(&g_cv);
         pthread_mutex_unlock(&g_mu);
@@ -322,6 +337,43 @@ int indelgpu_bam_fetch(bamFile fp, const bam_index_t* idx, int tid, int beg, int
     bam_iter_destroy(pa.iter);
     g_in_fetch = 0;
     return ret == -1 ? 0 : ret;                                            /* bam_index.c:725 */
+}
+
+/* Row f3, second half.  calculate_cov_params (shared.c:178-212, compiled with -Dbam_fetch=indelgpu_bam_fetch_cov) fetches
+ * the region of every printed variant: samtools starts at the linear-index offset of the region's 16 kb window and parses
+ * ~1 500 records to find the ~50 that overlap -- 3.7 times the whole file over a 30x run, all on the main thread.  Those
+ * records went through this file a moment ago: the consumer's block and the three before it are still in memory, in file
+ * order.  A fetch whose region they cover completely is answered from them with bam_iter_read's own test
+ * (bam_index.c:642-655, :695-701: same contig, pos < end, end of the alignment > beg) in the same order; anything else
+ * goes to samtools. */
+int indelgpu_bam_fetch_cov(bamFile fp, const bam_index_t* idx, int tid, int beg, int end, void* data, bam_fetch_f func)
+{
+    if (beg < 0) beg = 0;                                                   /* bam_iter_query, bam_index.c:604 */
+    const int c = g_cur_serial >= 0 ? g_cur_serial : g_last_serial;        /* the variants left at the end of a contig are printed after its fetch */
+    if (c < 0 || tid != g_fetch_tid || end <= beg || beg < g_fetch_beg || end > g_fetch_end ||
+        getenv("INDELGPU_NO_BAM_CACHE") != NULL) { g_cov_fallback++; return bam_fetch(fp, idx, tid, beg, end, data, func); }
+    const int lo = c - KEEP > 0 ? c - KEEP : 0;
+    const pf_block* kc = &g_blk[c % NBLK];
+    const pf_block* k0 = &g_blk[lo % NBLK];
+    /* nothing that overlaps the region may lie before the first kept record or after the last one */
+    const int before_ok = lo == 0 || (k0->nrec > 0 && (int64_t)k0->recs[0].core.pos + kc->maxspan <= beg);
+    const int after_ok = kc->last || (kc->nrec > 0 && kc->recs[kc->nrec - 1].core.pos >= end);
+    if (!before_ok || !after_ok) { g_cov_fallback++; return bam_fetch(fp, idx, tid, beg, end, data, func); }
+    const int64_t from = (int64_t)beg - kc->maxspan;                        /* records that start before this cannot reach beg */
+    for (int sidx = lo; sidx <= c; sidx++) {
+        const pf_block* k = &g_blk[sidx % NBLK];
+        if (k->nrec == 0 || k->recs[k->nrec - 1].core.pos < from) continue;
+        int a = 0, z = k->nrec;                                             /* first record with pos >= from */
+        while (a < z) { const int m = (a + z) >> 1; if (k->recs[m].core.pos < from) a = m + 1; else z = m; }
+        for (int i = a; i < k->nrec; i++) {
+            const bam1_t* b = &k->recs[i];
+            if (b->core.pos >= end) { g_cov_served++; return 0; }
+            const uint32_t rend = b->core.n_cigar ? bam_calend(&b->core, bam1_cigar(b)) : (uint32_t)b->core.pos + 1;
+            if (rend > (uint32_t)beg) func(b, data);
+        }
+    }
+    g_cov_served++;
+    return 0;
 }
 
 int indelgpu_inline_lookup(int32_t tid, int32_t position, int32_t range1, const char* read, int32_t readlen,

@@ -51,6 +51,9 @@ def test_inline_mode_vcf_identical_on_test_data(args, golden, block):
     assert hits + direct == 697                  # every attempt_pe_alignment call of the reference's own run (golden trace)
     assert hits > 400 and batches >= 1
     assert prefetched == hits                    # the producer foresaw exactly the calls that were made: no wasted GPU work
+    # row f3: calculate_cov_params' per-variant region fetches are answered from the records still in memory
+    m = re.search(r"(\d+) per-variant region fetches served from the retained records, (\d+) from the BAM", err)
+    assert m and int(m.group(1)) == 14 and int(m.group(2)) == 0
 
 
 @pytest.fixture(scope="module")
