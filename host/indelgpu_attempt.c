@@ -538,9 +538,15 @@ evidence* attempt_pe_alignment(char** const sequences,
     memset(&out, 0, sizeof(out));
     out.status = &status; out.nseg = &nseg; out.rstart = &rstart; out.seg_off = &segoff;
     out.segs = g_segs; out.seg_capacity = g_segcap;
+    static int first_call = 1;
+    const double t0 = first_call ? now_ms() : 0;
     pthread_mutex_lock(&indelgpu_glue_gpu_mu);
     const int rc = indelgpu_realign_batch(ctx, &in, &out);
     pthread_mutex_unlock(&indelgpu_glue_gpu_mu);
     if (rc != 0) gpu_die("indelgpu_realign_batch");
+    if (first_call) {
+        first_call = 0;
+        if (getenv("INDELGPU_VERBOSE")) fprintf(stderr, "libindelgpu: the first per-read call took %.0f ms\n", now_ms() - t0);
+    }
     return consume_segments(rln, read, nseg, rstart, g_segs + segoff);
 }

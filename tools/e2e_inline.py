@@ -72,16 +72,14 @@ def vcf_wall_time(length=4_000_000, depth=30, modes=("inline",), reference=True,
             res["reference_threads"] = 1
             res["records"] = sum(1 for ln in ref_vcf.splitlines() if not ln.startswith("#"))
         for k, mode in enumerate(modes):
-            vcf, t, err = run_program("indelminer_gpu", d, args, dict(INDELGPU_MODE=mode))
+            vcf, t, err = run_program("indelminer_gpu", d, args, dict(INDELGPU_MODE=mode, INDELGPU_VERBOSE="1"))
             key = "gpu_s" if k == 0 else f"gpu_{mode}_s"
             res[key] = round(t, 3)
             if k == 0:
                 res["gpu_mode"] = f"INDELGPU_MODE={mode}"
                 res["records"] = sum(1 for ln in vcf.splitlines() if not ln.startswith("#"))
                 res["vcf_md5"] = hashlib.md5(vcf.encode()).hexdigest()
-                for ln in err.splitlines():
-                    if "inline mode:" in ln and "BAM records" in ln:
-                        res["gpu_log"] = ln.strip()
+                res["gpu_log"] = [ln.strip() for ln in err.splitlines() if ln.startswith("libindelgpu:")]
             if ref_vcf is not None:
                 res["identical" if k == 0 else f"identical_{mode}"] = (vcf == ref_vcf)
         return res
