@@ -18,6 +18,8 @@
  *
  *   synth_bam PREFIX --contigs N --length L [--lengths l1,l2,...] --depth D --readlen M --insert MEAN,SD
  *             --spacing S --maxindel K --subrate R --seed X [--keep F] [--readseed Y] [--level Z] [--rg N]
+ * --bigdel K (default 0) turns K of every contig's sites into 1.5-3 kb deletions; pairs that span one come out with an
+ * insert beyond the proper range and are flagged improper (0x2 clear): the reference's paired-end evidence path.
  * --rg N (default 0 = no RG tag) deals the pairs to N read groups rg0 .. rgN-1 (RG:Z tag, @RG header lines) and gives
  * every group its own IL line in the config (the maximum grows by 10 per group): exercises the per-read-group range.
  * writes PREFIX.fa, PREFIX.bam, PREFIX.bam.bai, PREFIX.config and prints one JSON line of counts.
@@ -152,6 +154,7 @@ static int key_cmp(const void* x, const void* y)
 static int op_code(char c) { return c == 'M' ? BAM_CMATCH : c == 'I' ? BAM_CINS : c == 'D' ? BAM_CDEL : BAM_CSOFT_CLIP; }
 
 static int g_nrg = 0;
+static int g_proper_max = 0;           /* > 0: pairs with a longer template are flagged improper (--bigdel) */
 
 static void write_record(bamFile out, int tid, uint64_t pair, const end_t* e, const end_t* mate, int is_first, int M)
 {
@@ -164,7 +167,6 @@ static void write_record(bamFile out, int tid, uint64_t pair, const end_t* e, co
     if (mate->rev) flag |= 0x20;
     if (e->unmapped) flag |= 0x4;
     if (mate->unmapped) flag |= 0x8;
-    if (!e->unmapped && !mate->unmapped) flag |= 0x2;
     const int64_t pos = e->unmapped ? mate->pos0 : e->pos0;
     const int64_t pnext = mate->unmapped ? pos : mate->pos0;
     int64_t tlen = 0, end = pos + 1;
@@ -173,6 +175,7 @@ static void write_record(bamFile out, int tid, uint64_t pair, const end_t* e, co
         const int64_t ee = ref_end(e), me = ref_end(mate);
         const int64_t lo = e->pos0 < mate->pos0 ? e->pos0 : mate->pos0, hi = ee > me ? ee : me;
         tlen = e->pos0 <= mate->pos0 ? hi - lo : -(hi - lo);
+        if (g_proper_max <= 0 || hi - lo <= g_proper_max) flag |= 0x2;
     }
     uint8_t* p = data;
     memcpy(p, name, (size_t)lq); p += lq;
@@ -201,7 +204,7 @@ int main(int argc, char** argv)
     const char* prefix = argv[1];
     int ncontigs = 1; int64_t length = 1000000; const char* lengths = NULL;
     double depth = 20; int M = 150, imean = 500, isd = 50, spacing = 2000, maxindel = 50, level = 1;
-    double subrate = 0.01, keep = 1.0; uint64_t seed = 7, readseed = 0; int have_readseed = 0;
+    double subrate = 0.01, keep = 1.0; uint64_t seed = 7, readseed = 0; int have_readseed = 0; int bigdel = 0;
     for (int i = 2; i + 1 < argc; i += 2) {
         const char* o = argv[i]; const char* v = argv[i + 1];
         if (!strcmp(o, "--contigs")) ncontigs = atoi(v);
@@ -218,9 +221,11 @@ int main(int argc, char** argv)
         else if (!strcmp(o, "--readseed")) { readseed = strtoull(v, NULL, 10); have_readseed = 1; }
         else if (!strcmp(o, "--level")) level = atoi(v);
         else if (!strcmp(o, "--rg")) g_nrg = atoi(v);
+        else if (!strcmp(o, "--bigdel")) bigdel = atoi(v);
         else { fprintf(stderr, "synth_bam: unknown option %s\n", o); return 2; }
     }
     if (M > 1000 || M < 20 || ncontigs < 1 || ncontigs > 512) return 2;
+    if (bigdel > 0) g_proper_max = imean + 4 * isd;
     int64_t* clen = calloc((size_t)ncontigs, sizeof(int64_t));
     for (int c = 0; c < ncontigs; c++) clen[c] = length;
     if (lengths) { const char* p = lengths; for (int c = 0; c < ncontigs && p; c++) { clen[c] = atoll(p); p = strchr(p, ','); if (p) p++; } }
@@ -283,13 +288,18 @@ int main(int argc, char** argv)
             sites[i].ins_off = instotal; instotal += sites[i].len;
             sites[i].keep = rnd_below(&rk, 1000000u) < (uint32_t)(keep * 1e6 + 0.5);
         }
+        if (bigdel > 0 && nsites > 2 * bigdel) {                        /* its own draws: the default data set does not change */
+            rng_t rb; rb.s = mix64(seed ^ (0xB16DE100ULL + (uint64_t)c));
+            const int64_t every = nsites / bigdel;
+            for (int64_t i = every / 2; i < nsites; i += every) { sites[i].isdel = 1; sites[i].len = 1500 + (int)rnd_below(&rb, 1500); }
+        }
         char* insbases = malloc((size_t)instotal + 1);
         for (int64_t i = 0; i < instotal; i++) insbases[i] = ACGT[rnd_below(&rs, 4)];
         g.samp = malloc((size_t)L + (size_t)instotal + 16);
         g.rcmap = malloc(sizeof(int32_t) * ((size_t)L + (size_t)instotal + 16));
         int64_t S = 0, prev = 0;
         for (int64_t i = 0; i < nsites; i++) {
-            if (!sites[i].keep) continue;
+            if (!sites[i].keep || sites[i].pos < prev) continue;           /* a site inside a big deletion is gone */
             for (int64_t p = prev; p < sites[i].pos; p++) { g.samp[S] = g.ref[p]; g.rcmap[S++] = (int32_t)p; }
             if (sites[i].isdel) { prev = sites[i].pos + sites[i].len; ndel++; }
             else { for (int t = 0; t < sites[i].len; t++) { g.samp[S] = insbases[sites[i].ins_off + t]; g.rcmap[S++] = -1; } prev = sites[i].pos; nins++; }

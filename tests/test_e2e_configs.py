@@ -199,7 +199,7 @@ def test_cfg5_reference_3_1_gb(gpu, oracle):
 
 def test_cfg5_full_reference_size_end_to_end(tmp_path):
     """config 5 at its named REFERENCE size through the whole program: 24 contigs with the lengths of GRCh38 chr1..22, X, Y
-    (3.1 Gb; 248 Mb contigs), one process over all of them, `-e 1`, at 0.2x coverage -- the depth at which the unmodified
+    (3.1 Gb; 248 Mb contigs), one process over all of them, `-e 1`, at 0.05x coverage -- the depth at which the unmodified
     reference (an hour for this data set: ~20 ms of strlen per candidate read on a 248 Mb contig) could be run once in the
     build container (tools/cfg5_full_reference_run.sh).  Every contig is uploaded when its first read arrives."""
     g = need("cfg5_full_reference.json", "indelminer_gpu", "synth_bam")
@@ -210,7 +210,7 @@ def test_cfg5_full_reference_size_end_to_end(tmp_path):
     assert md5(os.path.join(d, "g.bam")) == g["bam_md5"]
     t, log = run_to_file("indelminer_gpu", ["-e", "1", "-i", "g.config", "g.fa", "s=g.bam"], d, "all.vcf", dict(INDELGPU_VERBOSE="1"))
     assert md5(os.path.join(d, "all.vcf")) == g["vcf_md5"]
-    note("r02_cfg5_full_reference_size.json", dict(config="cfg5 reference size: 3.1 Gb in 24 contigs, 0.2x, -e 1, one process", identical_md5=True,
+    note("r02_cfg5_full_reference_size.json", dict(config="cfg5 reference size: 3.1 Gb in 24 contigs, 0.05x, -e 1, one process", identical_md5=True,
                                                     bam_records=g["generated"]["records"], vcf_records=g["records"], generate_s=round(t_gen, 1),
                                                     gpu_wall_s=round(t, 1), reference_wall_s=g["reference_seconds"],
                                                     gpu_log=[ln for ln in log.splitlines() if "inline mode" in ln]))

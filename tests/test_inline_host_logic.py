@@ -136,3 +136,24 @@ def test_inline_mode_learns_the_range_of_every_read_group(tmp_path):
     m = re.search(r"(\d+) calls answered from (\d+) prefetched batches \((\d+) reads realigned in them\), (\d+) computed per read", err)
     hits, _b, prefetched, direct = map(int, m.groups())
     assert hits > 10 * direct and prefetched == hits
+
+
+def test_paired_end_evidence_and_the_indexed_graph(tmp_path):
+    """1.5-3 kb deletions: pairs spanning them are flagged improper and become PAIRED_READ evidence (indelminer.c:516-612),
+    the reads crossing them go through attempt_pe_alignment.  Exercises the indexed add_node (host/indelgpu_graph.c, row f4)
+    on both kinds of node, the mate look-up's nested bam_fetch, and per-variant fetches wider than a read.  The VCF must
+    equal the unmodified reference's with the index on and off."""
+    need("indelminer_ref", "indelminer_fakegpu", "synth_bam")
+    d = str(tmp_path)
+    subprocess.check_call([os.path.join(REFDIR, "synth_bam"), "pe", "--length", "600000", "--depth", "25", "--seed", "13", "--bigdel", "12"],
+                          cwd=d, stdout=subprocess.DEVNULL)
+    want, _ = run("indelminer_ref", ["-i", "pe.config", "pe.fa", "s=pe.bam"], d)
+    assert sum("PAIRED_READ" in ln for ln in want.splitlines() if not ln.startswith("#")) >= 4
+    for env in (dict(INDELGPU_MODE="inline"), dict(INDELGPU_MODE="inline", INDELGPU_NO_GRAPH_INDEX="1"), dict(INDELGPU_NO_GRAPH_INDEX="1"), {}):
+        out, _ = run("indelminer_fakegpu", ["-i", "pe.config", "pe.fa", "s=pe.bam"], d, env)
+        assert out == want, env
+    # region runs: the mate of an improper pair may lie outside the region (find_mate_rln, indelminer.c:255-280)
+    for reg in ("chr1:1-300000", "chr1:300001-600000"):
+        want_r, _ = run("indelminer_ref", ["-i", "pe.config", "-c", reg, "pe.fa", "s=pe.bam"], d)
+        out_r, _ = run("indelminer_fakegpu", ["-i", "pe.config", "-c", reg, "pe.fa", "s=pe.bam"], d, dict(INDELGPU_MODE="inline"))
+        assert out_r == want_r, reg

@@ -1,13 +1,13 @@
 #!/bin/sh
 # TEST INFRASTRUCTURE.  BASELINE config 5 at its named REFERENCE size, end to end: 24 contigs with the lengths of
-# GRCh38 chr1..22, X, Y (3.1 Gb), 2x150 bp pairs with planted indels -- at 0.2x coverage instead of 30x, because the
+# GRCh38 chr1..22, X, Y (3.1 Gb), 2x150 bp pairs with planted indels -- at 0.05x coverage instead of 30x, because the
 # unmodified reference spends ~20 ms per candidate read in strlen() of a 248 Mb contig (alignment.c:771): the
-# ~0.25 M calls of this data set already cost it about an hour, 30x would cost it a week.  `-e 1` (minimum support 1)
+# ~80 k calls of this data set already cost it about an hour, 30x would cost it a week.  `-e 1` (minimum support 1)
 # so that the thin coverage still yields thousands of calls.  Writes tests/golden/cfg5_full_reference.json.
 #   tools/cfg5_full_reference_run.sh [WORKDIR] [DEPTH] [OUT.json]
 set -e
 HERE=$(cd "$(dirname "$0")/.." && pwd)
-W=${1:-/tmp/cfg5full}; DEPTH=${2:-0.2}; OUT=${3:-$HERE/tests/golden/cfg5_full_reference.json}
+W=${1:-/tmp/cfg5full}; DEPTH=${2:-0.05}; OUT=${3:-$HERE/tests/golden/cfg5_full_reference.json}
 G=$HERE/oracle/_ref
 mkdir -p "$W"; cd "$W"
 LENS=$(python3 -c "
