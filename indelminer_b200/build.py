@@ -7,7 +7,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libindelgpu.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["kernels.cuh", "band_dp.cuh", "warp_vote.cuh", "realign_kernel.cuh", "realign_pipeline.cuh", "task_kernels.cuh", "indel_support.cuh",
+HEADERS = ["kernels.cuh", "band_dp.cuh", "warp_vote.cuh", "realign_kernel.cuh", "realign_pipeline.cuh", "task_kernels.cuh", "indel_support.cuh", "indel_support_pack.cuh",
            os.path.join("..", "..", "include", "indelgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

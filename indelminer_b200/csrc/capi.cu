@@ -20,6 +20,7 @@
 #include "realign_pipeline.cuh"
 #include "task_kernels.cuh"
 #include "indel_support.cuh"
+#include "indel_support_pack.cuh"
 
 using namespace indelgpu;
 
@@ -108,6 +109,9 @@ struct indelgpu_ctx {
     DevBuf counters;         // bytes: 0 work counter (int) | 8 seg count (u64) | 16 cells (3 x u64) | 40 error flag (int) | 48 algorithmic bytes (u64) | 56 ALIGN cells not swept (u64, band tasks)
     DevBuf scratch;
     DevBuf s_tgt, s_toff, s_qry, s_qoff, s_out, s_ord, s_idx, s_V, s_I, s_F;
+    // the two-pass support check (indel_support_pack.cuh): scratch of up to three launches in flight -- the walk back of
+    // one runs (on st_out) beside the wavefront pass of the next
+    struct PackSlot { DevBuf dirs, cpl, best; cudaEvent_t packed = nullptr, walked = nullptr; bool busy = false; } pk[3];
     int32_t* h_order = nullptr; size_t h_order_cap = 0;            // pinned work list of the support check   // known-indel support check (indel_support.cuh)
     DevBuf p_low, p_aln, p_cig, p_plan, p_flags;      // intermediates of the banded pipeline (realign_pipeline.cuh)
     // task API staging
@@ -187,10 +191,11 @@ extern "C" void indelgpu_destroy(indelgpu_ctx* c)
                      &c->in_pos, &c->in_rng, &c->out_status, &c->out_nseg, &c->out_rstart, &c->out_segoff,
                      &c->out_segs, &c->out_detail, &c->out_cig1, &c->out_cig2, &c->counters, &c->chunk_counts, &c->scratch,
                      &c->p_low, &c->p_aln, &c->p_cig, &c->p_plan, &c->p_flags,
-                     &c->s_tgt, &c->s_toff, &c->s_qry, &c->s_qoff, &c->s_out, &c->s_ord, &c->s_idx, &c->s_V, &c->s_I, &c->s_F,
+                     &c->s_tgt, &c->s_toff, &c->s_qry, &c->s_qoff, &c->s_out, &c->s_ord, &c->s_idx, &c->s_V, &c->s_I, &c->s_F, &c->pk[0].dirs, &c->pk[0].cpl, &c->pk[0].best, &c->pk[1].dirs, &c->pk[1].cpl, &c->pk[1].best, &c->pk[2].dirs, &c->pk[2].cpl, &c->pk[2].best,
                      &c->t_reads, &c->t_roff, &c->t_refs, &c->t_woff, &c->t_packed, &c->t_anchor, &c->t_low,
                      &c->t_up, &c->t_score, &c->t_ends, &c->t_ncig, &c->t_cig, &c->t_script};
     for (DevBuf* b : all) b->release();
+    for (auto& k : c->pk) { if (k.packed) cudaEventDestroy(k.packed); if (k.walked) cudaEventDestroy(k.walked); }
     if (c->pinned_small) cudaFreeHost(c->pinned_small);
     delete c;
 }
@@ -1054,12 +1059,17 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
     CU(cudaMemcpyAsync(c->s_toff.p, h_target_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->s_qoff.p, h_query_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(c->counters.p, 0, 64, st));
-    // pairs the wavefront kernel's packing holds go there (all real reads), in three classes by target length
-    // (8, 16 or 32 lanes per pair) and sorted by that length inside a class; the rest, one pair per thread
+    // Six work lists for the two wavefront kernels, each sorted by target length (counting sort): three classes by
+    // target length (8, 16 or 32 lanes per pair) x query short enough for the 16-bit two-pass kernel
+    // (indel_support_pack.cuh: every short read) or not (indel_support.cuh); the rest, one pair per thread.
+    static const bool no_pack = getenv("INDELGPU_SUPPORT_NOPACK") != nullptr;        // A/B measurements only
+    const int pack_max_query = no_pack ? -1 : (int)kPackMaxQuery;
     std::vector<int32_t> slow;
     int max1 = 0, max2 = 0;
     long long cells = 0;
-    std::vector<int32_t> bucket(kWaveMaxTarget + 2, 0);
+    const int NB = kWaveMaxTarget + 1;                             // bucket = (wave ? NB : 0) + target length
+    std::vector<int32_t> bucket(2 * NB + 1, 0);
+    int pack_max2[3] = {0, 0, 0};                                  // longest query per packed class: sizes its shared memory
     for (int i = 0; i < n; i++) {
         const int64_t l1 = h_target_off[i + 1] - h_target_off[i], l2 = h_query_off[i + 1] - h_query_off[i];
         if (l1 < 0 || l2 < 0 || l1 > 8000 || l2 > 8000) {
@@ -1068,11 +1078,13 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
         }
         cells += l1 * l2;
         if (l1 > kWaveMaxTarget || l2 > kWaveMaxQuery) { slow.push_back(i); max1 = std::max(max1, (int)l1); max2 = std::max(max2, (int)l2); }
-        else bucket[l1 + 1]++;
+        else if (l2 <= pack_max_query) { bucket[l1 + 1]++; int& m = pack_max2[l1 <= 128 ? 0 : l1 <= 256 ? 1 : 2]; m = std::max(m, (int)l2); }
+        else bucket[NB + l1 + 1]++;
     }
     const int nslow = (int)slow.size(), nfast = n - nslow;
-    for (int l = 0; l <= kWaveMaxTarget; l++) bucket[l + 1] += bucket[l];                 // counting sort by target length
-    const int class_end[3] = {bucket[128 + 1], bucket[256 + 1], bucket[kWaveMaxTarget + 1]};   // <= 128 | <= 256 | <= 512 bases
+    for (int l = 0; l < 2 * NB; l++) bucket[l + 1] += bucket[l];
+    // list boundaries: packed <= 128 | <= 256 | <= 512 | wave <= 128 | <= 256 | <= 512
+    const int list_end[6] = {bucket[128 + 1], bucket[256 + 1], bucket[NB], bucket[NB + 128 + 1], bucket[NB + 256 + 1], bucket[2 * NB]};
     if (c->h_order_cap < (size_t)std::max(nfast, 1)) {           // pinned: the copy below must not wait for a staging pass
         if (c->h_order) cudaFreeHost(c->h_order);
         c->h_order = nullptr; c->h_order_cap = 0;
@@ -1084,7 +1096,7 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
         std::vector<int32_t> at(bucket.begin(), bucket.end() - 1);
         for (int i = 0; i < n; i++) {
             const int64_t l1 = h_target_off[i + 1] - h_target_off[i], l2 = h_query_off[i + 1] - h_query_off[i];
-            if (l1 <= kWaveMaxTarget && l2 <= kWaveMaxQuery) order[at[l1]++] = i;
+            if (l1 <= kWaveMaxTarget && l2 <= kWaveMaxQuery) order[at[(l2 <= pack_max_query ? 0 : NB) + l1]++] = i;
         }
     }
     if (nfast > 0) CU(cudaMemcpyAsync(c->s_ord.p, order, 4 * (size_t)nfast, cudaMemcpyHostToDevice, st));
@@ -1092,8 +1104,62 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
     int32_t* d_indels = d_subs + n;
     int32_t* d_aligned = d_indels + n;
     CU(cudaEventRecord(c->ev_t0, st));
+    // the 16-bit two-pass kernels: a wavefront pass that leaves two direction bits per cell in a scratch buffer, then
+    // the walk back with one thread per pair.  A class is cut into launches whose scratch stays under ~2 GB.
+    static const int pack_shape = getenv("INDELGPU_PACK_SHAPE") ? atoi(getenv("INDELGPU_PACK_SHAPE")) : 1;   // experiments
+    int pack_launch = 0;
     for (int cls = 0; cls < 3; cls++) {
-        const int first = cls ? class_end[cls - 1] : 0, cnt = class_end[cls] - first;
+        const int cfirst = cls ? list_end[cls - 1] : 0, ccnt = list_end[cls] - cfirst;
+        if (ccnt <= 0) continue;
+        // lanes per pair and columns per lane: <= 128 | <= 256 | <= 512 target bases
+        int seg = cls == 0 ? 16 : 32, maxcpl = cls == 2 ? 16 : 8;
+        if (pack_shape == 1) { seg = cls == 0 ? 8 : cls == 1 ? 16 : 32; maxcpl = 16; }
+        const int steps_cap = pack_max2[cls] + seg - 1;
+        const int per_pass = 2 * (32 / seg);
+        const size_t pass_bytes = pack_dirs_bytes(per_pass, seg, maxcpl, steps_cap);
+        const long long max_pairs = std::max<long long>(per_pass, (long long)((2ull << 30) / pass_bytes) * per_pass);
+        for (long long done = 0; done < ccnt; done += max_pairs) {
+            const int cnt = (int)std::min<long long>(max_pairs, ccnt - done);
+            const long long npass = ((long long)cnt + per_pass - 1) / per_pass;
+            indelgpu_ctx::PackSlot& k = c->pk[pack_launch++ % 3];
+            if (!k.packed) { CU(cudaEventCreateWithFlags(&k.packed, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&k.walked, cudaEventDisableTiming)); }
+            if (k.busy) { CU(cudaStreamWaitEvent(st, k.walked, 0)); k.busy = false; }           // the slot's previous walk has read its scratch
+            if (k.dirs.ensure(pack_dirs_bytes(cnt, seg, maxcpl, steps_cap)) || k.cpl.ensure(4 * (size_t)npass) || k.best.ensure(4 * (size_t)cnt)) {
+                cudaStreamSynchronize(st); cudaStreamSynchronize(c->st_out); return INDELGPU_ENOMEM;
+            }
+            PackArgs w;
+            w.n = cnt;
+            w.order = c->s_ord.as<int32_t>() + cfirst + done;
+            w.targets = c->s_tgt.as<uint8_t>(); w.target_off = c->s_toff.as<int64_t>();
+            w.queries = c->s_qry.as<uint8_t>(); w.query_off = c->s_qoff.as<int64_t>();
+            w.subs = d_subs; w.indels = d_indels; w.aligned = d_aligned;
+            w.dirs = k.dirs.as<uint32_t>(); w.pass_cpl = k.cpl.as<int32_t>(); w.best = k.best.as<uint32_t>();
+            w.steps_cap = steps_cap; w.seg = seg; w.maxcpl = maxcpl; w.one = 1u;
+            w.error_flag = ctr_err(c);
+            int occ = 0;
+#define PACK_LAUNCH(S, M) { CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, indel_support_pack_kernel<S, M>, 128, 0)); \
+                            if (occ >= 1) indel_support_pack_kernel<S, M><<<(int)std::min<long long>((long long)c->sms * occ, (npass + 3) / 4), 128, 0, st>>>(w); }
+            if (seg == 8) PACK_LAUNCH(8, 16)
+            else if (seg == 16 && maxcpl == 8) PACK_LAUNCH(16, 8)
+            else if (seg == 16) PACK_LAUNCH(16, 16)
+            else if (maxcpl == 8) PACK_LAUNCH(32, 8)
+            else PACK_LAUNCH(32, 16)
+#undef PACK_LAUNCH
+            if (occ < 1) { cudaStreamSynchronize(st); cudaStreamSynchronize(c->st_out); return fail(INDELGPU_ELIMIT, "support kernel does not fit on an SM"); }
+            c->launches++;
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(k.packed, st));
+            CU(cudaStreamWaitEvent(c->st_out, k.packed, 0));
+            indel_support_walk_kernel<<<(cnt + 127) / 128, 128, 0, c->st_out>>>(w);
+            c->launches++;
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(k.walked, c->st_out));
+            k.busy = true;
+        }
+    }
+    for (auto& k : c->pk) if (k.busy) { CU(cudaStreamWaitEvent(st, k.walked, 0)); k.busy = false; }
+    for (int cls = 0; cls < 3; cls++) {                            // queries too long for it: the carried-counter wavefront
+        const int first = list_end[2 + cls], cnt = list_end[3 + cls] - first;
         if (cnt <= 0) continue;
         WaveArgs w;
         w.n = cnt;

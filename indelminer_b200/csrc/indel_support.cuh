@@ -44,7 +44,7 @@ struct SupportArgs {
     int* error_flag;
 };
 
-__device__ __forceinline__ int up_case(int c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
+__host__ __device__ __forceinline__ int up_case(int c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
 
 __global__ void __launch_bounds__(128)
 indel_support_kernel(const __grid_constant__ SupportArgs a)

@@ -47,3 +47,73 @@ extern "C" int hh_band_align_interleaved(const int* prm, const uint8_t* read, in
     for (size_t i = 0; i < scratch.size(); i++) if ((int)(i & 31) != lane && scratch[i] != 0x5A5A5A5A) return -2;
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// the 16-bit two-pass support check (indel_support_pack.cuh): one segment of SEG lanes emulated in lockstep,
+// shuffles replaced by array reads, the per-lane row step and the walk back being the device source itself
+// ---------------------------------------------------------------------------------------------------
+#include "../../indelminer_b200/csrc/indel_support_pack.cuh"
+
+template <int CPL>
+static void hh_pack_run(int SEG, const uint8_t* t1a, int len1a, const uint8_t* t2a, int len2a,
+                        const uint8_t* t1b, int len1b, const uint8_t* t2b, int len2b, int* out6)
+{
+    std::vector<PackLane<CPL>> L((size_t)SEG);
+    for (int li = 0; li < SEG; li++) L[li].init(t1a, len1a, t1b, len1b, li * CPL);
+    const int len1 = std::max(len1a, len1b), len2 = std::max(len2a, len2b);
+    const int nl = (len1 + CPL - 1) / CPL;
+    const int steps = (len1 > 0 && len2 > 0) ? len2 + nl - 1 : 0;
+    const int steps_pad = (steps + 8) & ~7;
+    const size_t plane = (size_t)steps_pad * 32;
+    std::vector<uint32_t> dirs(plane * 3, 0xDEADBEEFu);
+    std::vector<unsigned> qcur((size_t)SEG, 0), qprev((size_t)SEG, 0), give((size_t)SEG), ov((size_t)SEG), oe((size_t)SEG);
+    for (int s = 0; s < steps; s++) {
+        const int sl = s & (SEG - 1);
+        for (int li = 0; li < SEG; li++) {
+            if (sl == 0) {
+                const int r = s + li;
+                const unsigned qa = r < len2a ? (unsigned)up_case(t2a[r]) << 4 : (unsigned)kPkPastQuery;
+                const unsigned qb = r < len2b ? (unsigned)up_case(t2b[r]) << 4 : (unsigned)kPkPastQuery;
+                qprev[li] = qcur[li];
+                qcur[li] = pk2(0u - qa, 0u - qb);
+            }
+            give[li] = li <= sl ? qcur[li] : qprev[li];
+            ov[li] = L[li].outV; oe[li] = L[li].outE;
+        }
+        for (int li = 0; li < SEG; li++) {
+            const unsigned nb = give[(s - li) & (SEG - 1)];
+            const unsigned inV = li ? ov[li - 1] : ov[li], inE = li ? oe[li - 1] : oe[li];   // shfl_up keeps lane 0's own value
+            const int i = s - li + 1;
+            if (i >= 1 && i <= len2 && li < nl) {
+                unsigned w[3];
+                L[li].row(i, li * CPL, li == 0, inV, inE, nb, 1u, w);
+                for (int p = 0; p < pack_planes(CPL); p++) dirs[p * plane + (size_t)li * steps_pad + s] = w[p];
+            }
+        }
+    }
+    unsigned ka = 0, kb = 0;
+    for (int li = 0; li < SEG; li++) { ka = std::max(ka, L[li].best_key(0, li * CPL)); kb = std::max(kb, L[li].best_key(1, li * CPL)); }
+    out6[0] = out6[1] = out6[3] = out6[4] = 0; out6[2] = out6[5] = 1;
+    if (ka) pack_walk_back(dirs.data(), plane, CPL, steps_pad, 0, 0x7FFFFu - (ka & 0x7FFFFu), t1a, t2a, out6[0], out6[1], out6[2]);
+    if (kb) pack_walk_back(dirs.data(), plane, CPL, steps_pad, 1, 0x7FFFFu - (kb & 0x7FFFFu), t1b, t2b, out6[3], out6[4], out6[5]);
+}
+
+// out6 = subs, indels, aligned of pair A, then of pair B.  Returns the columns per lane used, < 0 if the pair does not fit.
+extern "C" int hh_support_pack(int SEG, const uint8_t* t1a, int len1a, const uint8_t* t2a, int len2a,
+                               const uint8_t* t1b, int len1b, const uint8_t* t2b, int len2b, int* out6)
+{
+    const int need = (std::max(len1a, len1b) + SEG - 1) / SEG;
+    if (need > 16 || (SEG != 8 && SEG != 16 && SEG != 32)) return -1;
+#define PACK(C) hh_pack_run<C>(SEG, t1a, len1a, t2a, len2a, t1b, len1b, t2b, len2b, out6); return C
+    switch ((need + 1) >> 1) {
+        case 0: case 1: PACK(2);
+        case 2: PACK(4);
+        case 3: PACK(6);
+        case 4: PACK(8);
+        case 5: PACK(10);
+        case 6: PACK(12);
+        case 7: PACK(14);
+        default: PACK(16);
+    }
+#undef PACK
+}

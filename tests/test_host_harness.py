@@ -158,3 +158,44 @@ def test_unique_diagonal_shortcut_is_exact_under_other_scorings(harness, oracle,
             assert scr == script, ctx
             assert (out[6], out[7], out[8]) == (cells.fwd, cells.rev, cells.glob), ctx
     assert n > 600
+
+
+def _harness_support():
+    deps = [SRC] + [os.path.join(HERE, "..", "indelminer_b200", "csrc", f) for f in ("kernels.cuh", "band_dp.cuh", "indel_support.cuh", "indel_support_pack.cuh")]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+                               "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO, SRC])
+    L = C.CDLL(SO)
+    L.hh_support_pack.restype = C.c_int
+    return L
+
+
+def test_packed_support_check_matches_oracle(oracle):
+    """indel_support_pack.cuh (16-bit halves, shifted score domain, direction bits + walk back): the per-lane row step
+    and the walk back are the device source compiled for the host, one segment of lanes stepped in lockstep.  Two
+    pairs share every register; compared with the oracle's plain DP on reference-shaped cases and on edge shapes."""
+    from tests.util import indel_support_cases
+    L = _harness_support()
+    rng = make_rng(91)
+    pairs = []
+    for c in indel_support_cases(rng, 1500):
+        ref, rstart, rstop, read, qstart, qstop, vtype, vstart, vstop, alt = c
+        pairs.append((oracle.indel_target(ref, rstart, rstop, vtype, vstart, vstop, alt), read[qstart:qstop].encode()))
+    for _ in range(600):                                   # unrelated / repetitive / N-rich / tiny pairs
+        alpha = rng.choice(["ACGT", "AC", "A", "ACGTN", "acgtACGT"])
+        pairs.append((rseq(rng, rng.randrange(0, 300), alpha).encode(), rseq(rng, rng.randrange(0, 200), alpha).encode()))
+    pairs += [(b"", b"ACGT"), (b"ACGT", b""), (b"", b""), (b"A", b"A"), (b"A", b"C"), (b"ACGT" * 128, b"ACGT" * 50), (b"acgt" * 20, b"ACGT" * 20)]
+    want = [oracle.indel_support_dp(t, q) for t, q in pairs]
+    out = (C.c_int * 6)()
+    n = 0
+    for k in range(0, len(pairs) - 1):
+        (ta, qa), (tb, qb) = pairs[k], pairs[(k * 7 + 3) % len(pairs)]
+        for seg in (8, 16, 32):
+            if max(len(ta), len(tb)) > 16 * seg:
+                continue
+            rc = L.hh_support_pack(seg, ta, len(ta), qa, len(qa), tb, len(tb), qb, len(qb), out)
+            assert rc > 0
+            assert tuple(out[0:3]) == want[k], (k, seg, rc, len(ta), len(qa))
+            assert tuple(out[3:6]) == want[(k * 7 + 3) % len(pairs)], (k, seg, rc, "B")
+            n += 1
+    assert n > 4000
