@@ -109,9 +109,9 @@ struct indelgpu_ctx {
     DevBuf counters;         // bytes: 0 work counter (int) | 8 seg count (u64) | 16 cells (3 x u64) | 40 error flag (int) | 48 algorithmic bytes (u64) | 56 ALIGN cells not swept (u64, band tasks)
     DevBuf scratch;
     DevBuf s_tgt, s_toff, s_qry, s_qoff, s_out, s_ord, s_idx, s_V, s_I, s_F;
-    // the two-pass support check (indel_support_pack.cuh): scratch of up to three launches in flight -- the walk back of
-    // one runs (on st_out) beside the wavefront pass of the next
-    struct PackSlot { DevBuf dirs, cpl, best; cudaEvent_t packed = nullptr, walked = nullptr; bool busy = false; } pk[3];
+    // the two-pass support check (indel_support_pack.cuh): scratch of up to three wavefront launches that share one
+    // launch of the walk back
+    struct PackSlot { DevBuf dirs, cpl, best; } pk[3];
     int32_t* h_order = nullptr; size_t h_order_cap = 0;            // pinned work list of the support check   // known-indel support check (indel_support.cuh)
     DevBuf p_low, p_aln, p_cig, p_plan, p_flags;      // intermediates of the banded pipeline (realign_pipeline.cuh)
     // task API staging
@@ -195,7 +195,6 @@ extern "C" void indelgpu_destroy(indelgpu_ctx* c)
                      &c->t_reads, &c->t_roff, &c->t_refs, &c->t_woff, &c->t_packed, &c->t_anchor, &c->t_low,
                      &c->t_up, &c->t_score, &c->t_ends, &c->t_ncig, &c->t_cig, &c->t_script};
     for (DevBuf* b : all) b->release();
-    for (auto& k : c->pk) { if (k.packed) cudaEventDestroy(k.packed); if (k.walked) cudaEventDestroy(k.walked); }
     if (c->pinned_small) cudaFreeHost(c->pinned_small);
     delete c;
 }
@@ -1107,7 +1106,8 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
     // the 16-bit two-pass kernels: a wavefront pass that leaves two direction bits per cell in a scratch buffer, then
     // the walk back with one thread per pair.  A class is cut into launches whose scratch stays under ~2 GB.
     static const int pack_shape = getenv("INDELGPU_PACK_SHAPE") ? atoi(getenv("INDELGPU_PACK_SHAPE")) : 1;   // experiments
-    int pack_launch = 0;
+    WalkArgs walk;
+    walk.njobs = 0; walk.first_block[0] = 0;
     for (int cls = 0; cls < 3; cls++) {
         const int cfirst = cls ? list_end[cls - 1] : 0, ccnt = list_end[cls] - cfirst;
         if (ccnt <= 0) continue;
@@ -1121,11 +1121,9 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
         for (long long done = 0; done < ccnt; done += max_pairs) {
             const int cnt = (int)std::min<long long>(max_pairs, ccnt - done);
             const long long npass = ((long long)cnt + per_pass - 1) / per_pass;
-            indelgpu_ctx::PackSlot& k = c->pk[pack_launch++ % 3];
-            if (!k.packed) { CU(cudaEventCreateWithFlags(&k.packed, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&k.walked, cudaEventDisableTiming)); }
-            if (k.busy) { CU(cudaStreamWaitEvent(st, k.walked, 0)); k.busy = false; }           // the slot's previous walk has read its scratch
+            indelgpu_ctx::PackSlot& k = c->pk[walk.njobs];
             if (k.dirs.ensure(pack_dirs_bytes(cnt, seg, maxcpl, steps_cap)) || k.cpl.ensure(4 * (size_t)npass) || k.best.ensure(4 * (size_t)cnt)) {
-                cudaStreamSynchronize(st); cudaStreamSynchronize(c->st_out); return INDELGPU_ENOMEM;
+                cudaStreamSynchronize(st); return INDELGPU_ENOMEM;
             }
             PackArgs w;
             w.n = cnt;
@@ -1145,19 +1143,24 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
             else if (maxcpl == 8) PACK_LAUNCH(32, 8)
             else PACK_LAUNCH(32, 16)
 #undef PACK_LAUNCH
-            if (occ < 1) { cudaStreamSynchronize(st); cudaStreamSynchronize(c->st_out); return fail(INDELGPU_ELIMIT, "support kernel does not fit on an SM"); }
+            if (occ < 1) { cudaStreamSynchronize(st); return fail(INDELGPU_ELIMIT, "support kernel does not fit on an SM"); }
             c->launches++;
             CU(cudaGetLastError());
-            CU(cudaEventRecord(k.packed, st));
-            CU(cudaStreamWaitEvent(c->st_out, k.packed, 0));
-            indel_support_walk_kernel<<<(cnt + 127) / 128, 128, 0, c->st_out>>>(w);
-            c->launches++;
-            CU(cudaGetLastError());
-            CU(cudaEventRecord(k.walked, c->st_out));
-            k.busy = true;
+            walk.first_block[walk.njobs + 1] = walk.first_block[walk.njobs] + (cnt + 127) / 128;
+            walk.job[walk.njobs++] = w;
+            if (walk.njobs == kWalkJobs) {                  // every scratch slot is in use
+                indel_support_walk_kernel<<<walk.first_block[walk.njobs], 128, 0, st>>>(walk);
+                c->launches++;
+                CU(cudaGetLastError());
+                walk.njobs = 0;
+            }
         }
     }
-    for (auto& k : c->pk) if (k.busy) { CU(cudaStreamWaitEvent(st, k.walked, 0)); k.busy = false; }
+    if (walk.njobs > 0) {
+        indel_support_walk_kernel<<<walk.first_block[walk.njobs], 128, 0, st>>>(walk);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
     for (int cls = 0; cls < 3; cls++) {                            // queries too long for it: the carried-counter wavefront
         const int first = list_end[2 + cls], cnt = list_end[3 + cls] - first;
         if (cnt <= 0) continue;

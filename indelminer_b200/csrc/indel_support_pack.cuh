@@ -163,10 +163,19 @@ struct PackLane {
 // `stride`: words from one LANE to the next -- a lane's steps are contiguous, so the cells of a diagonal (same lane,
 // one step back per cell) share 32-byte sectors.  Cell (i, j) of half h: lane (j-1) / cpl at step i - 1 + lane,
 // column c = (j-1) % cpl of that lane.
-// Every step of the walk is a dependent load from a buffer far larger than L2, and most steps are substitutions:
-// the words and bases of the next kPackAhead cells of the current DIAGONAL are fetched together, and consumed for
-// as long as the path stays on it.
+// Every word is a dependent load from a buffer far larger than L2.  One word holds a whole row of a lane's columns,
+// so the words of the next kPackAhead ROWS -- in the lanes the current diagonal passes through -- are fetched
+// together and serve substitutions, insertions (one row up, same word as the diagonal's) and deletions (same row,
+// same word) alike until the path leaves those lanes.  Substitutions are only counted as runs of a diagonal; their
+// bases are compared (raw bytes, variant.c:1412) when the run ends, with loads that do not depend on each other.
 enum { kPackAhead = 8 };
+__host__ __device__ __forceinline__ int pack_count_mismatches(const uint8_t* __restrict__ t1, const uint8_t* __restrict__ t2, int i, int j, int run)
+{
+    int ns = 0;                                            // the run's cells: (i + k, j + k), k = 1 .. run
+    for (int k = 1; k <= run; k++) ns += t1[j + k - 1] != t2[i + k - 1];
+    return ns;
+}
+
 __host__ __device__ __forceinline__ void pack_walk_back(const uint32_t* __restrict__ dirs, size_t plane, int cpl, int stride, int h, unsigned pos,
                                                         const uint8_t* __restrict__ t1, const uint8_t* __restrict__ t2,
                                                         int& subs, int& indels, int& aligned)
@@ -175,34 +184,46 @@ __host__ __device__ __forceinline__ void pack_walk_back(const uint32_t* __restri
     int ns = 0, ni = 0, na = 1;                            // the NUL column (:1405)
     const size_t pplane = (size_t)(pack_planes(cpl) - 1) * plane;
     int lj = (j - 1) / cpl, c = (j - 1) - lj * cpl;        // kept incrementally: no division inside the loop
-    bool walking = true;
+    int run = 0;                                           // substitutions since the last gap, not compared yet
+    bool walking = true, flush = false;
     while (walking && i > 0 && j > 0) {                    // row 0 and column 0 hold negative scores
-        unsigned wp[kPackAhead], wd[kPackAhead], neq[kPackAhead];
+        if (flush) { ns += pack_count_mismatches(t1, t2, i, j, run); run = 0; flush = false; }
+        unsigned wp[kPackAhead], w0[kPackAhead], w1[kPackAhead];
+        int lane_of[kPackAhead];
         {
             int ljt = lj, ct = c;
 #pragma unroll
             for (int t = 0; t < kPackAhead; t++) {
-                wp[t] = wd[t] = neq[t] = 0;
-                if (i - t > 0 && j - t > 0) {
+                lane_of[t] = ljt;
+                wp[t] = w0[t] = w1[t] = 0;
+                if (i - t > 0 && ljt >= 0) {
                     const uint32_t* w = dirs + (size_t)ljt * stride + (i - t - 1 + ljt);
                     wp[t] = w[pplane];
-                    wd[t] = w[(size_t)(ct >> 3) * plane];
-                    neq[t] = t1[j - t - 1] != t2[i - t - 1];
+                    w0[t] = w[0];
+                    if (cpl > 8) w1[t] = w[plane];
                 }
                 if (--ct < 0) { ct = cpl - 1; ljt--; }
             }
         }
+        bool on = true;                                    // still inside the words that were fetched
 #pragma unroll
-        for (int t = 0; t < kPackAhead; t++) {
-            if (!(i > 0 && j > 0)) { walking = false; break; }
-            if (!((wp[t] >> ((((c & 1) << 1) + h) * 8 + (c >> 1))) & 1u)) { walking = false; break; }      // V <= 0
-            const int cnt = (c >> 3) ? cpl - 8 : (cpl < 8 ? cpl : 8);
-            const unsigned code = (wd[t] >> (16 * h + 2 * (cnt - 1 - (c & 7)))) & 3u;
-            if (code != 1) { if (--c < 0) { c = cpl - 1; lj--; } }      // one column to the left
-            if (code == 2) { ns += (int)neq[t]; na++; i--; j--; }        // still on the diagonal that was fetched
-            else { if (code == 1) { ni++; na++; i--; } else { ni++; j--; } break; }
+        for (int t = 0; t < kPackAhead; t++) {             // row i0 - t
+            while (on) {                                   // its cells, leftwards over deletions
+                if (i <= 0 || j <= 0) { walking = false; on = false; break; }
+                if (lane_of[t] != lj) { on = false; break; }
+                if (!((wp[t] >> ((((c & 1) << 1) + h) * 8 + (c >> 1))) & 1u)) { walking = false; on = false; break; }   // V <= 0
+                const int cnt = (c >> 3) ? cpl - 8 : (cpl < 8 ? cpl : 8);
+                const unsigned code = (((c >> 3) ? w1[t] : w0[t]) >> (16 * h + 2 * (cnt - 1 - (c & 7)))) & 3u;
+                if (code != 2 && run > 0) { flush = true; on = false; break; }          // the run of substitutions ends here
+                if (code != 1) { j--; if (--c < 0) { c = cpl - 1; lj--; } }           // one column to the left
+                if (code == 0) { ni++; continue; }                                       // deletion: same row
+                if (code == 1) ni++; else run++;
+                na++; i--;
+                break;                                                                   // one row up: the next word
+            }
         }
     }
+    ns += pack_count_mismatches(t1, t2, i, j, run);
     subs = ns; indels = ni; aligned = na;
 }
 
@@ -239,17 +260,19 @@ __device__ __forceinline__ void support_pack_pass(const uint8_t* t1a, int len1a,
     const int nl = (len1 + CPL - 1) / CPL;
     const int steps = (len1 > 0 && len2 > 0) ? len2 + nl - 1 : 0;
     const int wsteps = __reduce_max_sync(FULL, steps);     // the segments of a warp step together
-    unsigned qcur = 0, qprev = 0;
+    // query bases, SEG rows per load and one load AHEAD of their use (the load's latency would otherwise stall the warp
+    // every SEG steps): qnext holds rows [s0 + SEG, s0 + 2 SEG) while the wavefront consumes qcur and qprev
+    auto load_q = [&](int r) {
+        const unsigned qa = r < len2a ? (unsigned)up_case(t2a[r]) << 4 : (unsigned)kPkPastQuery;
+        const unsigned qb = r < len2b ? (unsigned)up_case(t2b[r]) << 4 : (unsigned)kPkPastQuery;
+        return pk2(0u - qa, 0u - qb);
+    };
+    unsigned qcur = 0, qprev = 0, qnext = load_q(li);
+    uint32_t* sp = stage;                                  // this step's slot of the staging tile
 #pragma unroll 1
     for (int s = 0; s < wsteps; s++) {
         const int sl = s & (SEG - 1);
-        if (sl == 0) {                                     // the next SEG query bases, one per lane
-            const int r = s + li;
-            const unsigned qa = r < len2a ? (unsigned)up_case(t2a[r]) << 4 : (unsigned)kPkPastQuery;
-            const unsigned qb = r < len2b ? (unsigned)up_case(t2b[r]) << 4 : (unsigned)kPkPastQuery;
-            qprev = qcur;
-            qcur = pk2(0u - qa, 0u - qb);
-        }
+        if (sl == 0) { qprev = qcur; qcur = qnext; qnext = load_q(s + SEG + li); }
         // lane li works on query index s - li: lane (s - li) mod SEG holds it, in qcur if it was loaded this round
         const unsigned give = li <= sl ? qcur : qprev;
         const unsigned nb = __shfl_sync(FULL, give, (s - li) & (SEG - 1), SEG);
@@ -260,9 +283,11 @@ __device__ __forceinline__ void support_pack_pass(const uint8_t* t1a, int len1a,
             unsigned w[3];
             L.row(i, j0, li == 0, inV, inE, nb, one, w);
 #pragma unroll
-            for (int p = 0; p < pack_planes(CPL); p++) stage[(p * 8 + (s & 7)) * 32] = w[p];
+            for (int p = 0; p < pack_planes(CPL); p++) sp[p * 256] = w[p];
         }
+        sp += 32;
         if ((s & 7) == 7 || s == wsteps - 1) {             // eight steps of this lane = one 32-byte sector per plane
+            sp = stage;
 #pragma unroll
             for (int p = 0; p < pack_planes(CPL); p++) {
                 uint4 lo, hi;
@@ -284,7 +309,7 @@ __device__ __forceinline__ void support_pack_pass(const uint8_t* t1a, int len1a,
 }
 
 template <int SEG, int MAXCPL>
-__global__ void __launch_bounds__(128, MAXCPL <= 8 ? 4 : 2)
+__global__ void __launch_bounds__(128, 4)
 indel_support_pack_kernel(const __grid_constant__ PackArgs a)
 {
     constexpr int SLOTS = 32 / SEG;                        // register halves come in pairs: 2 * SLOTS pairs per pass
@@ -340,11 +365,19 @@ indel_support_pack_kernel(const __grid_constant__ PackArgs a)
     }
 }
 
-// pass 2, one THREAD per pair: a warp walks 32 paths at once instead of leaving 30 lanes idle behind the wavefront
-__global__ void __launch_bounds__(128)
-indel_support_walk_kernel(const __grid_constant__ PackArgs a)
+// pass 2, one THREAD per pair: a warp walks 32 paths at once instead of leaving 30 lanes idle behind the wavefront.
+// One launch serves the pass launches that are waiting for it (blocks [first_block[q], first_block[q + 1]) walk job q):
+// the kernel is a chain of dependent loads per thread, so its duration hardly depends on the number of pairs.
+enum { kWalkJobs = 3 };
+struct WalkArgs { int njobs; int first_block[kWalkJobs + 1]; PackArgs job[kWalkJobs]; };
+
+__global__ void __launch_bounds__(128, 8)
+indel_support_walk_kernel(const __grid_constant__ WalkArgs wa)
 {
-    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int q = 0;
+    while (q + 1 < wa.njobs && (int)blockIdx.x >= wa.first_block[q + 1]) q++;
+    const PackArgs& a = wa.job[q];
+    const long long k = (blockIdx.x - wa.first_block[q]) * (long long)blockDim.x + threadIdx.x;
     if (k >= a.n) return;
     const int per_pass = 2 * (32 / a.seg);
     const int steps_pad = (a.steps_cap + 7) & ~7;
