@@ -315,7 +315,8 @@ class Realigner:
         _check(self._L.indelgpu_indel_support_batch(
             self._ctx, n, tb.ctypes.data, toff.ctypes.data, qb.ctypes.data, qoff.ctypes.data,
             subs.ctypes.data, indels.ctypes.data, aligned.ctypes.data, C.addressof(cells)))
-        return dict(subs=subs, indels=indels, aligned=aligned, cells=cells.value)
+        return dict(subs=subs, indels=indels, aligned=aligned, cells=cells.value,
+                    launches=int(self._L.indelgpu_last_launch_count(self._ctx)))
 
     def attempt_band_alignment(self, refseq, zstart1, end1, readseq, zstart2, end2, low, up):
         """alignment.c:343-391, same arguments; returns ((r1, r2, q1, q2), cigar words)."""

@@ -23,8 +23,8 @@
 // multiply-adds on the otherwise idle FMA pipe; bit 15 of a key says V > 0, and the largest key of a lane's row is its
 // best cell with the reference's "first maximum" order inside the row.
 //
-// Lengths: target <= 512, query <= kPackMaxQuery (bounds the scratch and the 16-bit ranges); longer queries stay on
-// indel_support_wave_kernel.  Reproduced quirks as in indel_support.cuh.
+// Lengths: target <= 512, query <= kPackMaxQuery = 500 (the 16-bit ranges: 16 * (V + 2047) needs |V| < 2048; a
+// position is 9 + 10 bits); anything longer goes to indel_support_kernel, one pair per thread.  Reproduced quirks as in indel_support.cuh.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -34,7 +34,7 @@
 
 namespace indelgpu {
 
-enum { kPackMaxQuery = 208 };
+enum { kPackMaxQuery = 500 };       // = kWaveMaxQuery: 9 bits of row in a position, V + 2047 in 12 bits
 enum : unsigned { kPkBias = 64u, kPkPastTarget = 0xFFF0u, kPkPastQuery = 0xFFE0u };
 
 __host__ __device__ __forceinline__ unsigned pk2(unsigned lo, unsigned hi) { return (lo & 0xFFFFu) | (hi << 16); }

@@ -116,3 +116,34 @@ def test_every_columns_per_lane_variant(gpu, oracle):
         for k, i in enumerate(sel):
             assert (out["subs"][k], out["indels"][k], out["aligned"][k]) == oracle.indel_support_dp(T[i], Q[i]), (i, len(T[i]), len(Q[i]))
         R.close()
+
+
+def test_scratch_ring_and_chunked_launches(gpu, oracle):
+    """enough long pairs that the direction bits of one class exceed the 2 GB a launch may use: the class is cut into
+    several wavefront launches, more than the three scratch slots, so slots are reused after a merged walk launch;
+    mixed with short pairs of the other classes in the same batch"""
+    rng = np.random.default_rng(23)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    base = acgt[rng.integers(0, 4, size=1 << 16)]
+    T, Q = [], []
+    for i in range(66_000):
+        s = int(rng.integers(0, (1 << 16) - 600))
+        if i % 11 == 0:
+            t = base[s:s + int(rng.integers(30, 250))]
+            q = t[int(rng.integers(0, 20)):][:150].copy()
+        else:
+            t = base[s:s + int(rng.integers(480, 513))]
+            q = np.concatenate([t[3:200], t[200 + int(rng.integers(0, 30)):]])[:500].copy()
+        if len(q) > 40:
+            q[int(rng.integers(0, len(q)))] = acgt[int(rng.integers(0, 4))]
+        T.append(t.tobytes())
+        Q.append(q.tobytes())
+    R = gpu.Realigner()
+    out = R.indel_support_batch(T, Q)
+    assert out["launches"] >= 7                              # wavefront launches of three classes, walks after every third
+    for i in list(range(0, len(T), 1009)) + [len(T) - 1, len(T) - 2]:
+        assert (out["subs"][i], out["indels"][i], out["aligned"][i]) == oracle.indel_support_dp(T[i], Q[i]), i
+    again = R.indel_support_batch(T, Q)                       # same context, warm buffers: identical
+    for k in ("subs", "indels", "aligned"):
+        assert np.array_equal(out[k], again[k])
+    R.close()

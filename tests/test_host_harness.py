@@ -184,6 +184,10 @@ def test_packed_support_check_matches_oracle(oracle):
     for _ in range(600):                                   # unrelated / repetitive / N-rich / tiny pairs
         alpha = rng.choice(["ACGT", "AC", "A", "ACGTN", "acgtACGT"])
         pairs.append((rseq(rng, rng.randrange(0, 300), alpha).encode(), rseq(rng, rng.randrange(0, 200), alpha).encode()))
+    for _ in range(60):                                    # the longest shapes the kernel takes: 512 x 500, related and not
+        t = rseq(rng, rng.randrange(400, 513), "ACGT")
+        q = mutate(rng, t[rng.randrange(0, 12):], "ACGT", sub=0.03, nindel=rng.randrange(0, 4), maxindel=30)[:500] if rng.random() < 0.7 else rseq(rng, 500, "AC")
+        pairs.append((t.encode(), q.encode()))
     pairs += [(b"", b"ACGT"), (b"ACGT", b""), (b"", b""), (b"A", b"A"), (b"A", b"C"), (b"ACGT" * 128, b"ACGT" * 50), (b"acgt" * 20, b"ACGT" * 20)]
     want = [oracle.indel_support_dp(t, q) for t, q in pairs]
     out = (C.c_int * 6)()
