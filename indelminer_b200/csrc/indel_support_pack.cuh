@@ -112,6 +112,7 @@ struct PackLane {
         unsigned diag = vdiag;
         vdiag = left;
         const unsigned rowK = pk_both((2047u - kPkBias - 17u - (unsigned)i - (unsigned)j0) * 16u);
+        const unsigned mone = 0u - one;                     // -1 at run time: keeps v4 - code a multiply-add
         unsigned acc0 = 0, acc1 = 0, P = 0, rowbest = 0;
 #pragma unroll
         for (int c = 0; c < CPL; c += 2) {
@@ -126,9 +127,9 @@ struct PackLane {
                 const unsigned ifdel = __viaddmax_u16x2(left, 0xFFF0FFF0u, E);         // tie bits 0
                 E = ifdel;
                 const unsigned v4 = __vimax3_u16x2(ifsub, ifins, ifdel);              // variant.c:1336-1342 in one instruction
-                const unsigned vc = v4 & 0xFFFCFFFCu;
-                if (c + d < 8) acc0 = pk_mad(acc0, 4u, 0u) | (v4 & 0x00030003u);
-                else acc1 = pk_mad(acc1, 4u, 0u) | (v4 & 0x00030003u);
+                const unsigned code = v4 & 0x00030003u;                                // which candidate it was
+                const unsigned vc = pk_mad(code, mone, v4);                            // v4 - code, on the FMA pipe
+                if (c + d < 8) acc0 = pk_mad(acc0, 4u, code); else acc1 = pk_mad(acc1, 4u, code);
                 // 16 * (V + 2047) + 15 - (c + d):  vc * 4 = 16 * (V + i + j0 + c + d + 1 + BIAS)
                 key[d] = pk_mad(pk_mad(vc, 4u, rowK), one, pk_both((unsigned)((16 - (c + d)) * 16 + 15 - (c + d))));
                 V[c + d] = vc; diag = up; left = vc;
