@@ -883,13 +883,57 @@ __device__ __forceinline__ BandLocal local_sweeps_warp(const DevParams& P, const
         Hr[c] = v ? 0 : kNeg; Dr[c] = v ? -G : kNeg;
     }
     int best = 0, endi = si, endt = 0, cf = 0;
+    // Rows whose band lies inside the window (nearly all of them) take a body without per-cell bounds tests: which of a
+    // lane's slots exist (t < band) does not change from row to row, the window byte of slot c is wl[c][i], the scan's
+    // position terms are per-lane constants, and the position of the lane's best cell of the row rides in the low bits
+    // of one maximum (key = score * 256 + 255 - t).
+    bool vs[C]; const uint8_t* wl[C]; int kA[C], tH[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const int t = t0 + c;
+        vs[c] = t < band;
+        wl[c] = win + (low - 1) + (vs[c] ? t : 0);                // a slot outside the band reads slot 0's byte and ignores it
+        kA[c] = (t + 1) * Hh - m;
+        tH[c] = t * Hh;
+    }
 #pragma unroll 1
     for (int i = si + 1; i <= ei; i++) {
         const int tlo = ig_max(0, -i - low), thi = ig_min(band - 1, N - i - low);
         const uint32_t ai = read[i - 1];
         int hnext = __shfl_down_sync(FULL, Hr[0], 1), dnext = __shfl_down_sync(FULL, Dr[0], 1);
         if (lane == 31) { hnext = kNeg; dnext = kNeg; }
-        int hq[C], dq[C], laneA = kLow;
+        int hq[C], dq[C];
+        if (i + low >= 1 && i + low + band - 1 <= N) {            // tlo == 0, thi == band - 1, every byte inside the window
+            int laneA = kLow;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const int hup = (c + 1 < C) ? Hr[c + 1] : hnext, dup = (c + 1 < C) ? Dr[c + 1] : dnext;
+                const int d = ig_max(hup - m, dup - Hh);
+                const uint32_t b = wl[c][i];
+                hq[c] = ig_max(Hr[c] + (b == ai ? P.match : P.mismatch), ig_max(d, 0));
+                dq[c] = d;
+                if (vs[c]) laneA = ig_max(laneA, hq[c] + kA[c]);
+            }
+            int incl = laneA;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl = ig_max(incl, v); }
+            int run = __shfl_up_sync(FULL, incl, 1);
+            if (lane == 0) run = kLow;
+            int key = -1;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                if (vs[c]) {
+                    const int cv = ig_max(hq[c], run - tH[c]);
+                    run = ig_max(run, hq[c] + kA[c]);
+                    Hr[c] = cv; Dr[c] = dq[c];
+                    key = ig_max(key, cv * 256 + (255 - (t0 + c)));
+                }
+            }
+            if ((key >> 8) > best) { best = key >> 8; endi = i; endt = 255 - (key & 255); }
+            cf += band;
+            continue;
+        }
+        int laneA = kLow;
 #pragma unroll
         for (int c = 0; c < C; c++) {
             const int t = t0 + c;
@@ -946,6 +990,9 @@ __device__ __forceinline__ BandLocal local_sweeps_warp(const DevParams& P, const
         }
     }
     int starti = 0, startt = 0, cr = 0; bool found = false;
+    int kB[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) kB[c] = -m - (t0 + c - 1) * Hh;
 #pragma unroll 1
     for (int i = endi; i >= 1 && !found; i--) {
         const int thi = ig_min(band - 1, tend + (endi - i) + 1);
@@ -953,7 +1000,39 @@ __device__ __forceinline__ BandLocal local_sweeps_warp(const DevParams& P, const
         const uint32_t ai = read[i - 1];
         int hprev = __shfl_up_sync(FULL, Hr[C - 1], 1), dprev = __shfl_up_sync(FULL, Dr[C - 1], 1);
         if (lane == 0) { hprev = kNeg; dprev = kNeg; }
-        int hq[C], dq[C], laneB = kLow;
+        int hq[C], dq[C];
+        if (thi == band - 1 && i + low >= 1 && i + low + band - 1 <= N) {   // the wedge has reached the band's width; all bytes inside
+            int laneB = kLow;
+#pragma unroll
+            for (int c = C - 1; c >= 0; c--) {
+                const int hdn = (c > 0) ? Hr[c - 1] : hprev, ddn = (c > 0) ? Dr[c - 1] : dprev;
+                const int d = ig_max(hdn - m, ddn - Hh);
+                const uint32_t b = wl[c][i];
+                hq[c] = ig_max(Hr[c] + (b == ai ? P.match : P.mismatch), d);
+                dq[c] = d;
+                if (vs[c]) laneB = ig_max(laneB, hq[c] + kB[c]);
+            }
+            int incl = laneB;                                     // suffix maximum over the lanes above
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_down_sync(FULL, incl, o); if (lane + o < 32) incl = ig_max(incl, v); }
+            int run = __shfl_down_sync(FULL, incl, 1);
+            if (lane == 31) run = kLow;
+            int hit = -1;                                         // largest own diagonal whose value equals the optimum
+#pragma unroll
+            for (int c = C - 1; c >= 0; c--) {
+                if (vs[c]) {
+                    const int cv = ig_max(hq[c], run + tH[c]);
+                    run = ig_max(run, hq[c] + kB[c]);
+                    Hr[c] = cv; Dr[c] = dq[c];
+                    if (cv == best && hit < 0) hit = t0 + c;
+                }
+            }
+            const int tophit = __reduce_max_sync(FULL, hit);
+            if (tophit >= 0) { found = true; starti = i; startt = tophit; cr += thi - tophit + 1; }
+            else cr += band;
+            continue;
+        }
+        int laneB = kLow;
 #pragma unroll
         for (int c = C - 1; c >= 0; c--) {
             const int t = t0 + c;

@@ -431,7 +431,8 @@ static int launch_realign(indelgpu_ctx* c, const indelgpu_batch* d_in, int max_r
     const long long nd = 2LL * ((long long)max_range1 + c->P.maxdel) + max_read + 2;
     if (nd > (1 << 20)) return fail(INDELGPU_ELIMIT, "window of %lld diagonals exceeds the kernel limit", nd);
     const int max_numdiag = (int)nd;
-    const bool banded = c->P.g > 0;
+    static const bool force_split = getenv("INDELGPU_SPLIT") != nullptr;     // experiment: -g 0 through the kernel pipeline
+    const bool banded = c->P.g > 0 || (force_split && !p4);
     // the banded pipeline only votes with this layout (its CIGARs live in HBM), so it takes the compact form too
     const long long vd = std::max(2LL * max_range1, (long long)max_range1 + c->P.maxdel) + max_read + 2;
     if (p4 && (c->P.k > 6 || c->idx_blocks > 0)) return fail(INDELGPU_EINVAL, "internal: only the direct-table window-scan kernel expands 4-bit reads");
