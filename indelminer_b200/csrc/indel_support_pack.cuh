@@ -78,7 +78,7 @@ __host__ __device__ __forceinline__ int pack_planes(int cpl) { return cpl <= 8 ?
 template <int CPL>
 struct PackLane {
     unsigned A[CPL];        // target codes (upper-cased byte << 4; past the target: matches nothing)
-    unsigned V[CPL];        // V4 of the previous row
+    unsigned V[CPL];        // V4 + 18 of the previous row (the substitution's constant, so that it is one multiply-add)
     unsigned F[CPL];        // ifins4 + 1 of the previous row
     unsigned best;          // largest key so far, per half
     unsigned rowA, rowB;    // the row it was seen in
@@ -93,21 +93,21 @@ struct PackLane {
             const unsigned ca = j < len1a ? (unsigned)up_case(t1a[j]) << 4 : (unsigned)kPkPastTarget;
             const unsigned cb = j < len1b ? (unsigned)up_case(t1b[j]) << 4 : (unsigned)kPkPastTarget;
             A[c] = pk2(ca, cb);
-            V[c] = pk_both(4 * (kPkBias - 4));                     // row 0: V = -4 - j (variant.c:1303-1306), shifted by j
+            V[c] = pk_both(4 * (kPkBias - 4) + 18);                // row 0: V = -4 - j (variant.c:1303-1306), shifted by j; V is kept + 18
             F[c] = pk_both(4 * (kPkBias + (unsigned)(j + 1)) + 1);   // F = 0, shifted by j; an insertion's tie bits
         }
         best = pk_both(2047u << 4); rowA = rowB = 0;               // score 0: nothing yet
-        vdiag = pk_both(4 * (kPkBias - 4));
+        vdiag = pk_both(4 * (kPkBias - 4) + 18);
         outV = outE = 0;
     }
 
-    // row i (1-based) of this lane's columns.  inV / inE: V4 and ifdel4 of (i, j0) from the lane on the left (first
+    // row i (1-based) of this lane's columns.  inV / inE: V4 + 18 and ifdel4 of (i, j0) from the lane on the left (first
     // lane: the column-0 values); nb: the negated query codes of row i; one: the number 1 at run time.
     // w[]: the direction words of the row's cells (pack_planes(CPL) of them).
     __host__ __device__ __forceinline__ void row(int i, int j0, bool first, unsigned inV, unsigned inE, unsigned nb, unsigned one,
                                                  unsigned* w)
     {
-        unsigned left = first ? pk_both(4 * (kPkBias - 4)) : inV;               // V[i][0] = -4 - i, shifted by i
+        unsigned left = first ? pk_both(4 * (kPkBias - 4) + 18) : inV;          // V[i][0] = -4 - i, shifted by i (+ 18)
         unsigned E = first ? pk_both(4 * (kPkBias + (unsigned)i)) : inE;         // E restarts at 0 on every row (:1322)
         unsigned diag = vdiag;
         vdiag = left;
@@ -121,10 +121,10 @@ struct PackLane {
             for (int d = 0; d < 2; d++) {
                 const unsigned up = V[c + d];
                 const unsigned m12 = __viaddmin_u16x2(A[c + d], nb, 0x000C000Cu);      // 0 if the bases match, else 12
-                const unsigned ifsub = diag + 0x00120012u - m12;                       // 4 * (4 | 1) + tie bits 2
-                const unsigned ifins = __viaddmax_u16x2(up, 0xFFF1FFF1u, F[c + d]);   // 4 * -4 + tie bits 1
+                const unsigned ifsub = pk_mad(m12, mone, diag);                        // (V + 18) - m12: 4 * (4 | 1) + tie bits 2
+                const unsigned ifins = __viaddmax_u16x2(up, 0xFFDFFFDFu, F[c + d]);   // (V + 18) - 33: 4 * -4 + tie bits 1
                 F[c + d] = ifins;
-                const unsigned ifdel = __viaddmax_u16x2(left, 0xFFF0FFF0u, E);         // tie bits 0
+                const unsigned ifdel = __viaddmax_u16x2(left, 0xFFDEFFDEu, E);         // (V + 18) - 34: tie bits 0
                 E = ifdel;
                 const unsigned v4 = __vimax3_u16x2(ifsub, ifins, ifdel);              // variant.c:1336-1342 in one instruction
                 const unsigned code = v4 & 0x00030003u;                                // which candidate it was
@@ -132,7 +132,8 @@ struct PackLane {
                 if (c + d < 8) acc0 = pk_mad(acc0, 4u, code); else acc1 = pk_mad(acc1, 4u, code);
                 // 16 * (V + 2047) + 15 - (c + d):  vc * 4 = 16 * (V + i + j0 + c + d + 1 + BIAS)
                 key[d] = pk_mad(pk_mad(vc, 4u, rowK), one, pk_both((unsigned)((16 - (c + d)) * 16 + 15 - (c + d))));
-                V[c + d] = vc; diag = up; left = vc;
+                const unsigned v18 = pk_mad(vc, one, 0x00120012u);
+                V[c + d] = v18; diag = up; left = v18;
             }
             rowbest = __vimax3_u16x2(rowbest, key[0], key[1]);
             P |= pk_signs(key[0], key[1]) & (0x01010101u << (c >> 1));
