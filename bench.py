@@ -445,7 +445,7 @@ def run_ours(a, rank, world, local_rank):
         except Exception as e:                                   # noqa: BLE001  (the headline must survive)
             line["extra"]["band_sweep"] = {"error": repr(e)}
         try:
-            line["extra"]["support"] = support_line(a, R, L, torch, local_rank, tasks=1 << 17, steps=100, warmup=2, cpu=False)
+            line["extra"]["support"] = support_line(a, R, L, torch, local_rank, tasks=1 << 17, steps=100, warmup=3, cpu=not a.no_cpu)
         except Exception as e:                                   # noqa: BLE001
             line["extra"]["support"] = {"error": repr(e)}
         try:

@@ -8,6 +8,8 @@ python tools/make_traffic_json.py $O/${R}_realign_final.ncu-rep profiles/traffic
 ncu --set full --import-source on --clock-control none -k regex:indel_support_ -c 3 -o $O/${R}_support_final -f \
     python bench.py --workload support --steps 1 --warmup 0 --no-cpu > $O/${R}_ncu_support.log 2>&1
 ncu -i $O/${R}_support_final.ncu-rep --page raw --csv > $O/${R}_support_ncu_full.csv 2>/dev/null
+python tools/ncu_summary.py $O/${R}_support_ncu_full.csv indel_support > $O/${R}_support_pack_ncu_summary.txt
+python tools/ncu_summary.py $O/${R}_realign_kernel_ncu_full.csv realign_kernel > $O/${R}_realign_kernel_ncu_summary.txt
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu --no-extra > /dev/null 2>&1
 python bench.py > $O/${R}_bench.json 2> $O/${R}_bench.err; tail -c 600 $O/${R}_bench.err
