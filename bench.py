@@ -603,7 +603,7 @@ def support_line(a, R, L, torch, dev_index, tasks, steps, warmup, cpu):
         tt = t["targets"][t["target_off"][k]:t["target_off"][k + 1]].tobytes()
         q = t["queries"][t["query_off"][k]:t["query_off"][k + 1]].tobytes()
         r = O.indel_support_dp(tt, q, cells=cc)
-        assert os.environ.get("INDELGPU_PACK_EXPERIMENT") or r == (int(out["subs"][k]), int(out["indels"][k]), int(out["aligned"][k])), k
+        assert r == (int(out["subs"][k]), int(out["indels"][k]), int(out["aligned"][k])), k
     dt = time.perf_counter() - t0
     cpu_obj = {"value": cc[0] / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port",
                "sample": f"first {ns} pairs through oracle/indel_oracle.c orc_indel_support_dp (results compared)"} if cpu else None

@@ -1062,7 +1062,13 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
     // Six work lists for the two wavefront kernels, each sorted by target length (counting sort): three classes by
     // target length (8, 16 or 32 lanes per pair) x query short enough for the 16-bit two-pass kernel
     // (indel_support_pack.cuh: every short read) or not (indel_support.cuh); the rest, one pair per thread.
-    static const bool no_pack = getenv("INDELGPU_SUPPORT_NOPACK") != nullptr;        // A/B measurements only
+    // Small batches (annotate mode scores the ~30 reads of one variant per call) stay on round 1's single-launch wavefront
+    // kernel: the two-pass kernels need a few thousand pairs to fill the GPU and win from ~6 000 pairs on (measured:
+    // 30 pairs 0.20 against 0.28 ms per call, 8 000 pairs 0.63 against 0.60 ms, 65 536 pairs 4.1 against 3.0 ms).
+    // INDELGPU_SUPPORT_PACK_MIN overrides the threshold (0: always two-pass); INDELGPU_SUPPORT_NOPACK=1: never.
+    const char* pm = getenv("INDELGPU_SUPPORT_PACK_MIN");
+    const int pack_min_pairs = pm ? atoi(pm) : 4096;
+    const bool no_pack = getenv("INDELGPU_SUPPORT_NOPACK") != nullptr || n < pack_min_pairs;
     const int pack_max_query = no_pack ? -1 : (int)kPackMaxQuery;
     std::vector<int32_t> slow;
     int max1 = 0, max2 = 0;
@@ -1106,7 +1112,7 @@ extern "C" int indelgpu_indel_support_batch(indelgpu_ctx* c, int32_t n, const ui
     CU(cudaEventRecord(c->ev_t0, st));
     // the 16-bit two-pass kernels: a wavefront pass that leaves two direction bits per cell in a scratch buffer, then
     // the walk back with one thread per pair.  A class is cut into launches whose scratch stays under ~2 GB.
-    static const int pack_shape = getenv("INDELGPU_PACK_SHAPE") ? atoi(getenv("INDELGPU_PACK_SHAPE")) : 1;   // experiments
+    const int pack_shape = getenv("INDELGPU_PACK_SHAPE") ? atoi(getenv("INDELGPU_PACK_SHAPE")) : 1;   // experiments
     WalkArgs walk;
     walk.njobs = 0; walk.first_block[0] = 0;
     for (int cls = 0; cls < 3; cls++) {

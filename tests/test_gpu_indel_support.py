@@ -2,12 +2,30 @@
 (variant.c:1246-1424), through indelgpu_indel_support_batch of the C ABI, against the reference's
 committed outputs (tests/golden/indel_support.tsv.gz) and against the oracle on seeded cases.
 Bit-exact: three integer counters per task."""
+import os
+
 import numpy as np
 import pytest
 
 from tests.util import indel_support_cases, load_indel_support_golden, make_rng, rseq
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["two-pass", "by-size"], autouse=True)
+def kernel_choice(request):
+    """every test runs twice: with the two-pass 16-bit kernels forced for any batch size, and with the library's own
+    choice (batches under 4 096 pairs take the single-launch wavefront kernel)"""
+    old = os.environ.get("INDELGPU_SUPPORT_PACK_MIN")
+    if request.param == "two-pass":
+        os.environ["INDELGPU_SUPPORT_PACK_MIN"] = "0"
+    else:
+        os.environ.pop("INDELGPU_SUPPORT_PACK_MIN", None)
+    yield request.param
+    if old is None:
+        os.environ.pop("INDELGPU_SUPPORT_PACK_MIN", None)
+    else:
+        os.environ["INDELGPU_SUPPORT_PACK_MIN"] = old
 
 
 @pytest.fixture(scope="module")
@@ -140,7 +158,7 @@ def test_scratch_ring_and_chunked_launches(gpu, oracle):
         Q.append(q.tobytes())
     R = gpu.Realigner()
     out = R.indel_support_batch(T, Q)
-    assert out["launches"] >= 7                              # wavefront launches of three classes, walks after every third
+    assert out["launches"] >= 7                              # wavefront launches of three classes, walks after every third (66 000 pairs: two-pass either way)
     for i in list(range(0, len(T), 1009)) + [len(T) - 1, len(T) - 2]:
         assert (out["subs"][i], out["indels"][i], out["aligned"][i]) == oracle.indel_support_dp(T[i], Q[i]), i
     again = R.indel_support_batch(T, Q)                       # same context, warm buffers: identical
