@@ -1005,6 +1005,16 @@ extern "C" int indelgpu_band_align_batch(indelgpu_ctx* c, int32_t n, const uint8
         band_tasks_kernel<<<blocks, 128, 0, st>>>(a);
         CU(cudaEventRecord(c->ev_t1, st));
         c->timed = true;
+    } else if (getenv("INDELGPU_ALIGN1_WARP") == nullptr) {
+        // bands of one diagonal, one alignment per thread (the warp-per-task kernel stays behind INDELGPU_ALIGN1_WARP=1)
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, align1_tasks_kernel, 128, 0));
+        if (occ < 1) return fail(INDELGPU_ELIMIT, "align kernel does not fit on an SM");
+        const int blocks = (int)std::min<long long>((long long)c->sms * occ, (n + 127) / 128);
+        CU(cudaEventRecord(c->ev_t0, st));
+        align1_tasks_kernel<<<blocks, 128, 0, st>>>(a);
+        CU(cudaEventRecord(c->ev_t1, st));
+        c->timed = true;
     } else {
         const SmemLayout L = make_layout(max_read, 0);
         if (L.total > c->max_smem_optin - 1024) return fail(INDELGPU_ELIMIT, "read too long for shared memory (%d bytes)", L.total);

@@ -136,6 +136,247 @@ align_tasks_kernel(const __grid_constant__ TaskArgs a)
     }
 }
 
+// The band of ONE diagonal, serial: what align_diag1 (kernels.cuh) computes with a warp, by one thread.  local_align with
+// low == up is a maximum-segment scan (SURVEY.md 8a'): the forward sweep keeps run = max(0, run + w) and its first strict
+// maximum, the reverse sweep walks down from the end row until the suffix sum reaches the optimum (localalign.c:100-176),
+// ALIGN takes its all-REP exit (globalalign.c:358-365) and fetch_cigar (:507-604) is the run-length code of the match
+// mask.  out9 as align_diag1's s_out; cig may be null (the operations are then only counted).
+// unaligned little-endian 32-bit read of bytes p[0..3] from two aligned words (the sequences of a batch are packed back
+// to back; the buffers are padded, so the word holding p[3] exists)
+__host__ __device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* p)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const unsigned sh = 8u * (unsigned)(a & 3);
+    const uint32_t lo = w[0];
+    if (sh == 0) return lo;
+    return (lo >> sh) | (w[1] << (32u - sh));
+}
+
+constexpr int kDiag1MaskWords = 5;                 // rows held as a match mask in registers: 160
+
+__host__ __device__ inline void align_diag1_serial(const DevParams& P, const uint8_t* __restrict__ read, int M,
+                                                   const uint8_t* __restrict__ win, int N, int d, uint32_t* cig, int cig_cap, int* out9)
+{
+    const int si = d < 0 ? -d : 0, ei = M < N - d ? M : N - d;                 // localalign.c:86-87
+    const uint8_t* w0 = win + d;                                                // row i compares read[i-1] with w0[i-1]
+    const int rows = ei - si;
+    int best = 0, endi = si, starti = 0;
+    uint32_t mask[kDiag1MaskWords];                                             // bit t: row si + 1 + t matches
+    const bool small = rows <= 32 * kDiag1MaskWords;
+    if (small) {
+        // one pass over memory, four rows per step; everything after it works on the mask
+#pragma unroll
+        for (int k = 0; k < kDiag1MaskWords; k++) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int t = 32 * k + 4 * q;
+                if (t < rows) {
+                    const uint32_t x = load_u32_unaligned(read + si + t) ^ load_u32_unaligned(w0 + si + t);
+                    uint32_t nib = 0;
+                    if ((x & 0x000000FFu) == 0u) nib |= 1u;
+                    if ((x & 0x0000FF00u) == 0u) nib |= 2u;
+                    if ((x & 0x00FF0000u) == 0u) nib |= 4u;
+                    if ((x & 0xFF000000u) == 0u) nib |= 8u;
+                    m |= nib << (4 * q);
+                }
+            }
+            const int left = rows - 32 * k;                                     // rows past the end match nothing
+            mask[k] = left >= 32 ? m : (left <= 0 ? 0u : (m & ((1u << left) - 1u)));
+        }
+        int run = 0;
+#pragma unroll
+        for (int k = 0; k < kDiag1MaskWords; k++) {
+            const uint32_t m = mask[k];
+            const int nb = rows - 32 * k < 32 ? rows - 32 * k : 32;
+            for (int b = 0; b < nb; b++) {
+                run += ((m >> b) & 1u) ? P.match : P.mismatch;
+                if (run < 0) run = 0;
+                if (run > best) { best = run; endi = si + 32 * k + b + 1; }   // strict: the first maximum
+            }
+        }
+        if (best > 0) {
+            int s = 0;
+            const int tend = endi - 1 - si;                                     // bit of the end row
+            bool found = false;
+#pragma unroll
+            for (int k = kDiag1MaskWords - 1; k >= 0; k--) {
+                if (!found && k <= (tend >> 5)) {
+                    const uint32_t m = mask[k];
+                    for (int b = (k == (tend >> 5)) ? (tend & 31) : 31; b >= 0; b--) {
+                        s += ((m >> b) & 1u) ? P.match : P.mismatch;
+                        if (s == best) { starti = si + 32 * k + b + 1; found = true; break; }
+                    }
+                }
+            }
+        }
+    } else {
+        int run = 0;
+        for (int i = si + 1; i <= ei; i++) {
+            run += (read[i - 1] == w0[i - 1]) ? P.match : P.mismatch;
+            if (run < 0) run = 0;
+            if (run > best) { best = run; endi = i; }
+        }
+        if (best > 0) {
+            int s = 0;
+            for (int i = endi; i > si; i--) {
+                s += (read[i - 1] == w0[i - 1]) ? P.match : P.mismatch;
+                if (s == best) { starti = i; break; }
+            }
+        }
+    }
+    const bool none = best <= 0 || starti == 0 || endi == starti;              // localalign.c:191-193
+    int n = 0;
+    if (!none) {
+        if (starti - 1 > 0) { if (cig && n < cig_cap) cig[n] = ((uint32_t)(starti - 1) << 4) | OP_SOFT; n++; }
+        if (small) {
+            // runs of equal bits of the mask between the start and the end row, a word at a time
+            const int tlast = endi - 1 - si;
+            int t = starti - 1 - si;
+            while (t <= tlast) {
+                uint32_t m = mask[0];
+#pragma unroll
+                for (int k = 1; k < kDiag1MaskWords; k++) if ((t >> 5) == k) m = mask[k];
+                const bool eq = ((m >> (t & 31)) & 1u) != 0u;
+                int q = t;                                                      // first position after the run
+                for (;;) {
+                    uint32_t mq = mask[0];
+#pragma unroll
+                    for (int k = 1; k < kDiag1MaskWords; k++) if ((q >> 5) == k) mq = mask[k];
+                    const uint32_t diff = (eq ? ~mq : mq) >> (q & 31);          // 1 where the run is broken
+                    if (diff) {
+#ifdef __CUDA_ARCH__
+                        q += __ffs((int)diff) - 1;
+#else
+                        q += __builtin_ctz(diff);
+#endif
+                        break;
+                    }
+                    q += 32 - (q & 31);
+                    if (q > tlast) break;
+                }
+                if (q > tlast + 1) q = tlast + 1;
+                if (cig && n < cig_cap) cig[n] = ((uint32_t)(q - t) << 4) | (eq ? OP_EQ : OP_X);
+                n++;
+                t = q;
+            }
+        } else {
+            int i = starti;
+            while (i <= endi) {
+                const bool eq = read[i - 1] == w0[i - 1];
+                int q = i + 1;
+                while (q <= endi && (read[q - 1] == w0[q - 1]) == eq) q++;
+                if (cig && n < cig_cap) cig[n] = ((uint32_t)(q - i) << 4) | (eq ? OP_EQ : OP_X);
+                n++;
+                i = q;
+            }
+        }
+        if (M - endi > 0) { if (cig && n < cig_cap) cig[n] = ((uint32_t)(M - endi) << 4) | OP_SOFT; n++; }
+    }
+    out9[0] = none ? 0 : best;
+    out9[1] = none ? 0 : starti;         // q1 (1-based inclusive)
+    out9[2] = none ? 0 : starti + d;     // r1
+    out9[3] = none ? 0 : endi;           // q2
+    out9[4] = none ? 0 : endi + d;       // r2
+    out9[5] = n;
+    out9[6] = ei - si;                                   // forward cells
+    out9[7] = best > 0 ? endi - starti + 1 : 0;          // reverse cells until the hit
+    out9[8] = 0;                                         // ALIGN exits before any sweep (band <= 1)
+}
+
+#ifdef __CUDACC__
+// local_align + ALIGN + fetch_cigar over n tasks with bands of ONE diagonal, one THREAD per task: the warp-per-task kernel
+// above spends two scans and a serial CIGAR loop of lane 0 on 150 rows; 32 independent tasks per warp do the same work
+// with every lane busy.  A thread reading its own task's bytes would make every load of the warp touch 32 cache lines
+// (measured: 0.77 ms per 2^20 tasks, bound by the load unit), so the warp first copies the rows each of its 32 tasks
+// needs -- M bytes of the read, M bytes along the window's diagonal -- into shared memory with coalesced loads, one
+// task after the other, and every lane then works on its own row of that tile (stride 41 words: conflict-free).
+constexpr int kAlign1RowWords = 41;               // 160 rows + 3 bytes of misalignment, rounded up; odd
+__global__ void __launch_bounds__(128)
+align1_tasks_kernel(const __grid_constant__ TaskArgs a)
+{
+    __shared__ uint32_t s_stage[4][2][32 * kAlign1RowWords];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* const sr = s_stage[warp][0];
+    uint32_t* const sw = s_stage[warp][1];
+    unsigned long long cf = 0, cr = 0;
+    const long long gwarp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long base = gwarp * 32; base < a.n; base += nwarps * 32) {
+        const long long idx = base + lane;
+        const bool have = idx < a.n;
+        int64_t roff = 0, woff = 0; int M = 0, N = 0, lo = 0, rows = 0, si = 0;
+        bool valid = false;
+        if (have) {
+            roff = a.read_off[idx]; woff = a.ref_off[idx];
+            M = (int)(a.read_off[idx + 1] - roff); N = (int)(a.ref_off[idx + 1] - woff);
+            lo = max(-M, a.low[idx]);
+            const int hi = min(N, a.up[idx]);                            // localalign.c:70-71
+            valid = !(M <= 0 || N <= 0 || M > a.max_read || hi - lo + 1 != 1);
+            si = lo < 0 ? -lo : 0;
+            rows = min(M, N - lo) - si;
+        }
+        const bool fast = valid && rows > 0 && rows <= 32 * kDiag1MaskWords;
+        const uint8_t* rsrc = a.reads + roff + si;                       // first byte of the rows this task compares
+        const uint8_t* wsrc = a.refs + woff + lo + si;
+        // stage: task q's bytes, whole aligned words, by all lanes
+#pragma unroll 4
+        for (int q = 0; q < 32; q++) {                                  // unrolled: the loads of four tasks are in flight together
+            const bool fq = __shfl_sync(FULL, (int)fast, q) != 0;
+            const unsigned long long rq = __shfl_sync(FULL, (unsigned long long)reinterpret_cast<uintptr_t>(rsrc), q);
+            const unsigned long long wq = __shfl_sync(FULL, (unsigned long long)reinterpret_cast<uintptr_t>(wsrc), q);
+            const int nrow = __shfl_sync(FULL, rows, q);
+            const uint32_t* rb = reinterpret_cast<const uint32_t*>(rq & ~3ull);
+            const uint32_t* wb = reinterpret_cast<const uint32_t*>(wq & ~3ull);
+            const int nr = min((nrow + (int)(rq & 3) + 3) / 4 + 1, (int)kAlign1RowWords);     // + 1: the word an unaligned read runs into
+            const int nw = min((nrow + (int)(wq & 3) + 3) / 4 + 1, (int)kAlign1RowWords);
+            uint32_t r0 = 0, r1 = 0, w0v = 0, w1v = 0;
+            if (fq) {
+                if (lane < nr) r0 = __ldg(rb + lane);
+                if (lane + 32 < nr) r1 = __ldg(rb + lane + 32);
+                if (lane < nw) w0v = __ldg(wb + lane);
+                if (lane + 32 < nw) w1v = __ldg(wb + lane + 32);
+                if (lane < nr) sr[q * kAlign1RowWords + lane] = r0;
+                if (lane + 32 < nr) sr[q * kAlign1RowWords + lane + 32] = r1;
+                if (lane < nw) sw[q * kAlign1RowWords + lane] = w0v;
+                if (lane + 32 < nw) sw[q * kAlign1RowWords + lane + 32] = w1v;
+            }
+        }
+        __syncwarp();
+        if (have) {
+            if (!valid) {
+                a.score[idx] = 0; a.ncigar[idx] = 0; for (int t = 0; t < 4; t++) a.ends[4 * idx + t] = 0; atomicExch(a.error_flag, 1);
+            } else {
+                // pointers with which read[si + t] and (win + lo)[si + t] land on the staged bytes
+                const uint8_t* rp = a.reads + roff; const uint8_t* wp = a.refs + woff;
+                if (fast) {
+                    rp = reinterpret_cast<const uint8_t*>(sr + lane * kAlign1RowWords) + (reinterpret_cast<uintptr_t>(rsrc) & 3) - si;
+                    wp = reinterpret_cast<const uint8_t*>(sw + lane * kAlign1RowWords) + (reinterpret_cast<uintptr_t>(wsrc) & 3) - lo - si;
+                }
+                int out[9];
+                align_diag1_serial(a.P, rp, M, wp, N, lo, a.cigar ? a.cigar + idx * a.cigar_stride : nullptr, a.cigar_stride, out);
+                const int score = out[0];
+                a.score[idx] = score;
+                for (int t = 0; t < 4; t++) a.ends[4 * idx + t] = score > 0 ? out[1 + t] : 0;   // q1 r1 q2 r2
+                a.ncigar[idx] = score > 0 ? out[5] : 0;
+                cf += (unsigned long long)out[6]; cr += (unsigned long long)out[7];
+                if (score > 0 && a.script) {
+                    int32_t* so = a.script + idx * a.script_stride;
+                    const int len = out[3] - out[1] + 1;                             // all-REP script (globalalign.c:358-365)
+                    for (int t = 0; t < min(len, a.script_stride); t++) so[t] = 0;
+                    if (len < a.script_stride) so[len] = 0x7FFFFFFF;
+                }
+            }
+        }
+        __syncwarp();                                                    // the next group overwrites the tile
+    }
+    for (int o = 16; o > 0; o >>= 1) { cf += __shfl_xor_sync(FULL, cf, o); cr += __shfl_xor_sync(FULL, cr, o); }
+    if (lane == 0 && (cf | cr)) { atomicAdd(a.cell_totals + 0, cf); atomicAdd(a.cell_totals + 1, cr); }
+}
+#endif
+
 // local_align + ALIGN + fetch_cigar over n tasks, ONE THREAD PER TASK (inter-task parallelism).
 // At the band widths the caller produces (numgaps + 1 diagonals, typically <= 17) one anti-diagonal
 // of a band holds at most band/2 independent cells, so a wavefront inside one alignment would leave

@@ -1,6 +1,7 @@
 // TEST ONLY: runs the serial (one-thread) pieces of the device source on the host so that the
 // divide-and-conquer control flow can be checked against the oracle without a GPU.  The library
 // itself never executes these functions on the CPU.
+#include <cstring>
 #include <vector>
 
 #include "../../indelminer_b200/csrc/kernels.cuh"
@@ -116,4 +117,26 @@ extern "C" int hh_support_pack(int SEG, const uint8_t* t1a, int len1a, const uin
         default: PACK(16);
     }
 #undef PACK
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the serial one-diagonal alignment of align1_tasks_kernel (task_kernels.cuh)
+// ---------------------------------------------------------------------------------------------------
+#include "../../indelminer_b200/csrc/task_kernels.cuh"
+
+extern "C" int hh_diag1(const int* prm, const uint8_t* read, int M, const uint8_t* win, int N, int low, int up, int* out9,
+                        uint32_t* cig, int cig_cap)
+{
+    DevParams P;
+    P.k = prm[0]; P.g = prm[1]; P.maxdel = prm[2]; P.ethr = prm[3];
+    P.match = prm[4]; P.mismatch = prm[5]; P.G = prm[6]; P.H = prm[7]; P.kmask = 0;
+    const int lo = low > -M ? low : -M, hi = up < N ? up : N;
+    if (hi - lo + 1 != 1) return -1;
+    // padded copies at every byte alignment (the kernel reads whole words around the rows it needs; device buffers are padded)
+    std::vector<uint32_t> rb((size_t)M / 4 + 16, 0xA5A5A5A5u), wb((size_t)N / 4 + 16, 0x5A5A5A5Au);
+    uint8_t* r = reinterpret_cast<uint8_t*>(rb.data()) + 4 + (M % 4);
+    uint8_t* w = reinterpret_cast<uint8_t*>(wb.data()) + 4 + ((N + M) % 4);
+    memcpy(r, read, (size_t)M); memcpy(w, win, (size_t)N);
+    align_diag1_serial(P, r, M, w, N, lo, cig, cig_cap, out9);
+    return 0;
 }

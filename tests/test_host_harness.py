@@ -17,7 +17,7 @@ SO = os.path.join(HERE, "host_harness", "libharness.so")
 
 @pytest.fixture(scope="module")
 def harness():
-    deps = [SRC] + [os.path.join(HERE, "..", "indelminer_b200", "csrc", f) for f in ("kernels.cuh", "band_dp.cuh")]
+    deps = [SRC] + [os.path.join(HERE, "..", "indelminer_b200", "csrc", f) for f in ("kernels.cuh", "band_dp.cuh", "indel_support.cuh", "indel_support_pack.cuh", "task_kernels.cuh", "warp_vote.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
                                "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO, SRC])
@@ -161,7 +161,7 @@ def test_unique_diagonal_shortcut_is_exact_under_other_scorings(harness, oracle,
 
 
 def _harness_support():
-    deps = [SRC] + [os.path.join(HERE, "..", "indelminer_b200", "csrc", f) for f in ("kernels.cuh", "band_dp.cuh", "indel_support.cuh", "indel_support_pack.cuh")]
+    deps = [SRC] + [os.path.join(HERE, "..", "indelminer_b200", "csrc", f) for f in ("kernels.cuh", "band_dp.cuh", "indel_support.cuh", "indel_support_pack.cuh", "task_kernels.cuh", "warp_vote.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
                                "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO, SRC])
@@ -203,3 +203,46 @@ def test_packed_support_check_matches_oracle(oracle):
             assert tuple(out[3:6]) == want[(k * 7 + 3) % len(pairs)], (k, seg, rc, "B")
             n += 1
     assert n > 4000
+
+
+def test_serial_one_diagonal_alignment_matches_oracle(oracle):
+    """align_diag1_serial (the thread-per-task kernel of one-diagonal bands): score, end points, cell counts and CIGAR
+    against the oracle's local_align / attempt_band_alignment with low == up, under several scorings"""
+    L = _harness_support()
+    L.hh_diag1.restype = C.c_int
+    rng = make_rng(606)
+    n = npos = 0
+    for it in range(6000):
+        prm = rng.choice([(6, 0, 1000, 10, 1, -10, 10, 10), (6, 0, 1000, 10, 2, -1, 4, 1), (6, 0, 1000, 10, 5, -4, 0, 0), (6, 0, 1000, 10, 1, -1, 1, 1)])
+        p = oracle.default_params()
+        p.match, p.mismatch, p.gapopen, p.gapextend = prm[4], prm[5], prm[6], prm[7]
+        alpha = rng.choice(["AC", "ACGT", "ACGTN", "A"])
+        N = rng.randrange(1, 400)
+        ref = rseq(rng, N, alpha)
+        M = rng.randrange(1, 160) if it % 5 else rng.randrange(150, 390)       # more than 160 rows: the loop without the register mask
+        if rng.random() < 0.8 and N > M + 2:
+            off = rng.randrange(0, N - M)
+            read = mutate(rng, ref[off:off + M], alpha, sub=rng.choice([0, 0.02, 0.1, 0.4]), nindel=0)
+            d = off + rng.randrange(-1, 2)
+        else:
+            read = rseq(rng, M, alpha)
+            d = rng.randrange(-M - 2, N + 2)
+        M = len(read)
+        low = up = d
+        if min(N, up) - max(-M, low) + 1 != 1:
+            continue
+        cells = oracle.Cells()
+        score, ends, _script = oracle.local_align(p, read, ref, low, up, cells=cells)
+        out = (C.c_int * 9)()
+        cig = (C.c_uint32 * (M + 8))()
+        assert L.hh_diag1((C.c_int * 8)(*prm), read.encode(), M, ref.encode(), N, low, up, out, cig, M + 8) == 0
+        ctx = (prm, read, ref, d)
+        assert out[0] == score, ctx
+        assert (out[6], out[7], out[8]) == (cells.fwd, cells.rev, cells.glob), ctx
+        n += 1
+        if score > 0:
+            npos += 1
+            assert tuple(out[1:5]) == ends, ctx
+            (_c, exp_cig, _s) = oracle.attempt_band_alignment(p, ref, 0, N, read, 0, M, low, up)
+            assert list(cig[:out[5]]) == exp_cig, ctx
+    assert npos > n // 3 and n > 3000
