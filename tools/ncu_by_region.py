@@ -10,8 +10,8 @@ def find(txt, src=wv):
     for i,l in enumerate(src,1):
         if txt in l: return i
     return 10**9
-m1=find("// 1. index the k-mers"); m2=find("// 2. scan the window"); mB=find("const int mine = __popc(hits);"); mC=find("// pass C: full chunks"); m3=find("// 3. bin_bands"); m4=find("// 4. leave the table")
-lk=find("__device__ __forceinline__ uint32_t kmer_lookup"); pk=find("__device__ __forceinline__ void pack_read_warp"); ka=find("__device__ __forceinline__ uint32_t kmer_at"); ts=find("__device__ __forceinline__ void tab_store")
+m1=find("// 1. index the k-mers"); m2=find("// 2. scan the window"); mB=find("const int mine = __popc(take);"); mC=find("// pass C: full chunks"); m3=find("// 3. bin_bands"); m4=find("// 4. leave the table")
+lk=find("__device__ __forceinline__ uint32_t kmer_lookup"); pk=find("__device__ __forceinline__ void pack_read_warp"); ka=find("__device__ __forceinline__ uint32_t kmer_at"); ts=find("__device__ __forceinline__ void tab_store"); vh=find("__device__ __forceinline__ void vote_hits_chunk"); sb=find("__device__ __forceinline__ int select_band_warp")
 kc = lines_of("kernels.cuh")
 d1=find("__device__ void align_diag1", kc); cm=find("__device__ int count_matches", kc); st=find("__device__ int stitch_segments", kc)
 inst=collections.Counter(); samp=collections.Counter(); thr=collections.Counter()
@@ -26,6 +26,8 @@ for l in out[2:]:
         elif ln>=mB: r="vote: pass B (append hits)"
         elif ln>=m2: r="vote: pass A (lookups)"
         elif ln>=m1: r="vote: table build"
+        elif ln>=sb: r="vote: select_band_warp"
+        elif ln>=vh: r="vote: pass C (vote_hits_chunk: merge + atomics)"
         elif ln>=ts: r="vote: tab_store"
         elif ln>=lk: r="vote: kmer_lookup (A+B)"
         elif ln>=ka: r="vote: kmer_at"
