@@ -90,6 +90,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self, wait_s=3.0):
+        """call right before the timed region: the sampler was started earlier (nvidia-smi needs a few hundred ms before
+        its first line, more than a short timed region lasts), only the lines from here on are the region's"""
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < wait_s:
+            time.sleep(0.01)
+        self.first = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -100,7 +108,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        first = getattr(self, "first", 0)
+        lines = self.lines[first:] or self.lines[-1:]          # a region shorter than the sampling period: the line just before it
+        for ln in lines:
             t = [x.strip() for x in ln.split(",")]
             if len(t) < 9:
                 continue
@@ -307,12 +317,13 @@ def run_ours(a, rank, world, local_rank):
         if rc != 0:
             raise RuntimeError(_lib.last_error())
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(a.warmup):
         flush.fill_(1)
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     evs = []
     launches = 0
     for _ in range(a.steps):
@@ -501,9 +512,10 @@ def band_sweep(a, R, L, torch, dev_index):
     for band in (1, 5, 9, 17, 33, 65, 129):
         low = (t["true_off"] - band // 2).astype(np.int32)
         up = (low + band - 1).astype(np.int32)
-        R.band_align_batch(None, None, low, up, packed=packed, want_cigar=False)          # warm-up
         sampler = ClockSampler(dev_index)
         sampler.start()
+        R.band_align_batch(None, None, low, up, packed=packed, want_cigar=False)          # warm-up
+        sampler.mark()
         kms, launches = [], 0
         for _ in range(3):
             res = R.band_align_batch(None, None, low, up, packed=packed, want_cigar=False)
@@ -532,11 +544,12 @@ def run_band(a, R, L, torch, dev, peak, peak_src, dev_index=0):
     gops = C.c_double(0)
     if L.indelgpu_int32_peak(R._ctx, C.byref(gops)) != 0:
         raise RuntimeError(_liberr())
+    sampler = ClockSampler(dev_index)
+    sampler.start()
     for _ in range(a.warmup):
         out = R.band_align_batch(None, None, t["low"], t["up"], packed=packed, want_cigar=False)
     torch.cuda.synchronize()
-    sampler = ClockSampler(dev_index)
-    sampler.start()
+    sampler.mark()
     kms, wall = [], []
     for _ in range(a.steps):
         t0 = time.perf_counter()
@@ -579,11 +592,12 @@ def support_line(a, R, L, torch, dev_index, tasks, steps, warmup, cpu):
     gops = C.c_double(0)
     if L.indelgpu_int32_peak(R._ctx, C.byref(gops)) != 0:
         raise RuntimeError(_liberr())
+    sampler = ClockSampler(dev_index)
+    sampler.start()
     for _ in range(warmup):
         out = R.indel_support_batch(None, None, packed=packed, out=outbuf)
     torch.cuda.synchronize()
-    sampler = ClockSampler(dev_index)
-    sampler.start()
+    sampler.mark()
     kms, wall, launches = [], [], 0
     for _ in range(steps):
         t0 = time.perf_counter()
